@@ -1,0 +1,265 @@
+// Tree attention for the draft/verify forward (reference: the 4-D additive mask built at
+// code/beamSD.py:87-91,203-211,396-400 and consumed by transformers' LlamaAttention).
+//
+// The reference lays all beams of all levels along the sequence axis and hands the model a dense
+// [T, S] fp32 mask.  Here a token's visibility is (a) a causal prefix length over the prompt slots and
+// (b) a 512-bit mask over the accepted/tree slots that follow the prompt -- a few words per token,
+// produced on the device by the beam kernels (beam.cu), never a dense mask.
+//
+// One CTA = 64 queries of one head (4 warps x 16 rows), keys streamed in tiles of 64 through shared
+// memory, flash-style online softmax in fp32.  QK^T and PV run on the legacy warp-level tensor-core
+// path (mma.sync m16n8k16 bf16); P is split into hi+lo bf16 parts so the PV product is accurate to
+// ~2^-16, which keeps this kernel within fp32-softmax tolerance of oracle/llama_ref.py.  The kernel
+// is <5% of a 7B forward at T<=300 (the GEMMs in gemm.cu dominate); a tcgen05 version is listed as
+// next work in DESIGN.md.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace atspeed {
+
+static constexpr int ATT_BQ = 64;   // queries per CTA
+static constexpr int ATT_BK = 64;   // keys per tile
+static constexpr int ATT_THREADS = 128;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 64-bit visibility window for keys [key0, key0+64) of one query row
+__device__ __forceinline__ uint64_t vis_window(const uint32_t* vrow, int key0, int vis_base) {
+    uint64_t out = 0;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int b = key0 + 32 * w - vis_base;   // bit index of this word's first key
+        uint32_t word = 0;
+        if (b >= 0) {
+            const int i = b >> 5, sh = b & 31;
+            const uint32_t lo = i < VIS_WORDS ? vrow[i] : 0u;
+            const uint32_t hi = (i + 1) < VIS_WORDS ? vrow[i + 1] : 0u;
+            word = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+        } else if (b > -32) {
+            word = vrow[0] << (-b);
+        }
+        out |= static_cast<uint64_t>(word) << (32 * w);
+    }
+    return out;
+}
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS)
+tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                      const __nv_bfloat16* __restrict__ vcache, const int* __restrict__ prefix_len,
+                      const uint32_t* __restrict__ vis, int vis_base, int T, int S, int n_heads, float scale,
+                      __nv_bfloat16* __restrict__ out) {
+    constexpr int LDS = D + 8;                     // padded row (bf16 elements): conflict-free fragment loads
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
+    __nv_bfloat16* sK = sQ + ATT_BQ * LDS;
+    __nv_bfloat16* sV = sK + ATT_BK * LDS;
+    __shared__ uint32_t sVis[ATT_BQ * VIS_WORDS];
+    __shared__ int sPl[ATT_BQ];
+    __shared__ int sMaxPl;
+    __shared__ uint32_t sAny[VIS_WORDS];
+
+    const int head = blockIdx.y, q0 = blockIdx.x * ATT_BQ;
+    const int HD = n_heads * D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+
+    if (threadIdx.x == 0) sMaxPl = 0;
+    if (threadIdx.x < VIS_WORDS) sAny[threadIdx.x] = 0;
+    __syncthreads();
+    // stage Q tile, prefix lengths and visibility words
+    for (int i = threadIdx.x; i < ATT_BQ * (D / 8); i += ATT_THREADS) {
+        const int r = i / (D / 8), c = (i % (D / 8)) * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q0 + r < T) v = *reinterpret_cast<const uint4*>(q + static_cast<long long>(q0 + r) * HD + head * D + c);
+        *reinterpret_cast<uint4*>(&sQ[r * LDS + c]) = v;
+    }
+    for (int i = threadIdx.x; i < ATT_BQ; i += ATT_THREADS) {
+        const int pl = (q0 + i < T) ? prefix_len[q0 + i] : 0;
+        sPl[i] = pl;
+        atomicMax(&sMaxPl, pl);
+    }
+    for (int i = threadIdx.x; i < ATT_BQ * VIS_WORDS; i += ATT_THREADS) {
+        const int r = i / VIS_WORDS, w = i % VIS_WORDS;
+        const uint32_t v = (q0 + r < T) ? vis[static_cast<long long>(q0 + r) * VIS_WORDS + w] : 0u;
+        sVis[i] = v;
+        if (v) atomicOr(&sAny[w], v);
+    }
+    __syncthreads();
+
+    const int r0 = warp * 16 + g, r1 = r0 + 8;         // the two query rows this thread owns
+    const int pl0 = sPl[r0], pl1 = sPl[r1];
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+
+    const int max_pl = sMaxPl;
+    for (int key0 = 0; key0 < S; key0 += ATT_BK) {
+        // skip tiles no query of this CTA can see (block-uniform decision)
+        bool need = key0 < max_pl;
+        if (!need && key0 + ATT_BK > vis_base) {
+            const int b0 = key0 - vis_base, b1 = b0 + ATT_BK - 1;
+            for (int w = (b0 < 0 ? 0 : b0 >> 5); w <= (b1 >> 5) && w < VIS_WORDS; ++w) need |= sAny[w] != 0;
+        }
+        if (!need) continue;
+        __syncthreads();   // previous tile fully consumed
+        for (int i = threadIdx.x; i < ATT_BK * (D / 8); i += ATT_THREADS) {
+            const int r = i / (D / 8), c = (i % (D / 8)) * 8;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (key0 + r < S) {
+                const long long off = static_cast<long long>(key0 + r) * HD + head * D + c;
+                kv = *reinterpret_cast<const uint4*>(kcache + off);
+                vv = *reinterpret_cast<const uint4*>(vcache + off);
+            }
+            *reinterpret_cast<uint4*>(&sK[r * LDS + c]) = kv;
+            *reinterpret_cast<uint4*>(&sV[r * LDS + c]) = vv;
+        }
+        __syncthreads();
+
+        // ---- S = Q K^T for this warp's 16 rows x 64 keys ----
+        float s[ATT_BK / 8][4];
+#pragma unroll
+        for (int nb = 0; nb < ATT_BK / 8; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+            const __nv_bfloat16* qa = &sQ[(warp * 16 + g) * LDS + kk * 16 + 2 * t4];
+            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(qa);
+            const uint32_t a1 = *reinterpret_cast<const uint32_t*>(qa + 8 * LDS);
+            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(qa + 8);
+            const uint32_t a3 = *reinterpret_cast<const uint32_t*>(qa + 8 * LDS + 8);
+#pragma unroll
+            for (int nb = 0; nb < ATT_BK / 8; ++nb) {
+                const __nv_bfloat16* kb = &sK[(nb * 8 + g) * LDS + kk * 16 + 2 * t4];
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kb);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kb + 8);
+                mma_bf16_16816(s[nb], a0, a1, a2, a3, b0, b1);
+            }
+        }
+        // ---- mask + online softmax ----
+        const uint64_t win0 = vis_window(&sVis[r0 * VIS_WORDS], key0, vis_base);
+        const uint64_t win1 = vis_window(&sVis[r1 * VIS_WORDS], key0, vis_base);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < ATT_BK / 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = nb * 8 + 2 * t4 + e, key = key0 + c;
+                const bool v0 = key < S && (key < pl0 || ((win0 >> c) & 1ull));
+                const bool v1 = key < S && (key < pl1 || ((win1 >> c) & 1ull));
+                s[nb][e] = v0 ? s[nb][e] * scale : -INFINITY;
+                s[nb][2 + e] = v1 ? s[nb][2 + e] * scale : -INFINITY;
+                mx0 = fmaxf(mx0, s[nb][e]);
+                mx1 = fmaxf(mx1, s[nb][2 + e]);
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float ref0 = mn0 == -INFINITY ? 0.f : mn0, ref1 = mn1 == -INFINITY ? 0.f : mn1;
+        const float corr0 = m0 == -INFINITY ? 0.f : expf(m0 - ref0), corr1 = m1 == -INFINITY ? 0.f : expf(m1 - ref1);
+        m0 = mn0; m1 = mn1;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < ATT_BK / 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                s[nb][e] = expf(s[nb][e] - ref0);          // exp(-inf) = 0 for masked keys
+                s[nb][2 + e] = expf(s[nb][2 + e] - ref1);
+                rs0 += s[nb][e];
+                rs1 += s[nb][2 + e];
+            }
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        l0 = l0 * corr0 + rs0;
+        l1 = l1 * corr1 + rs1;
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) { o[i][0] *= corr0; o[i][1] *= corr0; o[i][2] *= corr1; o[i][3] *= corr1; }
+
+        // ---- O += P V, P = hi + lo (two bf16 parts) ----
+#pragma unroll
+        for (int kk = 0; kk < ATT_BK / 16; ++kk) {
+            // S accumulator layout of n-blocks 2kk, 2kk+1 == A fragment layout of a 16x16 tile
+            float ph[8], plo[8];
+            const float src[8] = {s[2 * kk][0], s[2 * kk][1], s[2 * kk][2], s[2 * kk][3],
+                                  s[2 * kk + 1][0], s[2 * kk + 1][1], s[2 * kk + 1][2], s[2 * kk + 1][3]};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ph[i] = bf16_round(src[i]); plo[i] = src[i] - ph[i]; }
+            const uint32_t ah0 = pack_bf16(ph[0], ph[1]), ah1 = pack_bf16(ph[2], ph[3]);
+            const uint32_t ah2 = pack_bf16(ph[4], ph[5]), ah3 = pack_bf16(ph[6], ph[7]);
+            const uint32_t al0 = pack_bf16(plo[0], plo[1]), al1 = pack_bf16(plo[2], plo[3]);
+            const uint32_t al2 = pack_bf16(plo[4], plo[5]), al3 = pack_bf16(plo[6], plo[7]);
+#pragma unroll
+            for (int nb = 0; nb < D / 8; ++nb) {
+                // B[k = key][n = d]: pairs of consecutive keys for one d
+                const __nv_bfloat16* vb = &sV[(kk * 16 + 2 * t4) * LDS + nb * 8 + g];
+                __nv_bfloat162 p0, p1;
+                p0.x = vb[0];           p0.y = vb[LDS];
+                p1.x = vb[8 * LDS];     p1.y = vb[9 * LDS];
+                const uint32_t b0 = *reinterpret_cast<uint32_t*>(&p0), b1 = *reinterpret_cast<uint32_t*>(&p1);
+                mma_bf16_16816(o[nb], ah0, ah1, ah2, ah3, b0, b1);
+                mma_bf16_16816(o[nb], al0, al1, al2, al3, b0, b1);
+            }
+        }
+    }
+    // ---- normalise and store (bf16) ----
+    const float inv0 = l0 > 0.f ? 1.0f / l0 : 0.f, inv1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+    const int tq0 = q0 + r0, tq1 = q0 + r1;
+#pragma unroll
+    for (int nb = 0; nb < D / 8; ++nb) {
+        const int c = head * D + nb * 8 + 2 * t4;
+        if (tq0 < T)
+            *reinterpret_cast<uint32_t*>(out + static_cast<long long>(tq0) * HD + c) =
+                pack_bf16(o[nb][0] * inv0, o[nb][1] * inv0);
+        if (tq1 < T)
+            *reinterpret_cast<uint32_t*>(out + static_cast<long long>(tq1) * HD + c) =
+                pack_bf16(o[nb][2] * inv1, o[nb][3] * inv1);
+    }
+}
+
+int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
+                   const BatchDesc& b, int T, int S, int n_heads, int head_dim, __nv_bfloat16* out, cudaStream_t st) {
+    ATS_CHECK_ARG(T >= 1 && S >= 1, "attention: T=%d S=%d", T, S);
+    dim3 grid((T + ATT_BQ - 1) / ATT_BQ, n_heads);
+    const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
+    const size_t smem = static_cast<size_t>(ATT_BQ + 2 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
+#define ATS_ATT(DD)                                                                                              \
+    do {                                                                                                         \
+        static bool attr_set = false;                                                                            \
+        if (!attr_set) {                                                                                         \
+            ATS_CUDA(cudaFuncSetAttribute(tree_attention_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          64 * 1024));                                                           \
+            attr_set = true;                                                                                     \
+        }                                                                                                        \
+        tree_attention_kernel<DD><<<grid, ATT_THREADS, smem, st>>>(q, kcache, vcache, b.prefix_len, b.vis,       \
+                                                                   b.vis_base, T, S, n_heads, scale, out);      \
+    } while (0)
+    switch (head_dim) {
+        case 16: ATS_ATT(16); break;
+        case 32: ATS_ATT(32); break;
+        case 64: ATS_ATT(64); break;
+        case 128: ATS_ATT(128); break;
+        default:
+            set_error("attention: head_dim=%d not in {16,32,64,128}", head_dim);
+            return ATS_ERR_ARG;
+    }
+#undef ATS_ATT
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
+}
+
+}  // namespace atspeed

@@ -1,0 +1,80 @@
+// Device-resident beam-tree state shared by beam.cu (kernels) and engine.cu (orchestration).
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace atspeed {
+
+// Per-user search state, all in HBM.  Levels: 0 = the round's root beams, 1.. = tokens proposed at each
+// step.  A level entry is a beam (token, parent index in the previous level, cumulative score, trie
+// node, KV slot, generated suffix, visibility mask over the accepted + tree KV slots).
+struct TreeDev {
+    int* cnt;          // [MAX_LEVELS]
+    int* tok;          // [MAX_LEVELS][MAX_BEAMS]
+    int* parent;       // [MAX_LEVELS][MAX_BEAMS]
+    int* node;         // [MAX_LEVELS][MAX_BEAMS]
+    int* slot;         // [MAX_LEVELS][MAX_BEAMS]
+    float* score;      // [MAX_LEVELS][MAX_BEAMS]
+    int* gen;          // [MAX_LEVELS][MAX_BEAMS][MAX_NEW]
+    uint32_t* vis;     // [MAX_LEVELS][MAX_BEAMS][VIS_WORDS]
+    // scalars: [0] P, [1] gen_len0 (tokens generated before this round), [2] first (roots == prompt),
+    //          [3] acc_n (accepted KV slots in use), [4] n_matches of the last verify, [5] miss_n,
+    //          [6] gather_n, [7] result_level
+    int* scal;
+    // verify trace (read back by tests): per verified level the K target picks and the hit positions
+    int* tr_pick_parent;   // [MAX_LEVELS][MAX_K]  parent position in the draft's level list (or root index)
+    int* tr_pick_tok;      // [MAX_LEVELS][MAX_K]
+    float* tr_pick_score;  // [MAX_LEVELS][MAX_K]
+    int* tr_hit_pos;       // [MAX_LEVELS][MAX_K]  draft position of each pick (-1 = not proposed)
+    int* tr_npick;         // [MAX_LEVELS]
+    // KV compaction lists produced by verify, consumed by kernel (c)
+    int* gather_src;       // [MAX_LEVELS * MAX_K]
+    int* gather_dst;
+    // draft tokens whose KV is missing after a fully accepted round
+    int* miss_tok;         // [MAX_K]
+    int* miss_pos;
+    int* miss_slot;
+    uint32_t* miss_vis;    // [MAX_K][VIS_WORDS]
+};
+enum { SC_P = 0, SC_GEN0 = 1, SC_FIRST = 2, SC_ACC = 3, SC_NMATCH = 4, SC_MISS = 5, SC_GATHER = 6, SC_RESULT = 7,
+       SC_COUNT = 16 };
+
+// Forward batch (one per model invocation) + logits-row selection, device arrays.
+struct BatchDev {
+    int* tok; int* pos; int* slot; int* prefix_len; uint32_t* vis;   // [T_max] ([T_max][VIS_WORDS])
+    int* rows_idx;    // [R_max] batch index of each logits row
+    int* row_node;    // [R_max] trie node of each logits row (-1 = padding row)
+};
+
+// Static (host-known) geometry of one search configuration.
+struct TreeGeom {
+    int K, N;          // target / draft beam widths
+    int A_cap;         // accepted-region slots after the prompt (MAX_NEW * K rounded)
+    int V;
+    __host__ __device__ int lvl_off(int l) const { return l == 0 ? 0 : K + (l - 1) * N; }      // tree-slot offset of a level
+    __host__ __device__ int tree_slot(int P, int l, int i) const { return P + A_cap + lvl_off(l) + i; }
+};
+
+// prompt batch: tok = prompt, pos = slot = i, prefix = i + 1
+int tree_begin(const TreeDev& t, const BatchDev& b, const int* prompt, int P, cudaStream_t st);
+// what a forward batch contains
+struct BatchPlan {
+    int with_prompt;   // 1: batch starts with the P prompt tokens (first round)
+    int with_missing;  // 1: then the draft's missing ancestors (cap K)
+    int l_from, l_to;  // then levels l_from..l_to (caps: level 0 -> K, others -> width)
+    int width;         // cap of levels >= 1
+    int rows_from;     // first level whose tokens produce logits rows; with_prompt adds the root row (P-1)
+    int root_row;      // 1: emit the prompt's last position as row 0 (first round)
+};
+int tree_build_batch(const TreeDev& t, const BatchDev& b, const TreeGeom& g, const BatchPlan& plan, int P, int T_cap,
+                     int R_cap, cudaStream_t st);
+// level l+1 = top-`width` of (logp + parent score) over the rows of level l
+int tree_select(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int level, int row0, int B,
+                const int* cand_tok, const int* cand_edge, const float* cand_logp, const int* cand_cnt, int width,
+                int P, cudaStream_t st);
+// kernel (b), strict mode
+int tree_verify_strict(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int draft_len, int root_rows,
+                       const int* cand_tok, const int* cand_edge, const float* cand_logp, const int* cand_cnt, int P,
+                       cudaStream_t st);
+
+}  // namespace atspeed

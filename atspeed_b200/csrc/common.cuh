@@ -1,0 +1,102 @@
+// Shared device/host helpers for the atspeed_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "atspeed_b200 kernels are written for sm_100a only"
+#endif
+
+namespace atspeed {
+
+// ---------------------------------------------------------------------------------------------
+// error reporting: every C-ABI entry returns 0 or a negative code; text via atspeed_last_error()
+// ---------------------------------------------------------------------------------------------
+enum : int {
+    ATS_OK = 0,
+    ATS_ERR_ARG = -1,      // bad argument (shape, alignment, limit)
+    ATS_ERR_CUDA = -2,     // CUDA runtime / driver error
+    ATS_ERR_STATE = -3,    // call out of order for the session state
+    ATS_ERR_LIMIT = -4,    // exceeds a compiled limit
+};
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define ATS_CHECK_ARG(cond, ...)                      \
+    do {                                              \
+        if (!(cond)) {                                \
+            ::atspeed::set_error(__VA_ARGS__);        \
+            return ::atspeed::ATS_ERR_ARG;            \
+        }                                             \
+    } while (0)
+
+#define ATS_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ::atspeed::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                                 __FILE__, __LINE__);                                         \
+            return ::atspeed::ATS_ERR_CUDA;                                                   \
+        }                                                                                     \
+    } while (0)
+
+#define ATS_LAUNCH_CHECK()  ATS_CUDA(cudaGetLastError())
+
+#define ATS_TRY(expr)                 \
+    do {                              \
+        int _r = (expr);              \
+        if (_r != 0) return _r;       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// limits of the beam-tree state (see DESIGN.md "Data layout")
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_BEAMS = 64;      // K (target beams) <= 32 is required; N (draft beams) <= 64
+constexpr int MAX_K = 32;
+constexpr int MAX_LEVELS = 5;      // roots + up to 4 draft levels per round
+constexpr int MAX_NEW = 6;         // max_new_tokens
+constexpr int VIS_WORDS = 16;      // 512 tree/accepted KV slots addressable by a beam's visibility mask
+constexpr int MAX_TREE_SLOTS = VIS_WORDS * 32;
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// total order used for every top-k in the library: higher score first, ties -> lower index first.
+// key = (orderable score bits << 32) | (0xffffffff - idx): bigger key wins.
+__device__ __forceinline__ unsigned long long rank_key(float score, uint32_t idx) {
+    uint32_t b = __float_as_uint(score);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return (static_cast<unsigned long long>(b) << 32) | static_cast<unsigned long long>(0xffffffffu - idx);
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+#endif
+
+}  // namespace atspeed

@@ -1,0 +1,643 @@
+// Session orchestration + the C ABI of libatspeed_b200 (include/atspeed.h).
+//
+// Host-side runtime of the draft/verify loop (reference code/beamSD.py:458-542 `BSSD`, :544-595
+// `target_generate`): it only sequences kernel launches on the caller's stream.  All search state lives
+// on the device (beam.cuh); the single device->host read per round is the accepted length.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "../../include/atspeed.h"
+#include "beam.cuh"
+#include "kernels.h"
+
+namespace atspeed {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+struct LayerRT {
+    GemmWeights qkv, o, gu, down;
+    int s_qkv, s_o, s_gu, s_down;   // split-K factors
+    const __nv_bfloat16 *ln1, *ln2;
+};
+
+struct ModelRT {
+    atspeed_model_desc d;
+    std::vector<LayerRT> layers;
+    GemmWeights lm;
+    int HD;
+    // activations (device, carved from the workspace)
+    __nv_bfloat16 *h, *x, *q, *a, *m, *xsel, *kv;
+    float *part, *logits;
+    long long kv_plane;   // elements per K (or V) plane of one layer
+    int ldl;              // logits row stride
+    int last_rows;
+    int forwards;
+};
+
+// host-side flags kept next to the pinned scalar mirror: is the root still the prompt, does the draft owe KV for
+// accepted tokens, which tree level holds the current beams
+enum { H_FIRST = 32, H_MISS = 33, H_LEVEL = 34 };
+
+struct Carver {
+    uint8_t* base;
+    size_t off;
+    template <typename T> T* take(size_t n) {
+        off = (off + 1023) & ~size_t(1023);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+}  // namespace atspeed
+
+using namespace atspeed;
+
+struct atspeed_session {
+    atspeed_config cfg;
+    TreeGeom geom;
+    TrieCSR trie;
+    ModelRT tgt, dft;
+    bool has_draft;
+    TreeDev tree;
+    BatchDev batch;
+    int *cand_tok, *cand_edge, *cand_cnt;
+    float *cand_logp, *lse;
+    int* prompt_dev;
+    int T_max, R_max, S_max;
+    int P;
+    int num_sms;
+    int* pinned;          // pinned host scratch
+    long long launches;
+};
+
+namespace atspeed {
+
+static size_t part_elems(const atspeed_model_desc& d, int T_max, int num_sms) {
+    const int HD = d.n_heads * d.head_dim;
+    const int kb_h = (d.hidden + 63) / 64, kb_hd = (HD + 63) / 64, kb_m = (d.mlp + 63) / 64;
+    auto tiles = [](int rows) { return (rows + 127) / 128; };
+    size_t e = 0;
+    auto upd = [&](int total_tiles, int kb, int cols) {
+        const size_t v = static_cast<size_t>(gemm_plan_splits(total_tiles, kb, num_sms)) * T_max * cols;
+        if (v > e) e = v;
+    };
+    upd(3 * tiles(HD), kb_h, 3 * HD);
+    upd(tiles(d.hidden), kb_hd, d.hidden);
+    upd(2 * tiles(d.mlp), kb_h, 2 * d.mlp);
+    upd(tiles(d.hidden), kb_m, d.hidden);
+    return e;
+}
+
+static void carve_model(Carver& c, ModelRT& m, const atspeed_model_desc& d, int T_max, int R_max, int S_max, int num_sms) {
+    m.d = d;
+    m.HD = d.n_heads * d.head_dim;
+    m.ldl = (d.vocab + 7) & ~7;
+    m.h = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * d.hidden);
+    m.x = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * d.hidden);
+    m.q = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * m.HD);
+    m.a = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * m.HD);
+    m.m = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * d.mlp);
+    m.xsel = c.take<__nv_bfloat16>(static_cast<size_t>(R_max) * d.hidden);
+    m.part = c.take<float>(part_elems(d, T_max, num_sms));
+    m.logits = c.take<float>(static_cast<size_t>(R_max) * m.ldl);
+    m.kv_plane = static_cast<long long>(S_max) * m.HD;
+    m.kv = c.take<__nv_bfloat16>(static_cast<size_t>(d.n_layers) * 2 * m.kv_plane);
+    m.last_rows = 0;
+    m.forwards = 0;
+}
+
+static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_desc* target, const atspeed_model_desc* draft) {
+    carve_model(c, s->tgt, *target, s->T_max, s->R_max, s->S_max, s->num_sms);
+    if (draft) carve_model(c, s->dft, *draft, s->T_max, s->R_max, s->S_max, s->num_sms);
+    TreeDev& t = s->tree;
+    t.cnt = c.take<int>(MAX_LEVELS);
+    t.tok = c.take<int>(MAX_LEVELS * MAX_BEAMS);
+    t.parent = c.take<int>(MAX_LEVELS * MAX_BEAMS);
+    t.node = c.take<int>(MAX_LEVELS * MAX_BEAMS);
+    t.slot = c.take<int>(MAX_LEVELS * MAX_BEAMS);
+    t.score = c.take<float>(MAX_LEVELS * MAX_BEAMS);
+    t.gen = c.take<int>(MAX_LEVELS * MAX_BEAMS * MAX_NEW);
+    t.vis = c.take<uint32_t>(MAX_LEVELS * MAX_BEAMS * VIS_WORDS);
+    t.scal = c.take<int>(SC_COUNT);
+    t.tr_pick_parent = c.take<int>(MAX_LEVELS * MAX_K);
+    t.tr_pick_tok = c.take<int>(MAX_LEVELS * MAX_K);
+    t.tr_pick_score = c.take<float>(MAX_LEVELS * MAX_K);
+    t.tr_hit_pos = c.take<int>(MAX_LEVELS * MAX_K);
+    t.tr_npick = c.take<int>(MAX_LEVELS);
+    t.gather_src = c.take<int>(MAX_LEVELS * MAX_K);
+    t.gather_dst = c.take<int>(MAX_LEVELS * MAX_K);
+    t.miss_tok = c.take<int>(MAX_K);
+    t.miss_pos = c.take<int>(MAX_K);
+    t.miss_slot = c.take<int>(MAX_K);
+    t.miss_vis = c.take<uint32_t>(MAX_K * VIS_WORDS);
+    BatchDev& b = s->batch;
+    b.tok = c.take<int>(s->T_max);
+    b.pos = c.take<int>(s->T_max);
+    b.slot = c.take<int>(s->T_max);
+    b.prefix_len = c.take<int>(s->T_max);
+    b.vis = c.take<uint32_t>(static_cast<size_t>(s->T_max) * VIS_WORDS);
+    b.rows_idx = c.take<int>(s->R_max);
+    b.row_node = c.take<int>(s->R_max);
+    s->cand_tok = c.take<int>(static_cast<size_t>(s->R_max) * MAX_BEAMS);
+    s->cand_edge = c.take<int>(static_cast<size_t>(s->R_max) * MAX_BEAMS);
+    s->cand_logp = c.take<float>(static_cast<size_t>(s->R_max) * MAX_BEAMS);
+    s->cand_cnt = c.take<int>(s->R_max);
+    s->lse = c.take<float>(s->R_max);
+    s->prompt_dev = c.take<int>(s->cfg.max_prompt);
+}
+
+static int check_cfg(const atspeed_model_desc* target, const atspeed_model_desc* draft, const atspeed_config* cfg) {
+    ATS_CHECK_ARG(target && cfg, "null target/config");
+    ATS_CHECK_ARG(cfg->K >= 1 && cfg->K <= MAX_K, "K=%d outside [1,%d]", cfg->K, MAX_K);
+    ATS_CHECK_ARG(cfg->N >= cfg->K && cfg->N <= MAX_BEAMS, "N=%d outside [K,%d]", cfg->N, MAX_BEAMS);
+    ATS_CHECK_ARG(cfg->max_new_tokens >= 1 && cfg->max_new_tokens <= MAX_NEW && cfg->max_new_tokens < MAX_LEVELS + 1,
+                  "max_new_tokens=%d outside [1,%d]", cfg->max_new_tokens, MAX_LEVELS);
+    ATS_CHECK_ARG(cfg->max_prompt >= 1, "max_prompt=%d", cfg->max_prompt);
+    const int bits = cfg->max_new_tokens * cfg->K + cfg->K + (MAX_LEVELS - 1) * cfg->N + cfg->K;
+    ATS_CHECK_ARG(bits <= MAX_TREE_SLOTS, "K=%d N=%d need %d tree slots > %d", cfg->K, cfg->N, bits, MAX_TREE_SLOTS);
+    for (const atspeed_model_desc* d : {target, draft}) {
+        if (!d) continue;
+        ATS_CHECK_ARG(d->hidden % 8 == 0 && d->mlp % 8 == 0 && (d->n_heads * d->head_dim) % 8 == 0,
+                      "hidden/mlp/heads*head_dim must be multiples of 8");
+        ATS_CHECK_ARG(d->head_dim == 16 || d->head_dim == 32 || d->head_dim == 64 || d->head_dim == 128,
+                      "head_dim=%d unsupported", d->head_dim);
+        ATS_CHECK_ARG(d->vocab == target->vocab, "draft and target vocabularies differ");
+    }
+    return ATS_OK;
+}
+
+static void session_dims(atspeed_session* s) {
+    const atspeed_config& c = s->cfg;
+    const int dl_max = c.max_new_tokens - 1 < MAX_LEVELS - 1 ? c.max_new_tokens - 1 : MAX_LEVELS - 1;
+    int T = c.max_prompt + dl_max * c.N;
+    if (T < c.max_prompt + c.K) T = c.max_prompt + c.K;   // target_generate-style steps of width K
+    if (T > 512) T = 512;
+    s->T_max = T;
+    s->geom.K = c.K; s->geom.N = c.N; s->geom.A_cap = c.max_new_tokens * c.K; s->geom.V = 0;
+    s->R_max = c.K + (MAX_LEVELS - 1) * c.N + 1;
+    s->S_max = c.max_prompt + s->geom.A_cap + s->geom.lvl_off(MAX_LEVELS) + c.K;
+}
+
+static int build_gemm(GemmWeights& g, int K, std::initializer_list<std::pair<const void*, int>> ws) {
+    g.n = 0; g.K = K;
+    int col = 0;
+    for (auto& w : ws) {
+        g.rows[g.n] = w.second;
+        g.colbase[g.n] = col;
+        ATS_TRY(make_tmap_bf16_kmajor(&g.tmap[g.n], w.first, w.second, K, 128));
+        col += w.second;
+        ++g.n;
+    }
+    return ATS_OK;
+}
+
+static int build_model(ModelRT& m, int num_sms) {
+    const atspeed_model_desc& d = m.d;
+    auto tiles = [](int rows) { return (rows + 127) / 128; };
+    m.layers.resize(d.n_layers);
+    for (int l = 0; l < d.n_layers; ++l) {
+        const void* const* w = d.layer_weights + static_cast<size_t>(l) * 9;
+        LayerRT& L = m.layers[l];
+        ATS_TRY(build_gemm(L.qkv, d.hidden, {{w[0], m.HD}, {w[1], m.HD}, {w[2], m.HD}}));
+        ATS_TRY(build_gemm(L.o, m.HD, {{w[3], d.hidden}}));
+        ATS_TRY(build_gemm(L.gu, d.hidden, {{w[4], d.mlp}, {w[5], d.mlp}}));
+        ATS_TRY(build_gemm(L.down, d.mlp, {{w[6], d.hidden}}));
+        L.s_qkv = gemm_plan_splits(3 * tiles(m.HD), (d.hidden + 63) / 64, num_sms);
+        L.s_o = gemm_plan_splits(tiles(d.hidden), (m.HD + 63) / 64, num_sms);
+        L.s_gu = gemm_plan_splits(2 * tiles(d.mlp), (d.hidden + 63) / 64, num_sms);
+        L.s_down = gemm_plan_splits(tiles(d.hidden), (d.mlp + 63) / 64, num_sms);
+        L.ln1 = static_cast<const __nv_bfloat16*>(w[7]);
+        L.ln2 = static_cast<const __nv_bfloat16*>(w[8]);
+    }
+    ATS_TRY(build_gemm(m.lm, d.hidden, {{d.lm_head, d.vocab}}));
+    return ATS_OK;
+}
+
+// One forward of `m` over the batch in `b` (T tokens; attention scans KV slots [0, S)), logits for R rows.
+static int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, const int* rows_idx, int R,
+                   cudaStream_t st) {
+    const atspeed_model_desc& d = m.d;
+    ATS_CHECK_ARG(T >= 1 && T <= s->T_max, "forward: T=%d exceeds T_max=%d", T, s->T_max);
+    ATS_CHECK_ARG(R >= 1 && R <= s->R_max, "forward: R=%d exceeds R_max=%d", R, s->R_max);
+    ATS_CHECK_ARG(S <= s->S_max, "forward: S=%d exceeds S_max=%d", S, s->S_max);
+    const auto* embed = static_cast<const __nv_bfloat16*>(d.embed);
+    ATS_TRY(embed_rows(embed, b.tok, T, d.hidden, d.vocab, m.h, st));
+    ATS_TRY(rmsnorm_rows(m.h, m.layers[0].ln1, T, d.hidden, d.rms_eps, m.x, nullptr, st));
+    s->launches += 2;
+    for (int l = 0; l < d.n_layers; ++l) {
+        LayerRT& L = m.layers[l];
+        __nv_bfloat16* kc = m.kv + static_cast<long long>(l) * 2 * m.kv_plane;
+        __nv_bfloat16* vc = kc + m.kv_plane;
+        const int c_qkv = 3 * m.HD, c_gu = 2 * d.mlp;
+        ATS_TRY(gemm_wx(L.qkv, m.x, T, m.part, c_qkv, static_cast<long long>(T) * c_qkv, L.s_qkv, st));
+        ATS_TRY(qkv_rope_append(m.part, L.s_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
+                                d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
+        ATS_TRY(tree_attention(m.q, kc, vc, b, T, S, d.n_heads, d.head_dim, m.a, st));
+        ATS_TRY(gemm_wx(L.o, m.a, T, m.part, d.hidden, static_cast<long long>(T) * d.hidden, L.s_o, st));
+        ATS_TRY(residual_rmsnorm(m.h, m.part, L.s_o, static_cast<long long>(T) * d.hidden, d.hidden, L.ln2, T, d.hidden,
+                                 d.rms_eps, m.x, st));
+        ATS_TRY(gemm_wx(L.gu, m.x, T, m.part, c_gu, static_cast<long long>(T) * c_gu, L.s_gu, st));
+        ATS_TRY(silu_mul(m.part, L.s_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
+        ATS_TRY(gemm_wx(L.down, m.m, T, m.part, d.hidden, static_cast<long long>(T) * d.hidden, L.s_down, st));
+        const __nv_bfloat16* next_ln = l + 1 < d.n_layers ? m.layers[l + 1].ln1 : nullptr;
+        ATS_TRY(residual_rmsnorm(m.h, m.part, L.s_down, static_cast<long long>(T) * d.hidden, d.hidden, next_ln, T,
+                                 d.hidden, d.rms_eps, m.x, st));
+        s->launches += 9;
+    }
+    ATS_TRY(rmsnorm_rows(m.h, static_cast<const __nv_bfloat16*>(d.final_norm), R, d.hidden, d.rms_eps, m.xsel, rows_idx, st));
+    ATS_TRY(gemm_wx(m.lm, m.xsel, R, m.logits, m.ldl, 0, 1, st));
+    s->launches += 2;
+    m.last_rows = R;
+    m.forwards++;
+    return ATS_OK;
+}
+
+static BatchDesc batch_desc(const atspeed_session* s) {
+    BatchDesc b;
+    b.tok = s->batch.tok; b.pos = s->batch.pos; b.slot = s->batch.slot; b.prefix_len = s->batch.prefix_len;
+    b.vis = s->batch.vis; b.vis_base = s->P; b.n_valid = nullptr;
+    return b;
+}
+
+static int run_topk(atspeed_session* s, ModelRT& m, int R, int B, cudaStream_t st) {
+    ATS_TRY(mask_logsoftmax_topk(m.logits, 0, R, m.d.vocab, m.ldl, s->batch.row_node, nullptr, s->trie, B, s->cand_tok,
+                                 s->cand_edge, s->cand_logp, s->cand_cnt, s->lse, st));
+    s->launches += 1;
+    return ATS_OK;
+}
+
+// one beam-search step of `width` on model m from tree level `level` -> level + 1
+// (one_step_beam_search, beamSD.py:40-106).  `first`: the roots are the prompt itself.
+static int search_step(atspeed_session* s, ModelRT& m, int level, int width, bool first, bool with_missing,
+                       cudaStream_t st) {
+    const TreeGeom& g = s->geom;
+    const int P = s->P;
+    BatchPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    int T, R, S;
+    if (level == 0 && first) {
+        plan.with_prompt = 1; plan.l_from = 1; plan.l_to = 0; plan.rows_from = 1; plan.root_row = 1; plan.width = width;
+        T = P; R = 1; S = P;
+    } else {
+        plan.with_missing = with_missing ? 1 : 0;
+        plan.l_from = plan.l_to = plan.rows_from = level; plan.width = width;
+        const int cap = level == 0 ? g.K : width;
+        T = (with_missing ? g.K : 0) + cap; R = cap;
+        S = g.tree_slot(P, level, 0) + cap;
+    }
+    ATS_TRY(tree_build_batch(s->tree, s->batch, g, plan, P, T, R, st));
+    s->launches += 1;
+    ATS_TRY(forward(s, m, batch_desc(s), T, S, s->batch.rows_idx, R, st));
+    ATS_TRY(run_topk(s, m, R, width, st));
+    ATS_TRY(tree_select(s->tree, g, s->trie, level, 0, width, s->cand_tok, s->cand_edge, s->cand_logp, s->cand_cnt, width,
+                        P, st));
+    s->launches += 1;
+    return ATS_OK;
+}
+
+}  // namespace atspeed
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* atspeed_last_error(void) { return atspeed::last_error(); }
+int atspeed_abi_version(void) { return ATSPEED_ABI_VERSION; }
+
+int atspeed_session_workspace_bytes(const atspeed_model_desc* target, const atspeed_model_desc* draft,
+                                    const atspeed_config* cfg, size_t* bytes) {
+    ATS_TRY(check_cfg(target, draft, cfg));
+    ATS_CHECK_ARG(bytes, "null bytes");
+    atspeed_session tmp;
+    tmp.cfg = *cfg;
+    tmp.num_sms = cfg->num_sms > 0 ? cfg->num_sms : 148;
+    session_dims(&tmp);
+    Carver c{nullptr, 0};
+    carve_session(c, &tmp, target, draft);
+    *bytes = c.off + 4096;
+    return ATS_OK;
+}
+
+int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model_desc* draft, const atspeed_config* cfg,
+                           const atspeed_trie_desc* trie, void* workspace, size_t workspace_bytes, atspeed_session** out) {
+    ATS_TRY(check_cfg(target, draft, cfg));
+    ATS_CHECK_ARG(trie && workspace && out, "null trie/workspace/out");
+    ATS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+    int dev = 0, sms = cfg->num_sms;
+    if (sms <= 0) {
+        ATS_CUDA(cudaGetDevice(&dev));
+        ATS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    atspeed_session* s = new atspeed_session();
+    s->cfg = *cfg;
+    s->num_sms = sms;
+    s->has_draft = draft != nullptr;
+    session_dims(s);
+    s->geom.V = target->vocab;
+    s->trie.child_off = trie->child_off; s->trie.child_tok = trie->child_tok; s->trie.child_node = trie->child_node;
+    s->trie.n_nodes = trie->n_nodes; s->trie.n_edges = trie->n_edges;
+    Carver c{static_cast<uint8_t*>(workspace), 0};
+    carve_session(c, s, target, draft);
+    if (c.off > workspace_bytes) {
+        set_error("workspace too small: need %zu bytes, got %zu", c.off, workspace_bytes);
+        delete s;
+        return ATS_ERR_ARG;
+    }
+    int r = build_model(s->tgt, sms);
+    if (r == ATS_OK && draft) r = build_model(s->dft, sms);
+    if (r != ATS_OK) { delete s; return r; }
+    if (cudaMallocHost(&s->pinned, 64 * sizeof(int)) != cudaSuccess) {
+        set_error("cudaMallocHost failed");
+        delete s;
+        return ATS_ERR_CUDA;
+    }
+    memset(s->pinned, 0, 64 * sizeof(int));
+    s->P = 0;
+    s->launches = 0;
+    *out = s;
+    return ATS_OK;
+}
+
+int atspeed_session_destroy(atspeed_session* s) {
+    if (!s) return ATS_OK;
+    if (s->pinned) cudaFreeHost(s->pinned);
+    delete s;
+    return ATS_OK;
+}
+
+int atspeed_session_begin(atspeed_session* s, const int32_t* prompt_host, int32_t P, void* stream) {
+    ATS_CHECK_ARG(s && prompt_host, "null session/prompt");
+    ATS_CHECK_ARG(P >= 1 && P <= s->cfg.max_prompt, "prompt length %d outside [1,%d]", P, s->cfg.max_prompt);
+    const int dl_max = s->cfg.max_new_tokens - 1;
+    ATS_CHECK_ARG(P + dl_max * s->cfg.N <= s->T_max && P + s->cfg.K <= s->T_max,
+                  "prompt length %d + %d tree tokens exceeds the %d-token forward limit", P, dl_max * s->cfg.N, s->T_max);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    s->P = P;
+    ATS_CUDA(cudaMemcpyAsync(s->prompt_dev, prompt_host, sizeof(int) * P, cudaMemcpyHostToDevice, st));
+    ATS_TRY(tree_begin(s->tree, s->batch, s->prompt_dev, P, st));
+    s->launches += 1;
+    s->pinned[H_FIRST] = 1;    // first
+    s->pinned[H_MISS] = 0;    // missing ancestors pending for the draft
+    s->pinned[H_LEVEL] = 0;   // result level
+    return ATS_OK;
+}
+
+int atspeed_session_draft(atspeed_session* s, int32_t draft_len, void* stream) {
+    ATS_CHECK_ARG(s && s->has_draft, "session has no draft model");
+    ATS_CHECK_ARG(draft_len >= 1 && draft_len < MAX_LEVELS, "draft_len=%d", draft_len);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int j = 0; j < draft_len; ++j)
+        ATS_TRY(search_step(s, s->dft, j, s->cfg.N, s->pinned[H_FIRST] != 0, j == 0 && s->pinned[H_MISS] != 0, st));
+    return ATS_OK;
+}
+
+int atspeed_session_target(atspeed_session* s, int32_t draft_len, void* stream) {
+    ATS_CHECK_ARG(s, "null session");
+    ATS_CHECK_ARG(draft_len >= 1 && draft_len < MAX_LEVELS, "draft_len=%d", draft_len);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const TreeGeom& g = s->geom;
+    const int P = s->P;
+    const bool first = s->pinned[H_FIRST] != 0;
+    BatchPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    plan.width = g.N;
+    int T, R;
+    if (first) {
+        plan.with_prompt = 1; plan.l_from = 1; plan.l_to = draft_len; plan.rows_from = 1; plan.root_row = 1;
+        T = P + draft_len * g.N; R = 1 + draft_len * g.N;
+    } else {
+        plan.l_from = 0; plan.l_to = draft_len; plan.rows_from = 0;
+        T = g.K + draft_len * g.N; R = T;
+    }
+    const int S = g.tree_slot(P, draft_len, 0) + g.N;
+    ATS_TRY(tree_build_batch(s->tree, s->batch, g, plan, P, T, R, st));
+    s->launches += 1;
+    ATS_TRY(forward(s, s->tgt, batch_desc(s), T, S, s->batch.rows_idx, R, st));
+    ATS_TRY(run_topk(s, s->tgt, R, g.K, st));
+    return ATS_OK;
+}
+
+int atspeed_session_verify(atspeed_session* s, int32_t draft_len, int32_t* n_matches_host, void* stream) {
+    ATS_CHECK_ARG(s && n_matches_host, "null session/out");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const TreeGeom& g = s->geom;
+    const bool first = s->pinned[H_FIRST] != 0;
+    ATS_TRY(tree_verify_strict(s->tree, g, s->trie, draft_len, first ? 1 : g.K, s->cand_tok, s->cand_edge, s->cand_logp,
+                               s->cand_cnt, s->P, st));
+    // kernel (c): move the survivors' ancestor rows into the accepted region, both caches, all layers
+    const int max_rows = (draft_len + 1) * g.K;
+    for (ModelRT* m : {&s->tgt, s->has_draft ? &s->dft : nullptr}) {
+        if (!m) continue;
+        ATS_TRY(kv_gather_rows(m->kv, m->kv_plane * 2 /*bytes per element*/, m->d.n_layers * 2, m->HD * 2, s->tree.gather_src,
+                               s->tree.gather_dst, s->tree.scal + SC_GATHER, max_rows, st));
+        s->launches += 1;
+    }
+    s->launches += 1;
+    ATS_CUDA(cudaMemcpyAsync(s->pinned, s->tree.scal, sizeof(int) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+    ATS_CUDA(cudaStreamSynchronize(st));
+    *n_matches_host = s->pinned[SC_NMATCH];
+    s->pinned[H_FIRST] = 0;
+    s->pinned[H_MISS] = s->pinned[SC_MISS] > 0 ? 1 : 0;
+    s->pinned[H_LEVEL] = 0;
+    return ATS_OK;
+}
+
+int atspeed_session_step(atspeed_session* s, int32_t model, int32_t width, void* stream) {
+    ATS_CHECK_ARG(s, "null session");
+    ATS_CHECK_ARG(model == 0 || (model == 1 && s->has_draft), "model=%d", model);
+    ATS_CHECK_ARG(width >= 1 && width <= MAX_BEAMS, "width=%d", width);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int level = s->pinned[H_LEVEL];
+    ATS_CHECK_ARG(level + 1 < MAX_LEVELS, "too many consecutive steps (%d)", level);
+    ATS_TRY(search_step(s, model == 0 ? s->tgt : s->dft, level, width, s->pinned[H_FIRST] != 0 && level == 0,
+                        model == 1 && level == 0 && s->pinned[H_MISS] != 0, st));
+    s->pinned[H_LEVEL] = level + 1;
+    return ATS_OK;
+}
+
+int atspeed_session_result(atspeed_session* s, int32_t* tokens_host, float* scores_host, int32_t* count, void* stream) {
+    ATS_CHECK_ARG(s && tokens_host && scores_host && count, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int level = s->pinned[H_LEVEL];
+    int cnt[MAX_LEVELS];
+    int gen[MAX_BEAMS * MAX_NEW];
+    float sc[MAX_BEAMS];
+    ATS_CUDA(cudaMemcpyAsync(cnt, s->tree.cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    ATS_CUDA(cudaMemcpyAsync(gen, s->tree.gen + static_cast<size_t>(level) * MAX_BEAMS * MAX_NEW, sizeof(gen),
+                             cudaMemcpyDeviceToHost, st));
+    ATS_CUDA(cudaMemcpyAsync(sc, s->tree.score + static_cast<size_t>(level) * MAX_BEAMS, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    ATS_CUDA(cudaStreamSynchronize(st));
+    const int n = cnt[level] < s->cfg.K ? cnt[level] : s->cfg.K;
+    const int L = s->cfg.max_new_tokens;
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < L; ++k) tokens_host[i * L + k] = gen[i * MAX_NEW + k];
+        scores_host[i] = sc[i];
+    }
+    *count = n;
+    return ATS_OK;
+}
+
+int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t gamma, int32_t* tokens_host,
+                 float* scores_host, int32_t* count, atspeed_stats* stats, void* stream) {
+    ATS_CHECK_ARG(s && s->has_draft, "session has no draft model");
+    ATS_CHECK_ARG(gamma >= 1, "gamma=%d", gamma);
+    const long long l0 = s->launches;
+    const int tf0 = s->tgt.forwards, df0 = s->dft.forwards;
+    ATS_TRY(atspeed_session_begin(s, prompt_host, P, stream));
+    const int L = s->cfg.max_new_tokens;
+    int done = 0, n_run = 0, total = 0;
+    int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    while (done < L) {
+        int dl = gamma < L - done - 1 ? gamma : L - done - 1;                 // beamSD.py:504
+        if (dl > MAX_LEVELS - 1) dl = MAX_LEVELS - 1;
+        if (dl == 0) {                                                         // beamSD.py:505-509
+            ATS_TRY(atspeed_session_step(s, 0, s->cfg.K, stream));
+            break;
+        }
+        ATS_TRY(atspeed_session_draft(s, dl, stream));
+        ATS_TRY(atspeed_session_target(s, dl, stream));
+        int m = 0;
+        ATS_TRY(atspeed_session_verify(s, dl, &m, stream));
+        done += m + 1;
+        if (n_run < 8) acc[n_run] = m;
+        ++n_run;
+        total += m;
+    }
+    ATS_TRY(atspeed_session_result(s, tokens_host, scores_host, count, stream));
+    if (stats) {
+        stats->n_run = n_run;
+        stats->total_accept_steps = total;
+        for (int i = 0; i < 8; ++i) stats->accept_steps[i] = acc[i];
+        stats->target_forwards = s->tgt.forwards - tf0;
+        stats->draft_forwards = s->dft.forwards - df0;
+        stats->kernel_launches = static_cast<int>(s->launches - l0);
+    }
+    return ATS_OK;
+}
+
+int atspeed_target_generate(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t* tokens_host,
+                            float* scores_host, int32_t* count, atspeed_stats* stats, void* stream) {
+    ATS_CHECK_ARG(s, "null session");
+    ATS_CHECK_ARG(s->cfg.max_new_tokens < MAX_LEVELS, "max_new_tokens=%d too large for target_generate", s->cfg.max_new_tokens);
+    const long long l0 = s->launches;
+    const int tf0 = s->tgt.forwards;
+    ATS_TRY(atspeed_session_begin(s, prompt_host, P, stream));
+    for (int i = 0; i < s->cfg.max_new_tokens; ++i) ATS_TRY(atspeed_session_step(s, 0, s->cfg.K, stream));
+    ATS_TRY(atspeed_session_result(s, tokens_host, scores_host, count, stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->target_forwards = s->tgt.forwards - tf0;
+        stats->kernel_launches = static_cast<int>(s->launches - l0);
+    }
+    return ATS_OK;
+}
+
+int atspeed_session_read(atspeed_session* s, int32_t field, void* host_dst, size_t bytes, void* stream) {
+    ATS_CHECK_ARG(s && host_dst, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const void* src = nullptr;
+    size_t avail = 0;
+    const TreeDev& t = s->tree;
+    switch (field) {
+        case ATSPEED_F_LEVEL_CNT: src = t.cnt; avail = sizeof(int) * MAX_LEVELS; break;
+        case ATSPEED_F_LEVEL_TOK: src = t.tok; avail = sizeof(int) * MAX_LEVELS * MAX_BEAMS; break;
+        case ATSPEED_F_LEVEL_PARENT: src = t.parent; avail = sizeof(int) * MAX_LEVELS * MAX_BEAMS; break;
+        case ATSPEED_F_LEVEL_SCORE: src = t.score; avail = sizeof(float) * MAX_LEVELS * MAX_BEAMS; break;
+        case ATSPEED_F_LEVEL_NODE: src = t.node; avail = sizeof(int) * MAX_LEVELS * MAX_BEAMS; break;
+        case ATSPEED_F_SCALARS: src = t.scal; avail = sizeof(int) * SC_COUNT; break;
+        case ATSPEED_F_PICK_PARENT: src = t.tr_pick_parent; avail = sizeof(int) * MAX_LEVELS * MAX_K; break;
+        case ATSPEED_F_PICK_TOK: src = t.tr_pick_tok; avail = sizeof(int) * MAX_LEVELS * MAX_K; break;
+        case ATSPEED_F_PICK_SCORE: src = t.tr_pick_score; avail = sizeof(float) * MAX_LEVELS * MAX_K; break;
+        case ATSPEED_F_HIT_POS: src = t.tr_hit_pos; avail = sizeof(int) * MAX_LEVELS * MAX_K; break;
+        case ATSPEED_F_NPICK: src = t.tr_npick; avail = sizeof(int) * MAX_LEVELS; break;
+        case ATSPEED_F_LOGITS_TARGET: src = s->tgt.logits; avail = sizeof(float) * s->R_max * s->tgt.ldl; break;
+        case ATSPEED_F_LOGITS_DRAFT:
+            ATS_CHECK_ARG(s->has_draft, "no draft model");
+            src = s->dft.logits; avail = sizeof(float) * s->R_max * s->dft.ldl; break;
+        case ATSPEED_F_ROW_NODE: src = s->batch.row_node; avail = sizeof(int) * s->R_max; break;
+        default: set_error("unknown field %d", field); return ATS_ERR_ARG;
+    }
+    ATS_CHECK_ARG(bytes <= avail, "field %d holds %zu bytes, %zu requested", field, avail, bytes);
+    ATS_CUDA(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    ATS_CUDA(cudaStreamSynchronize(st));
+    return ATS_OK;
+}
+
+int atspeed_session_info(atspeed_session* s, int64_t* info8) {
+    ATS_CHECK_ARG(s && info8, "null argument");
+    info8[0] = s->tgt.ldl; info8[1] = s->R_max; info8[2] = s->T_max; info8[3] = s->S_max; info8[4] = s->geom.A_cap;
+    info8[5] = s->launches; info8[6] = s->tgt.last_rows; info8[7] = s->has_draft ? s->dft.last_rows : 0;
+    return ATS_OK;
+}
+
+int atspeed_session_forward_raw(atspeed_session* s, int32_t model, const int32_t* tok, const int32_t* pos,
+                                const int32_t* slot, const int32_t* prefix_len, const uint32_t* vis, int32_t vis_base,
+                                int32_t T, int32_t S, const int32_t* rows_idx, int32_t R, void* stream) {
+    ATS_CHECK_ARG(s && tok && pos && slot && prefix_len && vis && rows_idx, "null argument");
+    ATS_CHECK_ARG(model == 0 || (model == 1 && s->has_draft), "model=%d", model);
+    BatchDesc b;
+    b.tok = tok; b.pos = pos; b.slot = slot; b.prefix_len = prefix_len; b.vis = vis; b.vis_base = vis_base; b.n_valid = nullptr;
+    return forward(s, model == 0 ? s->tgt : s->dft, b, T, S, rows_idx, R, static_cast<cudaStream_t>(stream));
+}
+
+int atspeed_mask_logsoftmax_topk(const void* logits, int32_t logits_bf16, int32_t rows, int32_t V, int64_t ld,
+                                 const int32_t* row_node, const int32_t* n_rows_dev, const atspeed_trie_desc* trie,
+                                 int32_t B, int32_t* cand_tok, int32_t* cand_edge, float* cand_logp, int32_t* cand_cnt,
+                                 float* lse, void* stream) {
+    ATS_CHECK_ARG(logits && row_node && trie && cand_tok && cand_edge && cand_logp && cand_cnt, "null argument");
+    TrieCSR t;
+    t.child_off = trie->child_off; t.child_tok = trie->child_tok; t.child_node = trie->child_node;
+    t.n_nodes = trie->n_nodes; t.n_edges = trie->n_edges;
+    return mask_logsoftmax_topk(logits, logits_bf16, rows, V, ld, row_node, n_rows_dev, t, B, cand_tok, cand_edge,
+                                cand_logp, cand_cnt, lse, static_cast<cudaStream_t>(stream));
+}
+
+int atspeed_kv_gather(const void* src_base, void* dst_base, int64_t src_plane_stride, int64_t dst_plane_stride,
+                      int32_t n_planes, int32_t row_bytes, const int32_t* src_rows, const int32_t* dst_rows,
+                      const int32_t* n_rows_dev, int32_t rows, void* stream) {
+    ATS_CHECK_ARG(src_base && dst_base && src_rows && dst_rows, "null argument");
+    return kv_gather_rows_oop(src_base, dst_base, src_plane_stride, dst_plane_stride, n_planes, row_bytes, src_rows,
+                              dst_rows, n_rows_dev, rows, static_cast<cudaStream_t>(stream));
+}
+
+int atspeed_gemm_bf16(const void* x, int32_t T, int32_t K, const void* w0, int32_t rows0, const void* w1, int32_t rows1,
+                      const void* w2, int32_t rows2, float* out, int32_t ldo, int32_t splits, void* stream) {
+    ATS_CHECK_ARG(x && w0 && out, "null argument");
+    GemmWeights g;
+    g.n = 0; g.K = K;
+    int col = 0;
+    const void* ws[3] = {w0, w1, w2};
+    const int rs[3] = {rows0, rows1, rows2};
+    for (int i = 0; i < 3 && ws[i]; ++i) {
+        g.rows[i] = rs[i]; g.colbase[i] = col;
+        ATS_TRY(make_tmap_bf16_kmajor(&g.tmap[i], ws[i], rs[i], K, 128));
+        col += rs[i];
+        g.n = i + 1;
+    }
+    ATS_CHECK_ARG(ldo >= col, "ldo=%d < total columns %d", ldo, col);
+    return gemm_wx(g, x, T, out, ldo, static_cast<long long>(T) * ldo, splits, static_cast<cudaStream_t>(stream));
+}
+
+int atspeed_tree_attention(const void* q, const void* kcache, const void* vcache, const int32_t* prefix_len,
+                           const uint32_t* vis, int32_t vis_base, int32_t T, int32_t S, int32_t n_heads, int32_t head_dim,
+                           void* out, void* stream) {
+    ATS_CHECK_ARG(q && kcache && vcache && prefix_len && vis && out, "null argument");
+    BatchDesc b;
+    memset(&b, 0, sizeof(b));
+    b.prefix_len = prefix_len; b.vis = vis; b.vis_base = vis_base;
+    return tree_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
+                          static_cast<const __nv_bfloat16*>(vcache), b, T, S, n_heads, head_dim,
+                          static_cast<__nv_bfloat16*>(out), static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

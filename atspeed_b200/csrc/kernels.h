@@ -1,0 +1,77 @@
+// Internal C++ interface between the .cu files of libatspeed_b200 (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace atspeed {
+
+// ---- gemm.cu ------------------------------------------------------------------------------------
+struct GemmWeights {
+    int n;                 // 1..3 weight matrices sharing one input
+    int K;                 // input features
+    int rows[3];           // output features of each
+    int colbase[3];        // first output column of each
+    CUtensorMap tmap[3];   // [rows_i, K] bf16, K-major, box 64 x 128, SWIZZLE_128B
+};
+int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, long long cols, int box_rows);
+int gemm_plan_splits(int total_tiles, int n_kblocks, int num_sms);
+int gemm_wx(const GemmWeights& w, const void* x, int T, float* out, int ldo, long long split_stride, int splits,
+            cudaStream_t stream);
+
+// ---- elementwise.cu -----------------------------------------------------------------------------
+// Forward-batch descriptor, all device arrays of length >= T (built by beam.cu kernels).
+struct BatchDesc {
+    const int* tok;          // token ids
+    const int* pos;          // RoPE positions
+    const int* slot;         // KV slot each token writes
+    const int* prefix_len;   // token attends KV slots [0, prefix_len)
+    const uint32_t* vis;     // [T][VIS_WORDS] bit j: token attends slot vis_base + j
+    int vis_base;            // first slot covered by the bit masks (= prompt length)
+    const int* n_valid;      // device scalar: tokens >= *n_valid are padding (may be nullptr = all valid)
+};
+int embed_rows(const __nv_bfloat16* table, const int* tok, int T, int hidden, int vocab, __nv_bfloat16* h,
+               cudaStream_t st);
+// x = rmsnorm(h) * g   (first layer / when no residual is pending)
+int rmsnorm_rows(const __nv_bfloat16* h, const __nv_bfloat16* g, int T, int hidden, float eps, __nv_bfloat16* x,
+                 const int* row_index, cudaStream_t st);
+// h = bf16(h + bf16(sum_s part[s])) ; x = rmsnorm(h) * g  (g == nullptr: residual only)
+int residual_rmsnorm(__nv_bfloat16* h, const float* part, int splits, long long split_stride, int ldp,
+                     const __nv_bfloat16* g, int T, int hidden, float eps, __nv_bfloat16* x, cudaStream_t st);
+// q,k,v = bf16(sum_s part[s]); RoPE(q,k) at pos; q -> qbuf [T, H*D]; k,v -> cache rows slot[t]
+// rope_cos/rope_sin: [max_pos][head_dim/2] fp32 tables holding bf16-rounded values (computed on the host exactly
+// as HF's LlamaRotaryEmbedding does, so the device never evaluates powf/cosf/sinf).
+int qkv_rope_append(const float* part, int splits, long long split_stride, int ldp, const BatchDesc& b, int T,
+                    int n_heads, int head_dim, const float* rope_cos, const float* rope_sin, int max_pos,
+                    __nv_bfloat16* qbuf, __nv_bfloat16* kcache, __nv_bfloat16* vcache, cudaStream_t st);
+// m = bf16(bf16(silu(g)) * u) with g,u = bf16(sum_s part[s]) at columns [0,mlp) and [mlp,2mlp)
+int silu_mul(const float* part, int splits, long long split_stride, int ldp, int T, int mlp, __nv_bfloat16* m,
+             cudaStream_t st);
+
+// ---- attention.cu -------------------------------------------------------------------------------
+int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
+                   const BatchDesc& b, int T, int S, int n_heads, int head_dim, __nv_bfloat16* out, cudaStream_t st);
+
+// ---- topk.cu: kernel (a) ------------------------------------------------------------------------
+struct TrieCSR {
+    const int* child_off;
+    const int* child_tok;
+    const int* child_node;
+    int n_nodes, n_edges;
+};
+// logits: rows x ld (bf16 if logits_bf16 else fp32). row_node[r] < 0 or r >= *n_rows_dev: row skipped (count 0).
+// Outputs per row r: cand_cnt[r] <= B; cand_tok/cand_edge/cand_logp[r*B + j] sorted by (logp desc, token asc);
+// lse[r] = log sum exp over the full vocabulary.
+int mask_logsoftmax_topk(const void* logits, int logits_bf16, int rows, int V, long long ld, const int* row_node,
+                         const int* n_rows_dev, const TrieCSR& trie, int B, int* cand_tok, int* cand_edge,
+                         float* cand_logp, int* cand_cnt, float* lse, cudaStream_t st);
+
+// ---- kvgather.cu: kernel (c) --------------------------------------------------------------------
+// For every plane p < n_planes and i < *n_rows_dev (<= max_rows): copy row_bytes from
+// base + p*plane_stride + src[i]*row_bytes to base + p*plane_stride + dst[i]*row_bytes. Source and
+// destination rows must not overlap as sets.
+int kv_gather_rows(void* base, long long plane_stride, int n_planes, int row_bytes, const int* src, const int* dst,
+                   const int* n_rows_dev, int max_rows, cudaStream_t st);
+int kv_gather_rows_oop(const void* src_base, void* dst_base, long long src_plane_stride, long long dst_plane_stride,
+                       int n_planes, int row_bytes, const int* src, const int* dst, const int* n_rows_dev,
+                       int max_rows, cudaStream_t st);
+
+}  // namespace atspeed

@@ -1,0 +1,202 @@
+/*
+ * atspeed.h -- C ABI of libatspeed_b200.so: the B200-native replacement for the hot path of
+ * Linxyhaha/AtSpeed, i.e. the speculative beam-search draft/verify loop of code/beamSD.py.
+ *
+ * The reference is pure Python: there is no FFI in it to mirror.  Each entry point below therefore
+ * cites the reference *function* (file:line relative to /root/reference) whose work it replaces; the
+ * Python host module atspeed_b200/beamSD.py keeps the reference's names and signatures on top of it
+ * (see INTEGRATION.md for the ctypes binding and the one-line change in inference.py).
+ *
+ * Conventions
+ *   - every pointer is a plain device or host address as stated; no torch / C++ types cross the ABI;
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); the only calls
+ *     that synchronise are the ones that return host values (documented per function);
+ *   - buffers are owned by the caller (PyTorch allocates them); the library owns only its handle and a
+ *     few bytes of pinned host memory inside it;
+ *   - return value 0 = success, negative = error; atspeed_last_error() gives the text.  Nothing throws,
+ *     nothing calls exit();
+ *   - thread-safety: calls on distinct sessions are independent; one session must be driven from one
+ *     thread at a time.
+ */
+#ifndef ATSPEED_H
+#define ATSPEED_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATSPEED_ABI_VERSION 1
+
+/* limits compiled into the library */
+#define ATSPEED_MAX_K 32          /* target beams  (reference: run_beam_sizes 10/20, code/script/inference.sh:16) */
+#define ATSPEED_MAX_N 64          /* draft beams   (reference: draft_beam_size 40, code/script/inference.sh:15)   */
+#define ATSPEED_MAX_NEW_TOKENS 6  /* reference uses 4 (code/inference.py:147) */
+#define ATSPEED_VIS_WORDS 16
+
+const char* atspeed_last_error(void);
+int atspeed_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model + session
+ * ---------------------------------------------------------------------------------------------- */
+
+/* A LLaMA decoder as laid out by HF `LlamaForCausalLM.state_dict()` (what `model(**inputs)` runs at
+ * code/beamSD.py:52,221): all weights bf16, row-major [out_features, in_features], on the device. */
+typedef struct atspeed_model_desc {
+    int32_t vocab, hidden, n_layers, n_heads, head_dim, mlp;
+    float rms_eps;
+    const void* embed;        /* [vocab, hidden]  model.embed_tokens.weight */
+    const void* final_norm;   /* [hidden]         model.norm.weight         */
+    const void* lm_head;      /* [vocab, hidden]  lm_head.weight            */
+    /* HOST array of n_layers*9 DEVICE pointers, per layer in this order:
+     * q_proj, k_proj, v_proj, o_proj, gate_proj, up_proj, down_proj, input_layernorm, post_attention_layernorm */
+    const void* const* layer_weights;
+    const float* rope_cos;    /* [max_pos, head_dim/2] fp32, bf16-rounded values (LlamaRotaryEmbedding) */
+    const float* rope_sin;
+    int32_t max_pos;
+} atspeed_model_desc;
+
+/* The compiled constraint (code/generation_trie.py Trie / code/data.py:84-104 positional fn): CSR child table. */
+typedef struct atspeed_trie_desc {
+    const int32_t* child_off;   /* [n_nodes + 1] device */
+    const int32_t* child_tok;   /* [n_edges]     device, ascending within a node */
+    const int32_t* child_node;  /* [n_edges]     device, -1 beyond the compiled depth */
+    int32_t n_nodes, n_edges;
+} atspeed_trie_desc;
+
+typedef struct atspeed_config {
+    int32_t K;                /* target.generation_config.num_beams  (code/beamSD.py:482) */
+    int32_t N;                /* draft.generation_config.num_beams   (code/beamSD.py:483) */
+    int32_t max_new_tokens;   /* code/inference.py:147 */
+    int32_t max_prompt;       /* longest prompt the session must hold */
+    int32_t num_sms;          /* 0 = query the device */
+} atspeed_config;
+
+typedef struct atspeed_session atspeed_session;
+
+/* Bytes of device workspace a session needs (activations, KV caches, beam-tree state, logits). */
+int atspeed_session_workspace_bytes(const atspeed_model_desc* target, const atspeed_model_desc* draft,
+                                    const atspeed_config* cfg, size_t* bytes);
+/* `draft` may be NULL (target_generate only).  `workspace` is a device buffer of at least the size above,
+ * 1024-byte aligned, that stays alive until atspeed_session_destroy. */
+int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model_desc* draft,
+                           const atspeed_config* cfg, const atspeed_trie_desc* trie, void* workspace,
+                           size_t workspace_bytes, atspeed_session** out);
+int atspeed_session_destroy(atspeed_session* s);
+
+/* ------------------------------------------------------------------------------------------------
+ * The hot path, stage by stage (mirrors BSSD's loop body, code/beamSD.py:503-526)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Start a user: copies the prompt ids (HOST int32[P], the `inputs["input_ids"]` of code/beamSD.py:486) to the
+ * device and resets the beam tree (beam_scores = 0, one root; code/beamSD.py:487-499). Asynchronous. */
+int atspeed_session_begin(atspeed_session* s, const int32_t* prompt_host, int32_t P, void* stream);
+
+/* draft_beam_search (code/beamSD.py:108-179): `draft_len` beam-search steps of width N on the draft model,
+ * each = forward + kernel (a) + merge.  Asynchronous. */
+int atspeed_session_draft(atspeed_session* s, int32_t draft_len, void* stream);
+
+/* target_beam_search (code/beamSD.py:190-232): ONE target forward over roots + all draft levels with the
+ * tree mask, then kernel (a) with B = K on every row of interest.  Asynchronous. */
+int atspeed_session_target(atspeed_session* s, int32_t draft_len, void* stream);
+
+/* verify, greedy branch = AtSpeed-S strict top-K (code/beamSD.py:242-456): kernel (b) + kernel (c) on both
+ * caches.  Writes the accepted length to *n_matches_host after synchronising the stream. */
+int atspeed_session_verify(atspeed_session* s, int32_t draft_len, int32_t* n_matches_host, void* stream);
+
+/* one_step_beam_search (code/beamSD.py:40-106) on the current beams: model 0 = target, 1 = draft; the new
+ * beams become level `+1` of the tree.  Used for the final step (code/beamSD.py:505-509) and by
+ * atspeed_target_generate.  Asynchronous. */
+int atspeed_session_step(atspeed_session* s, int32_t model, int32_t width, void* stream);
+
+/* Final beams: tokens_host int32[K * max_new_tokens] (generated suffix per beam, score-descending),
+ * scores_host float[K], *count = beams returned.  Synchronises the stream. */
+int atspeed_session_result(atspeed_session* s, int32_t* tokens_host, float* scores_host, int32_t* count,
+                           void* stream);
+
+typedef struct atspeed_stats {
+    int32_t n_run;                /* rounds                      (code/beamSD.py:527) */
+    int32_t total_accept_steps;   /* sum of n_matches            (code/beamSD.py:528) */
+    int32_t accept_steps[8];      /* n_matches per round */
+    int32_t target_forwards, draft_forwards;
+    int32_t kernel_launches;      /* kernels of this library launched for the call */
+} atspeed_stats;
+
+/* BSSD (code/beamSD.py:458-542), whole loop for one user (prompt on the HOST).  Synchronises once per round
+ * (the 4-byte n_matches) and once for the result. */
+int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t gamma, int32_t* tokens_host,
+                 float* scores_host, int32_t* count, atspeed_stats* stats, void* stream);
+
+/* target_generate (code/beamSD.py:544-595): plain tree-mask beam search on the target. */
+int atspeed_target_generate(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t* tokens_host,
+                            float* scores_host, int32_t* count, atspeed_stats* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Introspection for parity tests (reads device state back; synchronises)
+ * ---------------------------------------------------------------------------------------------- */
+enum atspeed_field {
+    ATSPEED_F_LEVEL_CNT = 0,     /* int32[5]                                   */
+    ATSPEED_F_LEVEL_TOK = 1,     /* int32[5][64]   step_beam_tokens            */
+    ATSPEED_F_LEVEL_PARENT = 2,  /* int32[5][64]   step_beam_indices           */
+    ATSPEED_F_LEVEL_SCORE = 3,   /* float[5][64]   beam_scores of each level   */
+    ATSPEED_F_SCALARS = 4,       /* int32[16]                                  */
+    ATSPEED_F_PICK_PARENT = 5,   /* int32[5][32]   verify: target picks per level */
+    ATSPEED_F_PICK_TOK = 6,
+    ATSPEED_F_PICK_SCORE = 7,    /* float[5][32] */
+    ATSPEED_F_HIT_POS = 8,       /* int32[5][32]   draft position of each pick, -1 = miss */
+    ATSPEED_F_NPICK = 9,         /* int32[5] */
+    ATSPEED_F_LOGITS_TARGET = 10,/* float[rows][ld]: last target logits (rows, ld via atspeed_session_info) */
+    ATSPEED_F_LOGITS_DRAFT = 11,
+    ATSPEED_F_ROW_NODE = 12,     /* int32[R_max]   trie node of each logits row of the last batch */
+    ATSPEED_F_LEVEL_NODE = 13    /* int32[5][64] */
+};
+int atspeed_session_read(atspeed_session* s, int32_t field, void* host_dst, size_t bytes, void* stream);
+/* info[0]=logits ld, [1]=R_max, [2]=T_max, [3]=S_max(target), [4]=A_cap, [5]=kernel launches so far,
+ * [6]=rows of the last target batch, [7]=rows of the last draft batch */
+int atspeed_session_info(atspeed_session* s, int64_t* info8);
+
+/* Run one forward of model `model` (0 target, 1 draft) on an explicit batch (all DEVICE arrays): used by the
+ * forward parity tests.  tok/pos/slot/prefix_len int32[T], vis uint32[T][16] relative to slot `vis_base`,
+ * rows_idx int32[R].  Logits land in the session's logits buffer (ATSPEED_F_LOGITS_*). Asynchronous. */
+int atspeed_session_forward_raw(atspeed_session* s, int32_t model, const int32_t* tok, const int32_t* pos,
+                                const int32_t* slot, const int32_t* prefix_len, const uint32_t* vis, int32_t vis_base,
+                                int32_t T, int32_t S, const int32_t* rows_idx, int32_t R, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone kernels (unit parity tests, roofline benches, drop-in use)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Kernel (a): F.log_softmax + PrefixConstrainedLogitsProcessor + per-row top-B (code/beamSD.py:58-78,285-325).
+ * logits: DEVICE [rows, ld], fp32 (logits_bf16 = 0) or bf16 (1); row_node int32[rows] (trie node per row, <0 =
+ * skip); n_rows_dev optional DEVICE scalar limiting the active rows.  Outputs (DEVICE): cand_tok/cand_edge
+ * int32[rows*B], cand_logp float[rows*B] sorted by (logp desc, token asc), cand_cnt int32[rows], lse float[rows]. */
+int atspeed_mask_logsoftmax_topk(const void* logits, int32_t logits_bf16, int32_t rows, int32_t V, int64_t ld,
+                                 const int32_t* row_node, const int32_t* n_rows_dev, const atspeed_trie_desc* trie,
+                                 int32_t B, int32_t* cand_tok, int32_t* cand_edge, float* cand_logp, int32_t* cand_cnt,
+                                 float* lse, void* stream);
+
+/* Kernel (c): row gather with TMA bulk copies.  For p < n_planes, i < rows: copy row_bytes from
+ * src_base + p*src_plane_stride + src_rows[i]*row_bytes to dst_base + p*dst_plane_stride + dst_rows[i]*row_bytes.
+ * Replaces the KV slicing/re-copy of code/beamSD.py:418-429 and HF's index_select cache reorder. */
+int atspeed_kv_gather(const void* src_base, void* dst_base, int64_t src_plane_stride, int64_t dst_plane_stride,
+                      int32_t n_planes, int32_t row_bytes, const int32_t* src_rows, const int32_t* dst_rows,
+                      const int32_t* n_rows_dev, int32_t rows, void* stream);
+
+/* The tcgen05 GEMM of the forward: out[s][t][colbase_i + n] = sum_k x[t][k] * w_i[n][k] (fp32 split-K slices).
+ * x bf16 [T, K]; up to three weights w_i bf16 [rows_i, K]; out fp32 [splits][T][ldo]. */
+int atspeed_gemm_bf16(const void* x, int32_t T, int32_t K, const void* w0, int32_t rows0, const void* w1, int32_t rows1,
+                      const void* w2, int32_t rows2, float* out, int32_t ldo, int32_t splits, void* stream);
+
+/* Tree attention of the forward (see csrc/attention.cu). q/out bf16 [T, n_heads*head_dim]; caches bf16
+ * [S, n_heads*head_dim]; prefix_len int32[T]; vis uint32[T][16] relative to vis_base. */
+int atspeed_tree_attention(const void* q, const void* kcache, const void* vcache, const int32_t* prefix_len,
+                           const uint32_t* vis, int32_t vis_base, int32_t T, int32_t S, int32_t n_heads,
+                           int32_t head_dim, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATSPEED_H */
