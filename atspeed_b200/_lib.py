@@ -52,6 +52,13 @@ SYMBOLS = {
     "atspeed_session_result": (C.c_int, [C.c_void_p, c_i32p, c_f32p, c_i32p, C.c_void_p]),
     "atspeed_bssd": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_f32p, c_i32p,
                                C.POINTER(Stats), C.c_void_p]),
+    "atspeed_bssd_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.POINTER(Stats), C.c_void_p]),
+    "atspeed_session_begin_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "atspeed_session_result_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "atspeed_session_profile": (C.c_int, [C.c_void_p, C.c_int32]),
+    "atspeed_session_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                               C.POINTER(C.c_double), C.c_void_p]),
     "atspeed_target_generate": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, c_i32p, c_f32p, c_i32p,
                                           C.POINTER(Stats), C.c_void_p]),
     "atspeed_session_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),

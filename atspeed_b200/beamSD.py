@@ -127,7 +127,7 @@ def _levels_dict(sess: Session, draft_len: int) -> Dict:
            "step_beam_tokens": tuple(torch.from_numpy(lv["tok"][l, :cnt[l]].astype("int64")) for l in range(1, draft_len + 1)),
            "step_beam_indices": tuple(torch.from_numpy(lv["parent"][l, :cnt[l]].astype("int64")) for l in range(1, draft_len + 1)),
            "step_beam_scores": tuple(torch.from_numpy(lv["score"][l, :cnt[l]].copy()) for l in range(1, draft_len + 1))}
-    V = sess.target.spec.vocab
+    V = sess.target_model.spec.vocab
     out["step_seq_tokens"] = tuple(i * V + t for i, t in zip(out["step_beam_indices"], out["step_beam_tokens"]))
     out["beam_scores"] = out["step_beam_scores"][-1] if draft_len else None
     return out

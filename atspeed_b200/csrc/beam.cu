@@ -43,21 +43,22 @@ int tree_begin(const TreeDev& t, const BatchDev& b, const int* prompt, int P, cu
 // ---------------------------------------------------------------------------------------------
 // forward batch = [prompt] [missing] [levels l_from..l_to]; logits rows = [root row] [levels rows_from..l_to]
 // ---------------------------------------------------------------------------------------------
-__global__ void tree_build_batch_kernel(TreeDev t, BatchDev b, TreeGeom g, BatchPlan plan, int P, int T_cap,
-                                        int R_cap) {
+__global__ void tree_build_batch_kernel(TreeDev t, BatchDev b, TreeGeom g, BatchPlan plan, const int* __restrict__ prompt,
+                                        int P, int T_cap, int R_cap) {
     const int gen0 = t.scal[SC_GEN0];
     const int miss_n = t.scal[SC_MISS];
     const int trash0 = g.tree_slot(P, MAX_LEVELS, 0);    // K trash slots after the last level, for padded entries
     const int n_prompt = plan.with_prompt ? P : 0;
     const int n_miss = plan.with_missing ? g.K : 0;
     for (int x = threadIdx.x; x < T_cap; x += blockDim.x) {
-        if (x < n_prompt) continue;                       // prompt entries were written by tree_begin
         int tok = 0, pos = 0, slot = 0, prefix = 0;
         uint32_t vis[VIS_WORDS];
 #pragma unroll
         for (int w = 0; w < VIS_WORDS; ++w) vis[w] = 0u;
         int y = x - n_prompt;
-        if (y < n_miss) {
+        if (x < n_prompt) {                               // causal prompt token (the batch arrays are reused by every forward)
+            tok = prompt[x]; pos = x; slot = x; prefix = x + 1;
+        } else if (y < n_miss) {
             if (y < miss_n) {
                 tok = t.miss_tok[y]; pos = t.miss_pos[y]; slot = t.miss_slot[y]; prefix = P;
 #pragma unroll
@@ -112,9 +113,9 @@ __global__ void tree_build_batch_kernel(TreeDev t, BatchDev b, TreeGeom g, Batch
     }
 }
 
-int tree_build_batch(const TreeDev& t, const BatchDev& b, const TreeGeom& g, const BatchPlan& plan, int P, int T_cap,
-                     int R_cap, cudaStream_t st) {
-    tree_build_batch_kernel<<<1, 256, 0, st>>>(t, b, g, plan, P, T_cap, R_cap);
+int tree_build_batch(const TreeDev& t, const BatchDev& b, const TreeGeom& g, const BatchPlan& plan, const int* prompt,
+                     int P, int T_cap, int R_cap, cudaStream_t st) {
+    tree_build_batch_kernel<<<1, 256, 0, st>>>(t, b, g, plan, prompt, P, T_cap, R_cap);
     ATS_LAUNCH_CHECK();
     return ATS_OK;
 }

@@ -66,8 +66,8 @@ struct BatchPlan {
     int rows_from;     // first level whose tokens produce logits rows; with_prompt adds the root row (P-1)
     int root_row;      // 1: emit the prompt's last position as row 0 (first round)
 };
-int tree_build_batch(const TreeDev& t, const BatchDev& b, const TreeGeom& g, const BatchPlan& plan, int P, int T_cap,
-                     int R_cap, cudaStream_t st);
+int tree_build_batch(const TreeDev& t, const BatchDev& b, const TreeGeom& g, const BatchPlan& plan, const int* prompt,
+                     int P, int T_cap, int R_cap, cudaStream_t st);
 // level l+1 = top-`width` of (logp + parent score) over the rows of level l
 int tree_select(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int level, int row0, int B,
                 const int* cand_tok, const int* cand_edge, const float* cand_logp, const int* cand_cnt, int width,

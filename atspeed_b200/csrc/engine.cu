@@ -77,9 +77,43 @@ struct atspeed_session {
     int num_sms;
     int* pinned;          // pinned host scratch
     long long launches;
+    // optional per-launch CUDA-event timing (bench.py roofline / share-of-step); off by default
+    bool prof_on;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_cat;
+    int prof_n;
+    double prof_bytes[6];
 };
 
 namespace atspeed {
+
+enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ELEM = 2, CAT_TOPK = 3, CAT_BEAM = 4, CAT_GATHER = 5, CAT_COUNT = 6 };
+static constexpr int PROF_PAIRS = 16384;
+
+static inline void prof_begin(atspeed_session* s, int cat, double bytes, cudaStream_t st) {
+    if (!s->prof_on || s->prof_n >= PROF_PAIRS) return;
+    s->prof_cat[s->prof_n] = cat;
+    s->prof_bytes[cat] += bytes;
+    cudaEventRecord(s->prof_ev[2 * s->prof_n], st);
+}
+static inline void prof_end(atspeed_session* s, cudaStream_t st) {
+    if (!s->prof_on || s->prof_n >= PROF_PAIRS) return;
+    cudaEventRecord(s->prof_ev[2 * s->prof_n + 1], st);
+    s->prof_n++;
+}
+#define PROF(s, cat, bytes, call)              \
+    do {                                       \
+        prof_begin(s, cat, bytes, st);         \
+        ATS_TRY(call);                         \
+        prof_end(s, st);                       \
+    } while (0)
+
+static double gemm_bytes(const GemmWeights& g, int T) {
+    double rows = 0;
+    for (int i = 0; i < g.n; ++i) rows += g.rows[i];
+    // algorithmic traffic: every weight once, the bf16 activations once, a bf16 result once
+    return 2.0 * (rows * g.K + static_cast<double>(T) * g.K + static_cast<double>(T) * rows);
+}
 
 static size_t part_elems(const atspeed_model_desc& d, int T_max, int num_sms) {
     const int HD = d.n_heads * d.head_dim;
@@ -230,31 +264,39 @@ static int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, in
     ATS_CHECK_ARG(R >= 1 && R <= s->R_max, "forward: R=%d exceeds R_max=%d", R, s->R_max);
     ATS_CHECK_ARG(S <= s->S_max, "forward: S=%d exceeds S_max=%d", S, s->S_max);
     const auto* embed = static_cast<const __nv_bfloat16*>(d.embed);
-    ATS_TRY(embed_rows(embed, b.tok, T, d.hidden, d.vocab, m.h, st));
-    ATS_TRY(rmsnorm_rows(m.h, m.layers[0].ln1, T, d.hidden, d.rms_eps, m.x, nullptr, st));
+    PROF(s, CAT_ELEM, 0, embed_rows(embed, b.tok, T, d.hidden, d.vocab, m.h, st));
+    PROF(s, CAT_ELEM, 0, rmsnorm_rows(m.h, m.layers[0].ln1, T, d.hidden, d.rms_eps, m.x, nullptr, st));
     s->launches += 2;
     for (int l = 0; l < d.n_layers; ++l) {
         LayerRT& L = m.layers[l];
         __nv_bfloat16* kc = m.kv + static_cast<long long>(l) * 2 * m.kv_plane;
         __nv_bfloat16* vc = kc + m.kv_plane;
         const int c_qkv = 3 * m.HD, c_gu = 2 * d.mlp;
-        ATS_TRY(gemm_wx(L.qkv, m.x, T, m.part, c_qkv, static_cast<long long>(T) * c_qkv, L.s_qkv, st));
-        ATS_TRY(qkv_rope_append(m.part, L.s_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
-                                d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
-        ATS_TRY(tree_attention(m.q, kc, vc, b, T, S, d.n_heads, d.head_dim, m.a, st));
-        ATS_TRY(gemm_wx(L.o, m.a, T, m.part, d.hidden, static_cast<long long>(T) * d.hidden, L.s_o, st));
-        ATS_TRY(residual_rmsnorm(m.h, m.part, L.s_o, static_cast<long long>(T) * d.hidden, d.hidden, L.ln2, T, d.hidden,
-                                 d.rms_eps, m.x, st));
-        ATS_TRY(gemm_wx(L.gu, m.x, T, m.part, c_gu, static_cast<long long>(T) * c_gu, L.s_gu, st));
-        ATS_TRY(silu_mul(m.part, L.s_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
-        ATS_TRY(gemm_wx(L.down, m.m, T, m.part, d.hidden, static_cast<long long>(T) * d.hidden, L.s_down, st));
+        PROF(s, CAT_GEMM, gemm_bytes(L.qkv, T),
+             gemm_wx(L.qkv, m.x, T, m.part, c_qkv, static_cast<long long>(T) * c_qkv, L.s_qkv, st));
+        PROF(s, CAT_ELEM, 0,
+             qkv_rope_append(m.part, L.s_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
+                             d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
+        PROF(s, CAT_ATTN, 0, tree_attention(m.q, kc, vc, b, T, S, d.n_heads, d.head_dim, m.a, st));
+        PROF(s, CAT_GEMM, gemm_bytes(L.o, T),
+             gemm_wx(L.o, m.a, T, m.part, d.hidden, static_cast<long long>(T) * d.hidden, L.s_o, st));
+        PROF(s, CAT_ELEM, 0,
+             residual_rmsnorm(m.h, m.part, L.s_o, static_cast<long long>(T) * d.hidden, d.hidden, L.ln2, T, d.hidden,
+                              d.rms_eps, m.x, st));
+        PROF(s, CAT_GEMM, gemm_bytes(L.gu, T),
+             gemm_wx(L.gu, m.x, T, m.part, c_gu, static_cast<long long>(T) * c_gu, L.s_gu, st));
+        PROF(s, CAT_ELEM, 0, silu_mul(m.part, L.s_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
+        PROF(s, CAT_GEMM, gemm_bytes(L.down, T),
+             gemm_wx(L.down, m.m, T, m.part, d.hidden, static_cast<long long>(T) * d.hidden, L.s_down, st));
         const __nv_bfloat16* next_ln = l + 1 < d.n_layers ? m.layers[l + 1].ln1 : nullptr;
-        ATS_TRY(residual_rmsnorm(m.h, m.part, L.s_down, static_cast<long long>(T) * d.hidden, d.hidden, next_ln, T,
-                                 d.hidden, d.rms_eps, m.x, st));
+        PROF(s, CAT_ELEM, 0,
+             residual_rmsnorm(m.h, m.part, L.s_down, static_cast<long long>(T) * d.hidden, d.hidden, next_ln, T,
+                              d.hidden, d.rms_eps, m.x, st));
         s->launches += 9;
     }
-    ATS_TRY(rmsnorm_rows(m.h, static_cast<const __nv_bfloat16*>(d.final_norm), R, d.hidden, d.rms_eps, m.xsel, rows_idx, st));
-    ATS_TRY(gemm_wx(m.lm, m.xsel, R, m.logits, m.ldl, 0, 1, st));
+    PROF(s, CAT_ELEM, 0,
+         rmsnorm_rows(m.h, static_cast<const __nv_bfloat16*>(d.final_norm), R, d.hidden, d.rms_eps, m.xsel, rows_idx, st));
+    PROF(s, CAT_GEMM, gemm_bytes(m.lm, R), gemm_wx(m.lm, m.xsel, R, m.logits, m.ldl, 0, 1, st));
     s->launches += 2;
     m.last_rows = R;
     m.forwards++;
@@ -269,8 +311,9 @@ static BatchDesc batch_desc(const atspeed_session* s) {
 }
 
 static int run_topk(atspeed_session* s, ModelRT& m, int R, int B, cudaStream_t st) {
-    ATS_TRY(mask_logsoftmax_topk(m.logits, 0, R, m.d.vocab, m.ldl, s->batch.row_node, nullptr, s->trie, B, s->cand_tok,
-                                 s->cand_edge, s->cand_logp, s->cand_cnt, s->lse, st));
+    PROF(s, CAT_TOPK, static_cast<double>(R) * m.d.vocab * 4.0,
+         mask_logsoftmax_topk(m.logits, 0, R, m.d.vocab, m.ldl, s->batch.row_node, nullptr, s->trie, B, s->cand_tok,
+                              s->cand_edge, s->cand_logp, s->cand_cnt, s->lse, st));
     s->launches += 1;
     return ATS_OK;
 }
@@ -294,12 +337,12 @@ static int search_step(atspeed_session* s, ModelRT& m, int level, int width, boo
         T = (with_missing ? g.K : 0) + cap; R = cap;
         S = g.tree_slot(P, level, 0) + cap;
     }
-    ATS_TRY(tree_build_batch(s->tree, s->batch, g, plan, P, T, R, st));
+    PROF(s, CAT_BEAM, 0, tree_build_batch(s->tree, s->batch, g, plan, s->prompt_dev, P, T, R, st));
     s->launches += 1;
     ATS_TRY(forward(s, m, batch_desc(s), T, S, s->batch.rows_idx, R, st));
     ATS_TRY(run_topk(s, m, R, width, st));
-    ATS_TRY(tree_select(s->tree, g, s->trie, level, 0, width, s->cand_tok, s->cand_edge, s->cand_logp, s->cand_cnt, width,
-                        P, st));
+    PROF(s, CAT_BEAM, 0,
+         tree_select(s->tree, g, s->trie, level, 0, width, s->cand_tok, s->cand_edge, s->cand_logp, s->cand_cnt, width, P, st));
     s->launches += 1;
     return ATS_OK;
 }
@@ -364,6 +407,9 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
     memset(s->pinned, 0, 64 * sizeof(int));
     s->P = 0;
     s->launches = 0;
+    s->prof_on = false;
+    s->prof_n = 0;
+    for (double& b : s->prof_bytes) b = 0;
     *out = s;
     return ATS_OK;
 }
@@ -371,6 +417,7 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
 int atspeed_session_destroy(atspeed_session* s) {
     if (!s) return ATS_OK;
     if (s->pinned) cudaFreeHost(s->pinned);
+    for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     delete s;
     return ATS_OK;
 }
@@ -384,11 +431,68 @@ int atspeed_session_begin(atspeed_session* s, const int32_t* prompt_host, int32_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     s->P = P;
     ATS_CUDA(cudaMemcpyAsync(s->prompt_dev, prompt_host, sizeof(int) * P, cudaMemcpyHostToDevice, st));
-    ATS_TRY(tree_begin(s->tree, s->batch, s->prompt_dev, P, st));
+    PROF(s, CAT_BEAM, 0, tree_begin(s->tree, s->batch, s->prompt_dev, P, st));
     s->launches += 1;
     s->pinned[H_FIRST] = 1;    // first
     s->pinned[H_MISS] = 0;    // missing ancestors pending for the draft
     s->pinned[H_LEVEL] = 0;   // result level
+    return ATS_OK;
+}
+
+int atspeed_session_begin_device(atspeed_session* s, const int32_t* prompt_dev, int32_t P, void* stream) {
+    ATS_CHECK_ARG(s && prompt_dev, "null session/prompt");
+    ATS_CHECK_ARG(P >= 1 && P <= s->cfg.max_prompt, "prompt length %d outside [1,%d]", P, s->cfg.max_prompt);
+    const int dl_max = s->cfg.max_new_tokens - 1;
+    ATS_CHECK_ARG(P + dl_max * s->cfg.N <= s->T_max && P + s->cfg.K <= s->T_max,
+                  "prompt length %d + %d tree tokens exceeds the %d-token forward limit", P, dl_max * s->cfg.N, s->T_max);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    s->P = P;
+    ATS_CUDA(cudaMemcpyAsync(s->prompt_dev, prompt_dev, sizeof(int) * P, cudaMemcpyDeviceToDevice, st));
+    PROF(s, CAT_BEAM, 0, tree_begin(s->tree, s->batch, s->prompt_dev, P, st));
+    s->launches += 1;
+    s->pinned[H_FIRST] = 1;
+    s->pinned[H_MISS] = 0;
+    s->pinned[H_LEVEL] = 0;
+    return ATS_OK;
+}
+
+int atspeed_session_result_device(atspeed_session* s, int32_t* tokens_dev, float* scores_dev, void* stream) {
+    ATS_CHECK_ARG(s && tokens_dev && scores_dev, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int level = s->pinned[H_LEVEL];
+    // [K][MAX_NEW] generated tokens and [K] scores of the current beams, device to device, no synchronisation
+    ATS_CUDA(cudaMemcpyAsync(tokens_dev, s->tree.gen + static_cast<size_t>(level) * MAX_BEAMS * MAX_NEW,
+                             sizeof(int) * s->cfg.K * MAX_NEW, cudaMemcpyDeviceToDevice, st));
+    ATS_CUDA(cudaMemcpyAsync(scores_dev, s->tree.score + static_cast<size_t>(level) * MAX_BEAMS, sizeof(float) * s->cfg.K,
+                             cudaMemcpyDeviceToDevice, st));
+    return ATS_OK;
+}
+
+int atspeed_session_profile(atspeed_session* s, int32_t enable) {
+    ATS_CHECK_ARG(s, "null session");
+    if (enable && s->prof_ev.empty()) {
+        s->prof_ev.resize(2 * PROF_PAIRS);
+        s->prof_cat.resize(PROF_PAIRS);
+        for (cudaEvent_t& e : s->prof_ev) ATS_CUDA(cudaEventCreate(&e));
+    }
+    s->prof_on = enable != 0;
+    s->prof_n = 0;
+    for (double& b : s->prof_bytes) b = 0;
+    return ATS_OK;
+}
+
+int atspeed_session_profile_read(atspeed_session* s, double* ms6, int64_t* count6, double* bytes6, void* stream) {
+    ATS_CHECK_ARG(s && ms6 && count6 && bytes6, "null argument");
+    ATS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    for (int c = 0; c < CAT_COUNT; ++c) { ms6[c] = 0; count6[c] = 0; bytes6[c] = s->prof_bytes[c]; }
+    for (int i = 0; i < s->prof_n; ++i) {
+        float ms = 0.f;
+        ATS_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[2 * i], s->prof_ev[2 * i + 1]));
+        ms6[s->prof_cat[i]] += ms;
+        count6[s->prof_cat[i]] += 1;
+    }
+    s->prof_n = 0;
+    for (double& b : s->prof_bytes) b = 0;
     return ATS_OK;
 }
 
@@ -420,7 +524,7 @@ int atspeed_session_target(atspeed_session* s, int32_t draft_len, void* stream) 
         T = g.K + draft_len * g.N; R = T;
     }
     const int S = g.tree_slot(P, draft_len, 0) + g.N;
-    ATS_TRY(tree_build_batch(s->tree, s->batch, g, plan, P, T, R, st));
+    PROF(s, CAT_BEAM, 0, tree_build_batch(s->tree, s->batch, g, plan, s->prompt_dev, P, T, R, st));
     s->launches += 1;
     ATS_TRY(forward(s, s->tgt, batch_desc(s), T, S, s->batch.rows_idx, R, st));
     ATS_TRY(run_topk(s, s->tgt, R, g.K, st));
@@ -432,14 +536,16 @@ int atspeed_session_verify(atspeed_session* s, int32_t draft_len, int32_t* n_mat
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const TreeGeom& g = s->geom;
     const bool first = s->pinned[H_FIRST] != 0;
-    ATS_TRY(tree_verify_strict(s->tree, g, s->trie, draft_len, first ? 1 : g.K, s->cand_tok, s->cand_edge, s->cand_logp,
-                               s->cand_cnt, s->P, st));
+    PROF(s, CAT_BEAM, 0,
+         tree_verify_strict(s->tree, g, s->trie, draft_len, first ? 1 : g.K, s->cand_tok, s->cand_edge, s->cand_logp,
+                            s->cand_cnt, s->P, st));
     // kernel (c): move the survivors' ancestor rows into the accepted region, both caches, all layers
     const int max_rows = (draft_len + 1) * g.K;
     for (ModelRT* m : {&s->tgt, s->has_draft ? &s->dft : nullptr}) {
         if (!m) continue;
-        ATS_TRY(kv_gather_rows(m->kv, m->kv_plane * 2 /*bytes per element*/, m->d.n_layers * 2, m->HD * 2, s->tree.gather_src,
-                               s->tree.gather_dst, s->tree.scal + SC_GATHER, max_rows, st));
+        PROF(s, CAT_GATHER, 0,
+             kv_gather_rows(m->kv, m->kv_plane * 2 /*bytes per element*/, m->d.n_layers * 2, m->HD * 2, s->tree.gather_src,
+                            s->tree.gather_dst, s->tree.scal + SC_GATHER, max_rows, st));
         s->launches += 1;
     }
     s->launches += 1;
@@ -487,13 +593,7 @@ int atspeed_session_result(atspeed_session* s, int32_t* tokens_host, float* scor
     return ATS_OK;
 }
 
-int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t gamma, int32_t* tokens_host,
-                 float* scores_host, int32_t* count, atspeed_stats* stats, void* stream) {
-    ATS_CHECK_ARG(s && s->has_draft, "session has no draft model");
-    ATS_CHECK_ARG(gamma >= 1, "gamma=%d", gamma);
-    const long long l0 = s->launches;
-    const int tf0 = s->tgt.forwards, df0 = s->dft.forwards;
-    ATS_TRY(atspeed_session_begin(s, prompt_host, P, stream));
+static int bssd_loop(atspeed_session* s, int32_t gamma, atspeed_stats* stats, long long l0, int tf0, int df0, void* stream) {
     const int L = s->cfg.max_new_tokens;
     int done = 0, n_run = 0, total = 0;
     int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -513,7 +613,6 @@ int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int3
         ++n_run;
         total += m;
     }
-    ATS_TRY(atspeed_session_result(s, tokens_host, scores_host, count, stream));
     if (stats) {
         stats->n_run = n_run;
         stats->total_accept_steps = total;
@@ -523,6 +622,28 @@ int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int3
         stats->kernel_launches = static_cast<int>(s->launches - l0);
     }
     return ATS_OK;
+}
+
+int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t gamma, int32_t* tokens_host,
+                 float* scores_host, int32_t* count, atspeed_stats* stats, void* stream) {
+    ATS_CHECK_ARG(s && s->has_draft, "session has no draft model");
+    ATS_CHECK_ARG(gamma >= 1, "gamma=%d", gamma);
+    const long long l0 = s->launches;
+    const int tf0 = s->tgt.forwards, df0 = s->dft.forwards;
+    ATS_TRY(atspeed_session_begin(s, prompt_host, P, stream));
+    ATS_TRY(bssd_loop(s, gamma, stats, l0, tf0, df0, stream));
+    return atspeed_session_result(s, tokens_host, scores_host, count, stream);
+}
+
+int atspeed_bssd_device(atspeed_session* s, const int32_t* prompt_dev, int32_t P, int32_t gamma, int32_t* tokens_dev,
+                        float* scores_dev, atspeed_stats* stats, void* stream) {
+    ATS_CHECK_ARG(s && s->has_draft, "session has no draft model");
+    ATS_CHECK_ARG(gamma >= 1, "gamma=%d", gamma);
+    const long long l0 = s->launches;
+    const int tf0 = s->tgt.forwards, df0 = s->dft.forwards;
+    ATS_TRY(atspeed_session_begin_device(s, prompt_dev, P, stream));
+    ATS_TRY(bssd_loop(s, gamma, stats, l0, tf0, df0, stream));
+    return atspeed_session_result_device(s, tokens_dev, scores_dev, stream);
 }
 
 int atspeed_target_generate(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t* tokens_host,

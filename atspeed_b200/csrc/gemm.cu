@@ -300,11 +300,15 @@ int gemm_wx(const GemmWeights& w, const void* x, int T, float* out, int ldo, lon
     ATS_TRY(make_tmap_bf16_kmajor(&tmX, x, T, w.K, p.T_pad > 256 ? 256 : p.T_pad));
     ATS_TRY(make_tmap_bf16_kmajor(&tmX1, x, T, w.K, p.T_pad > 256 ? p.T_pad - 256 : 16));
     const size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ATS_CUDA(cudaFuncSetAttribute(gemm_wx_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+    static int max_dyn = 0;
+    if (!max_dyn) {
+        cudaFuncAttributes fa;
+        ATS_CUDA(cudaFuncGetAttributes(&fa, gemm_wx_tcgen05));
+        const int want = 227 * 1024 - static_cast<int>(fa.sharedSizeBytes);   // static barriers share the 227 KiB budget
+        ATS_CUDA(cudaFuncSetAttribute(gemm_wx_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+        max_dyn = want;
     }
+    ATS_CHECK_ARG(static_cast<int>(smem_bytes) <= max_dyn, "gemm: %zu bytes of shared memory > %d", smem_bytes, max_dyn);
     dim3 grid(total_tiles, splits);
     gemm_wx_tcgen05<<<grid, GEMM_THREADS, smem_bytes, stream>>>(w.tmap[0], w.tmap[w.n > 1 ? 1 : 0],
                                                                   w.tmap[w.n > 2 ? 2 : 0], tmX, tmX1, p);

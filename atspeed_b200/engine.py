@@ -135,7 +135,7 @@ class Session:
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.AtSpeedError("atspeed_b200 needs a CUDA device (sm_100a); there is no CPU path")
-        self.target, self.draft, self.trie = target, draft, trie
+        self.target_model, self.draft_model, self.trie = target, draft, trie
         self.K, self.N, self.L = K, N, max_new_tokens
         if max_prompt is None:
             max_prompt = 512 - max(max_new_tokens - 1, 1) * N
@@ -192,6 +192,24 @@ class Session:
             _lib.check(self.lib.atspeed_bssd(self.handle, ptr, P, gamma, self._tok, self._sc, C.byref(self._cnt),
                                              C.byref(st), self._stream()))
         return self._collect(st)
+
+    def bssd_device(self, prompt_dev: torch.Tensor, gamma: int, tokens_dev: torch.Tensor, scores_dev: torch.Tensor) -> Dict:
+        """Prompt (int32 CUDA tensor) and results (int32 [K,6], fp32 [K] CUDA tensors) stay in HBM."""
+        st = _lib.Stats()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.atspeed_bssd_device(self.handle, prompt_dev.data_ptr(), int(prompt_dev.shape[0]), gamma,
+                                                    tokens_dev.data_ptr(), scores_dev.data_ptr(), C.byref(st), self._stream()))
+        return {"n_run": st.n_run, "total_accept_steps": st.total_accept_steps, "target_forwards": st.target_forwards,
+                "draft_forwards": st.draft_forwards, "kernel_launches": st.kernel_launches}
+
+    def profile(self, enable: bool):
+        _lib.check(self.lib.atspeed_session_profile(self.handle, 1 if enable else 0))
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        ms, cnt, by = (C.c_double * 6)(), (C.c_int64 * 6)(), (C.c_double * 6)()
+        _lib.check(self.lib.atspeed_session_profile_read(self.handle, ms, cnt, by, self._stream()))
+        names = ("gemm", "attention", "rowwise", "topk", "beam", "kvgather")
+        return {n: {"ms": ms[i], "launches": int(cnt[i]), "bytes": by[i]} for i, n in enumerate(names)}
 
     def target_generate(self, prompt_ids: Sequence[int]) -> Dict:
         arr, ptr, P = self._prompt(prompt_ids)
@@ -253,7 +271,7 @@ class Session:
 
     def logits(self, model: int, rows: int) -> np.ndarray:
         full = self.read(_lib.F_LOGITS_TARGET if model == 0 else _lib.F_LOGITS_DRAFT, (rows, self.ldl), np.float32)
-        return full[:, : self.target.spec.vocab]
+        return full[:, : self.target_model.spec.vocab]
 
     def forward_raw(self, model: int, tok, pos, slot, prefix_len, vis, vis_base: int, S: int, rows_idx):
         """tok/pos/slot/prefix_len int32 CUDA tensors [T], vis int32 CUDA [T,16], rows_idx int32 CUDA [R]."""

@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the atspeed_b200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): LLaMA-7B-shape target + LLaMA-68M-shape draft (random-init bf16
+weights), AtSpeed-S strict top-K verify, Beauty test users, K=10 target beams, N=40 draft beams, gamma=3,
+4 new tokens, strict item trie.  A "step" = one batch of `--users-per-step` users, each taken through the
+whole speculative beam search (reference code/beamSD.py:458-542).  metric = ranked top-K lists produced
+per second over the whole job ("users/s").
+
+  value : prompts already resident in HBM, results left in HBM (atspeed_bssd_device); timed with CUDA
+          events on the launching stream between barriers, max over ranks.
+  e2e   : same users through the host-buffer C ABI call (atspeed_bssd): prompt ids copied host->device and
+          ranked lists + scores device->host inside the timed region.
+  roofline : the dominant kernel (the tcgen05 GEMM): algorithmic bytes / CUDA-event duration per launch,
+          measured in a second pass over the same users with per-launch events enabled (the first pass stays
+          unperturbed), against MEASURED_PEAKS.json.
+  cpu_baseline : oracle port (oracle/bssd_ref.py + oracle/llama_ref.py) on the host cores, bounded sample.
+
+Ranks shard users (rank r takes users r, r+W, ...); the only collective is one all-gather of the ranked
+lists per step.  `--impl reference` times the CPU oracle port alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPES = {"7b": dict(hidden=4096, n_layers=32, n_heads=32, mlp=11008),
+          "68m": dict(hidden=768, n_layers=2, n_heads=12, mlp=3072),
+          "small": dict(hidden=256, n_layers=2, n_heads=4, mlp=512),
+          "small_draft": dict(hidden=128, n_layers=1, n_heads=2, mlp=256)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="atspeed", choices=["atspeed", "reference"])
+    ap.add_argument("--users-per-step", type=int, default=8)
+    ap.add_argument("--dataset", default="beauty")
+    ap.add_argument("--K", type=int, default=10)
+    ap.add_argument("--N", type=int, default=40)
+    ap.add_argument("--gamma", type=int, default=3)
+    ap.add_argument("--target", default="7b")
+    ap.add_argument("--draft", default="68m")
+    ap.add_argument("--constraint", default="strict", choices=["strict", "positional"])
+    ap.add_argument("--profile-users", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hf-baseline-users", type=int, default=0, help="also time HF generate(num_beams=K) on the GPU")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"LLaMA-{a.target}-shape target + LLaMA-{a.draft}-shape draft, AtSpeed-S strict top-K verify, "
+            f"{a.dataset} test users, {a.constraint} constraint, K={a.K} N={a.N} gamma={a.gamma} max_new_tokens=4, "
+            f"{a.users_per_step} users/step/GPU, batch 1 per search (as the reference)")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------------
+def gpu_weights(spec, seed, device):
+    g = torch.Generator(device=device).manual_seed(seed)
+    r = lambda *s: (torch.randn(*s, generator=g, device=device, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+    hd = spec.n_heads * spec.head_dim
+    W = {"embed": r(spec.vocab, spec.hidden), "norm": torch.ones(spec.hidden, device=device, dtype=torch.bfloat16),
+         "lm_head": r(spec.vocab, spec.hidden), "layers": []}
+    for _ in range(spec.n_layers):
+        W["layers"].append({"wq": r(hd, spec.hidden), "wk": r(hd, spec.hidden), "wv": r(hd, spec.hidden),
+                            "wo": r(spec.hidden, hd), "wg": r(spec.mlp, spec.hidden), "wu": r(spec.mlp, spec.hidden),
+                            "wd": r(spec.hidden, spec.mlp),
+                            "ln1": torch.ones(spec.hidden, device=device, dtype=torch.bfloat16),
+                            "ln2": torch.ones(spec.hidden, device=device, dtype=torch.bfloat16)})
+    return W
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU oracle port (cpu_baseline, --impl reference)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_models(a, vocab):
+    """Oracle models of the benchmark shapes on the host.  Timing does not depend on weight values, so the
+    decoder layers share one set of random tensors (keeps the 7B shape at ~2 GB instead of 27 GB)."""
+    from oracle import llama_ref as LR
+    out = []
+    for name, seed in ((a.target, 1), (a.draft, 2)):
+        s = SHAPES[name]
+        sh = LR.LlamaShape(vocab, s["hidden"], 1, s["n_heads"], s["mlp"])
+        W = LR.make_weights(sh, seed, std=0.02)
+        W["layers"] = W["layers"] * s["n_layers"]
+        sh.n_layers = s["n_layers"]
+        out.append(LR.RefLlama(sh, W, "fp32"))
+    return out
+
+
+def cpu_one_user(a, models, ds, fn, u):
+    from oracle import bssd_ref
+    t0 = time.perf_counter()
+    res = bssd_ref.bssd(models[0], models[1], ds.prompt_ids(u), a.K, a.N, a.gamma, 4, fn)
+    return time.perf_counter() - t0, res
+
+
+def make_fn(ds, kind):
+    from atspeed_b200.generation_trie import (Trie, positional_prefix_allowed_tokens_fn, suffix_prefix_allowed_tokens_fn)
+    from atspeed_b200.prompts import RESPONSE_SEP
+    if kind == "strict":
+        return suffix_prefix_allowed_tokens_fn(Trie(ds.strict_trie_sequences()), RESPONSE_SEP)
+    return positional_prefix_allowed_tokens_fn(ds.positional_allowed(), RESPONSE_SEP)
+
+
+def reference_arm(a, rank):
+    if rank != 0:
+        return
+    from atspeed_b200.prompts import load_dataset
+    ds = load_dataset(a.dataset)
+    fn = make_fn(ds, a.constraint)
+    models = cpu_models(a, ds.vocab_size)
+    users = list(range(ds.n_users))
+    for w in range(a.warmup):
+        cpu_one_user(a, models, ds, fn, users[w % len(users)])
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        cpu_one_user(a, models, ds, fn, users[(a.warmup + s) % len(users)])
+    dt = time.perf_counter() - t0
+    val = a.steps / dt
+    cores = torch.get_num_threads()
+    sample = "1 user per step (bounded sample of the per-step user batch); oracle port, fp32, layer weights shared across layers"
+    print(json.dumps({"impl": "reference", "metric": "topk_recs_per_sec", "value": val, "unit": "users/s", "n_gpus": a.gpus,
+                      "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": workload_name(a)},
+                      "cpu_baseline": {"value": val, "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ---------------------------------------------------------------------------------------------------------
+def atspeed_arm(a, rank, world, local_rank):
+    import torch.distributed as dist
+    from atspeed_b200 import _lib
+    from atspeed_b200.constraint import compile_constraint
+    from atspeed_b200.engine import DeviceModel, DeviceTrie, ModelSpec, Session
+    from atspeed_b200.prompts import load_dataset
+    from atspeed_b200.runner import shard_users
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    ds = load_dataset(a.dataset)
+    V = ds.vocab_size
+    fn = make_fn(ds, a.constraint)
+    specs = []
+    for name in (a.target, a.draft):
+        s = SHAPES[name]
+        specs.append(ModelSpec(V, s["hidden"], s["n_layers"], s["n_heads"], s["hidden"] // s["n_heads"], s["mlp"]))
+    tdm = DeviceModel(specs[0], gpu_weights(specs[0], 1, dev), dev)
+    ddm = DeviceModel(specs[1], gpu_weights(specs[1], 2, dev), dev)
+    csr = compile_constraint(fn, ds.prompt_ids(0), 4, other_prompt=ds.prompt_ids(1))
+    sess = Session(tdm, ddm, DeviceTrie(csr, dev), a.K, a.N, 4)
+    U = a.users_per_step
+    mine = shard_users(list(range(ds.n_users)), rank, world)
+    n_steps_total = a.warmup + a.steps
+    step_users = [[mine[(s * U + i) % len(mine)] for i in range(U)] for s in range(n_steps_total)]
+    prompts_host = {u: ds.prompt_ids(u) for us in step_users for u in us}
+    prompts_dev = {u: torch.tensor(p, dtype=torch.int32, device=dev) for u, p in prompts_host.items()}
+    tok_dev = torch.zeros(U, a.K, _lib.MAX_NEW, dtype=torch.int32, device=dev)
+    sc_dev = torch.zeros(U, a.K, dtype=torch.float32, device=dev)
+    gathered = [torch.zeros_like(tok_dev) for _ in range(world)] if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device(s):
+        launches = accept = runs = 0
+        for i, u in enumerate(step_users[s]):
+            st = sess.bssd_device(prompts_dev[u], a.gamma, tok_dev[i], sc_dev[i])
+            launches += st["kernel_launches"]; accept += st["total_accept_steps"]; runs += st["n_run"]
+        if world > 1:   # the one collective of the path: ranked lists of every rank, over NVLink
+            dist.all_gather(gathered, tok_dev)
+        return launches, accept, runs
+
+    def step_host(s):
+        lat, items = [], []
+        for u in step_users[s]:
+            t0 = time.perf_counter()
+            out = sess.bssd(prompts_host[u], a.gamma)
+            lat.append(time.perf_counter() - t0)
+            items.append(out["tokens"])
+        if world > 1:
+            t = torch.from_numpy(np.stack(items)).to(dev)
+            dist.all_gather([torch.empty_like(t) for _ in range(world)], t)
+        return lat
+
+    # ---- device-resident pass (value) ----
+    for s in range(a.warmup):
+        step_device(s)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = accept = runs = 0
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for s in range(a.warmup, n_steps_total):
+            l, ac, rn = step_device(s)
+            launches += l; accept += ac; runs += rn
+        ev1.record()
+        barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    # ---- host-buffer pass (e2e) ----
+    for s in range(min(a.warmup, 1)):
+        step_host(s)
+    barrier()
+    t0 = time.perf_counter()
+    lat = []
+    for s in range(a.warmup, n_steps_total):
+        lat += step_host(s)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    h2d = int(np.mean([sum(len(prompts_host[u]) * 4 for u in step_users[s]) for s in range(a.warmup, n_steps_total)]))
+    d2h = U * (a.K * 4 * 4 + a.K * 4) + int(round(runs / max(a.steps, 1))) * 64
+    # ---- profiled pass (roofline of the dominant kernel, share of step per kernel group) ----
+    roofline, groups = None, None
+    if rank == 0:
+        sess.profile(True)
+        for u in step_users[a.warmup][: max(1, a.profile_users)]:
+            sess.bssd_device(prompts_dev[u], a.gamma, tok_dev[0], sc_dev[0])
+        prof = sess.profile_read()
+        sess.profile(False)
+        tot = sum(v["ms"] for v in prof.values())
+        groups = {k: {"ms_per_user": v["ms"] / max(1, a.profile_users), "launches_per_user": v["launches"] / max(1, a.profile_users),
+                      "share": v["ms"] / tot if tot else 0.0} for k, v in prof.items()}
+        g = prof["gemm"]
+        peak, how = peaks()
+        ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] else 0.0
+        roofline = {"kernel": "gemm_wx_tcgen05", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": how,
+                    "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]), "launches": g["launches"],
+                    "algorithmic_bytes_per_launch": g["bytes"] / max(1, g["launches"])}
+    users_total = world * U * a.steps
+    out = {"metric": "topk_recs_per_sec", "value": users_total / (ms_total * 1e-3), "unit": "users/s", "n_gpus": world,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (13.5 GB of weights streamed per forward)",
+                      "parallelism": f"user-sharded x{world}, one all-gather of ranked lists per step"},
+           "clocks": clocks.summary(),
+           "e2e": {"value": users_total / float(e2e_s.item()), "unit": "users/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches),
+           "latency_ms_p50": float(np.percentile(np.asarray(lat) * 1e3, 50)),
+           "latency_ms_p95": float(np.percentile(np.asarray(lat) * 1e3, 95)),
+           "accepted_tokens_per_verify": accept * a.K / max(1, runs),
+           "kernel_groups": groups, "roofline": roofline}
+    if rank == 0:
+        if world == 1 and not a.no_cpu_baseline:
+            models = cpu_models(a, V)
+            dt, _ = cpu_one_user(a, models, ds, fn, step_users[a.warmup][0])
+            out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": "1 user of the same workload through oracle/bssd_ref.py (fp32, layer weights "
+                                             "shared across layers); %.1f s of CPU work" % dt}
+        else:
+            out["cpu_baseline"] = None
+        if a.hf_baseline_users > 0:
+            out["hf_gpu_baseline"] = hf_baseline(a, ds, fn, dev, step_users[a.warmup][: a.hf_baseline_users])
+        print(json.dumps(out))
+
+
+def hf_baseline(a, ds, fn, dev, users):
+    """HF `generate(num_beams=K, prefix_allowed_tokens_fn=...)` on the same GPU and shape (reference
+    code/inference.py:177-178, the `TF_target` column): the north star's >= 2x comparison.  Informative only."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    s = SHAPES[a.target]
+    cfg = LlamaConfig(vocab_size=ds.vocab_size, hidden_size=s["hidden"], intermediate_size=s["mlp"],
+                      num_hidden_layers=s["n_layers"], num_attention_heads=s["n_heads"], num_key_value_heads=s["n_heads"],
+                      tie_word_embeddings=False, pad_token_id=0, bos_token_id=1, eos_token_id=2)
+    with torch.device(dev):
+        m = LlamaForCausalLM(cfg).to(torch.bfloat16).eval()
+    lat = []
+    for i, u in enumerate([users[0]] + list(users)):
+        ids = torch.tensor([ds.prompt_ids(u)], device=dev)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            m.generate(input_ids=ids, num_beams=a.K, num_return_sequences=a.K, max_new_tokens=4, do_sample=False,
+                       prefix_allowed_tokens_fn=fn, use_cache=True, pad_token_id=0)
+        torch.cuda.synchronize(dev)
+        if i:
+            lat.append(time.perf_counter() - t0)
+    del m
+    torch.cuda.empty_cache()
+    return {"users_per_s": len(lat) / sum(lat), "latency_ms_p50": float(np.percentile(np.asarray(lat) * 1e3, 50)),
+            "users": len(lat), "what": "transformers LlamaForCausalLM.generate(num_beams=K) bf16, same GPU, same shape"}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if a.impl == "reference":
+        reference_arm(a, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        atspeed_arm(a, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,14 @@ typedef struct atspeed_stats {
 int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t gamma, int32_t* tokens_host,
                  float* scores_host, int32_t* count, atspeed_stats* stats, void* stream);
 
+/* Same loop with the prompt already resident in HBM (DEVICE int32[P]) and the result left on the device:
+ * tokens_dev int32[K][6] (generated suffix per beam, row stride 6 = ATSPEED_MAX_NEW_TOKENS), scores_dev float[K].
+ * The only host synchronisation is the per-round n_matches.  This is what bench.py times as `value`. */
+int atspeed_bssd_device(atspeed_session* s, const int32_t* prompt_dev, int32_t P, int32_t gamma, int32_t* tokens_dev,
+                        float* scores_dev, atspeed_stats* stats, void* stream);
+int atspeed_session_begin_device(atspeed_session* s, const int32_t* prompt_dev, int32_t P, void* stream);
+int atspeed_session_result_device(atspeed_session* s, int32_t* tokens_dev, float* scores_dev, void* stream);
+
 /* target_generate (code/beamSD.py:544-595): plain tree-mask beam search on the target. */
 int atspeed_target_generate(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t* tokens_host,
                             float* scores_host, int32_t* count, atspeed_stats* stats, void* stream);
@@ -157,6 +165,13 @@ int atspeed_session_read(atspeed_session* s, int32_t field, void* host_dst, size
 /* info[0]=logits ld, [1]=R_max, [2]=T_max, [3]=S_max(target), [4]=A_cap, [5]=kernel launches so far,
  * [6]=rows of the last target batch, [7]=rows of the last draft batch */
 int atspeed_session_info(atspeed_session* s, int64_t* info8);
+
+/* Per-launch CUDA-event timing (the reference's `Timer` blocks, code/beamSD.py:12-37,51,60,220,276, without the
+ * forced device syncs): when enabled every kernel launch is bracketed by two events on the caller's stream.
+ * profile_read synchronises and returns, per category {0 gemm, 1 attention, 2 row-wise, 3 kernel (a), 4 beam/verify
+ * kernel (b), 5 kernel (c)}: total milliseconds, launch count and algorithmic bytes, then resets the counters. */
+int atspeed_session_profile(atspeed_session* s, int32_t enable);
+int atspeed_session_profile_read(atspeed_session* s, double* ms6, int64_t* count6, double* bytes6, void* stream);
 
 /* Run one forward of model `model` (0 target, 1 draft) on an explicit batch (all DEVICE arrays): used by the
  * forward parity tests.  tok/pos/slot/prefix_len int32[T], vis uint32[T][16] relative to slot `vis_base`,

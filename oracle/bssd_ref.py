@@ -32,6 +32,7 @@ import torch
 from .llama_ref import RefCache, RefLlama
 
 NEG_INF = float("-inf")
+GAP_LOG = None   # set to a list to record, for every greedy top-k, the score margin at the cut-off (near-tie diagnostics)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -195,7 +196,10 @@ def _expand(logits_rows: torch.Tensor, frontier: List[Node], width: int, fn, pro
         keep = torch.isfinite(vals)
         vals, idx = vals[keep], idx[keep]
     else:
-        vals, idx = _topk_lowest_index(flat, width)
+        vals, idx = _topk_lowest_index(flat, width + 1)
+        if GAP_LOG is not None and len(vals) > width:
+            GAP_LOG.append(float(vals[width - 1] - vals[width]))   # margin between the last kept and first dropped
+        vals, idx = vals[:width], idx[:width]
     kids = [Node(int(i % V), frontier[int(i // V)], float(v)) for v, i in zip(vals, idx)]
     return kids, idx, probs, flat
 
