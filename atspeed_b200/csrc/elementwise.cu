@@ -99,8 +99,81 @@ __global__ void residual_rmsnorm_kernel(__nv_bfloat16* __restrict__ h, const flo
     }
 }
 
+// Vectorised variant: hidden % 4 == 0, ldp % 4 == 0, hidden <= THREADS * 4 * CH.  Each thread keeps its CH float4
+// chunks of the row in registers, so the row is read once and all split slices are fetched with independent 128-bit
+// loads (memory-level parallelism instead of a dependent scalar loop).
+template <int THREADS, int CH>
+__global__ void __launch_bounds__(THREADS)
+residual_rmsnorm_vec_kernel(__nv_bfloat16* __restrict__ h, const float* __restrict__ part, int splits,
+                            long long split_stride, int ldp, const __nv_bfloat16* __restrict__ g, int hidden, float eps,
+                            __nv_bfloat16* __restrict__ x) {
+    __shared__ float red[32];
+    const int t = blockIdx.x;
+    __nv_bfloat16* hrow = h + static_cast<long long>(t) * hidden;
+    const float* prow = part + static_cast<long long>(t) * ldp;
+    const int nchunk = hidden >> 2;
+    float4 v[CH];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int i = threadIdx.x + c * THREADS;
+        if (i < nchunk) {
+            float4 acc = __ldg(reinterpret_cast<const float4*>(prow) + i);
+            for (int s = 1; s < splits; ++s) {
+                const float4 o = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride) + i);
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            const uint2 hb = *reinterpret_cast<const uint2*>(hrow + 4 * i);
+            const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hb.x);
+            const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hb.y);
+            float4 hn;
+            hn.x = bf16_round(__bfloat162float(h01.x) + bf16_round(acc.x));
+            hn.y = bf16_round(__bfloat162float(h01.y) + bf16_round(acc.y));
+            hn.z = bf16_round(__bfloat162float(h23.x) + bf16_round(acc.z));
+            hn.w = bf16_round(__bfloat162float(h23.y) + bf16_round(acc.w));
+            __nv_bfloat162 o01 = __floats2bfloat162_rn(hn.x, hn.y), o23 = __floats2bfloat162_rn(hn.z, hn.w);
+            uint2 ob;
+            ob.x = *reinterpret_cast<uint32_t*>(&o01); ob.y = *reinterpret_cast<uint32_t*>(&o23);
+            *reinterpret_cast<uint2*>(hrow + 4 * i) = ob;
+            v[c] = hn;
+            ss += hn.x * hn.x + hn.y * hn.y + hn.z * hn.z + hn.w * hn.w;
+        }
+    }
+    if (g == nullptr) return;
+    ss = block_sum(ss, red);
+    const float rstd = 1.0f / sqrtf(ss / static_cast<float>(hidden) + eps);
+    __nv_bfloat16* dst = x + static_cast<long long>(t) * hidden;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int i = threadIdx.x + c * THREADS;
+        if (i < nchunk) {
+            const uint2 gb = __ldg(reinterpret_cast<const uint2*>(g + 4 * i));
+            const __nv_bfloat162 g01 = *reinterpret_cast<const __nv_bfloat162*>(&gb.x);
+            const __nv_bfloat162 g23 = *reinterpret_cast<const __nv_bfloat162*>(&gb.y);
+            __nv_bfloat162 o01 = __floats2bfloat162_rn(__bfloat162float(g01.x) * bf16_round(v[c].x * rstd),
+                                                       __bfloat162float(g01.y) * bf16_round(v[c].y * rstd));
+            __nv_bfloat162 o23 = __floats2bfloat162_rn(__bfloat162float(g23.x) * bf16_round(v[c].z * rstd),
+                                                       __bfloat162float(g23.y) * bf16_round(v[c].w * rstd));
+            uint2 ob;
+            ob.x = *reinterpret_cast<uint32_t*>(&o01); ob.y = *reinterpret_cast<uint32_t*>(&o23);
+            *reinterpret_cast<uint2*>(dst + 4 * i) = ob;
+        }
+    }
+}
+
 int residual_rmsnorm(__nv_bfloat16* h, const float* part, int splits, long long split_stride, int ldp,
                      const __nv_bfloat16* g, int T, int hidden, float eps, __nv_bfloat16* x, cudaStream_t st) {
+    if ((hidden & 3) == 0 && (ldp & 3) == 0 && (split_stride & 3) == 0 && hidden <= 512 * 4 * 4 &&
+        (reinterpret_cast<uintptr_t>(part) & 15) == 0) {
+        if (hidden <= 256 * 4)
+            residual_rmsnorm_vec_kernel<256, 1><<<T, 256, 0, st>>>(h, part, splits, split_stride, ldp, g, hidden, eps, x);
+        else if (hidden <= 512 * 4 * 2)
+            residual_rmsnorm_vec_kernel<512, 2><<<T, 512, 0, st>>>(h, part, splits, split_stride, ldp, g, hidden, eps, x);
+        else
+            residual_rmsnorm_vec_kernel<512, 4><<<T, 512, 0, st>>>(h, part, splits, split_stride, ldp, g, hidden, eps, x);
+        ATS_LAUNCH_CHECK();
+        return ATS_OK;
+    }
     ATS_CHECK_ARG(hidden * 4 <= 96 * 1024, "residual_rmsnorm: hidden=%d too large", hidden);
     static bool attr_set = false;
     if (!attr_set) {
@@ -153,10 +226,74 @@ __global__ void qkv_rope_append_kernel(const float* __restrict__ part, int split
     }
 }
 
+// Vectorised variant: one thread = 4 consecutive rotary pairs (i..i+3, i+half..i+half+3) of one head.
+__global__ void __launch_bounds__(256)
+qkv_rope_append_vec_kernel(const float* __restrict__ part, int splits, long long split_stride, int ldp,
+                           const int* __restrict__ pos, const int* __restrict__ slot, int n_heads, int head_dim,
+                           const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int max_pos,
+                           __nv_bfloat16* __restrict__ qbuf, __nv_bfloat16* __restrict__ kcache,
+                           __nv_bfloat16* __restrict__ vcache) {
+    const int t = blockIdx.x;
+    const int HD = n_heads * head_dim, half = head_dim >> 1, q4 = half >> 2;
+    const int e = blockIdx.y * blockDim.x + threadIdx.x;
+    if (e >= n_heads * q4) return;
+    const int hd = e / q4, i = (e - hd * q4) * 4;
+    int p = pos[t];
+    p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
+    const long long srow = static_cast<long long>(slot[t]) * HD;
+    const float* prow = part + static_cast<long long>(t) * ldp;
+    const int c0 = hd * head_dim + i, c1 = c0 + half;
+    float4 a[6];
+    const int cols[6] = {c0, c1, HD + c0, HD + c1, 2 * HD + c0, 2 * HD + c1};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = __ldg(reinterpret_cast<const float4*>(prow + cols[k]));
+    for (int s = 1; s < splits; ++s) {
+        const float* ps = prow + s * split_stride;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float4 o = __ldg(reinterpret_cast<const float4*>(ps + cols[k]));
+            a[k].x += o.x; a[k].y += o.y; a[k].z += o.z; a[k].w += o.w;
+        }
+    }
+    const float4 cs = __ldg(reinterpret_cast<const float4*>(rope_cos + static_cast<long long>(p) * half + i));
+    const float4 sn = __ldg(reinterpret_cast<const float4*>(rope_sin + static_cast<long long>(p) * half + i));
+    auto rope = [](float x0, float x1, float c, float s_, float& o0, float& o1) {
+        x0 = bf16_round(x0); x1 = bf16_round(x1);
+        o0 = bf16_round(bf16_round(x0 * c) + bf16_round(-x1 * s_));
+        o1 = bf16_round(bf16_round(x1 * c) + bf16_round(x0 * s_));
+    };
+    auto pack4 = [](float x, float y, float z, float w) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(x, y), hi = __floats2bfloat162_rn(z, w);
+        uint2 r;
+        r.x = *reinterpret_cast<uint32_t*>(&lo); r.y = *reinterpret_cast<uint32_t*>(&hi);
+        return r;
+    };
+    float4 q0, q1, k0, k1;
+    rope(a[0].x, a[1].x, cs.x, sn.x, q0.x, q1.x); rope(a[0].y, a[1].y, cs.y, sn.y, q0.y, q1.y);
+    rope(a[0].z, a[1].z, cs.z, sn.z, q0.z, q1.z); rope(a[0].w, a[1].w, cs.w, sn.w, q0.w, q1.w);
+    rope(a[2].x, a[3].x, cs.x, sn.x, k0.x, k1.x); rope(a[2].y, a[3].y, cs.y, sn.y, k0.y, k1.y);
+    rope(a[2].z, a[3].z, cs.z, sn.z, k0.z, k1.z); rope(a[2].w, a[3].w, cs.w, sn.w, k0.w, k1.w);
+    *reinterpret_cast<uint2*>(qbuf + static_cast<long long>(t) * HD + c0) = pack4(q0.x, q0.y, q0.z, q0.w);
+    *reinterpret_cast<uint2*>(qbuf + static_cast<long long>(t) * HD + c1) = pack4(q1.x, q1.y, q1.z, q1.w);
+    *reinterpret_cast<uint2*>(kcache + srow + c0) = pack4(k0.x, k0.y, k0.z, k0.w);
+    *reinterpret_cast<uint2*>(kcache + srow + c1) = pack4(k1.x, k1.y, k1.z, k1.w);
+    *reinterpret_cast<uint2*>(vcache + srow + c0) = pack4(a[4].x, a[4].y, a[4].z, a[4].w);
+    *reinterpret_cast<uint2*>(vcache + srow + c1) = pack4(a[5].x, a[5].y, a[5].z, a[5].w);
+}
+
 int qkv_rope_append(const float* part, int splits, long long split_stride, int ldp, const BatchDesc& b, int T,
                     int n_heads, int head_dim, const float* rope_cos, const float* rope_sin, int max_pos,
                     __nv_bfloat16* qbuf, __nv_bfloat16* kcache, __nv_bfloat16* vcache, cudaStream_t st) {
     ATS_CHECK_ARG((head_dim & 1) == 0, "head_dim=%d must be even", head_dim);
+    if ((head_dim & 7) == 0 && (ldp & 3) == 0 && (split_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0) {
+        const int work = n_heads * (head_dim >> 3);
+        dim3 grid(T, (work + 255) / 256);
+        qkv_rope_append_vec_kernel<<<grid, 256, 0, st>>>(part, splits, split_stride, ldp, b.pos, b.slot, n_heads, head_dim,
+                                                         rope_cos, rope_sin, max_pos, qbuf, kcache, vcache);
+        ATS_LAUNCH_CHECK();
+        return ATS_OK;
+    }
     qkv_rope_append_kernel<<<T, 256, 0, st>>>(part, splits, split_stride, ldp, b.pos, b.slot, n_heads, head_dim,
                                               rope_cos, rope_sin, max_pos, qbuf, kcache, vcache);
     ATS_LAUNCH_CHECK();
@@ -177,8 +314,39 @@ __global__ void silu_mul_kernel(const float* __restrict__ part, int splits, long
     }
 }
 
+__global__ void __launch_bounds__(256)
+silu_mul_vec_kernel(const float* __restrict__ part, int splits, long long split_stride, int ldp, int mlp,
+                    __nv_bfloat16* __restrict__ m) {
+    const int t = blockIdx.x;
+    const int i = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (i >= mlp) return;
+    const float* prow = part + static_cast<long long>(t) * ldp;
+    float4 g = __ldg(reinterpret_cast<const float4*>(prow + i));
+    float4 u = __ldg(reinterpret_cast<const float4*>(prow + mlp + i));
+    for (int s = 1; s < splits; ++s) {
+        const float4 g2 = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + i));
+        const float4 u2 = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + mlp + i));
+        g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+        u.x += u2.x; u.y += u2.y; u.z += u2.z; u.w += u2.w;
+    }
+    auto f = [](float gg, float uu) {
+        gg = bf16_round(gg); uu = bf16_round(uu);
+        return bf16_round(gg / (1.0f + expf(-gg))) * uu;
+    };
+    __nv_bfloat162 lo = __floats2bfloat162_rn(f(g.x, u.x), f(g.y, u.y)), hi = __floats2bfloat162_rn(f(g.z, u.z), f(g.w, u.w));
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&lo); r.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(m + static_cast<long long>(t) * mlp + i) = r;
+}
+
 int silu_mul(const float* part, int splits, long long split_stride, int ldp, int T, int mlp, __nv_bfloat16* m,
              cudaStream_t st) {
+    if ((mlp & 3) == 0 && (ldp & 3) == 0 && (split_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0) {
+        dim3 grid(T, (mlp / 4 + 255) / 256);
+        silu_mul_vec_kernel<<<grid, 256, 0, st>>>(part, splits, split_stride, ldp, mlp, m);
+        ATS_LAUNCH_CHECK();
+        return ATS_OK;
+    }
     silu_mul_kernel<<<T, 256, 0, st>>>(part, splits, split_stride, ldp, mlp, m);
     ATS_LAUNCH_CHECK();
     return ATS_OK;
