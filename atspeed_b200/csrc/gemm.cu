@@ -261,12 +261,19 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, lon
 }
 
 int gemm_plan_splits(int total_tiles, int n_kblocks, int num_sms) {
-    // enough CTAs to pull HBM from (nearly) every SM, but never an empty split
-    int splits = 1;
-    while (total_tiles * splits < num_sms && splits * 2 <= n_kblocks && splits < 16) splits *= 2;
-    // prefer the split count whose CTA total is closest to a multiple of the SM count from below
-    if (splits > 1 && total_tiles * splits > 2 * num_sms) splits /= 2;
-    return splits;
+    // Pick the split-K factor with the cheapest estimated schedule: waves x (k-blocks per CTA + a fixed per-CTA cost of
+    // ~6 k-block times for prologue/epilogue), measured on B200 with tools/gemm_bench.py.  Splitting multiplies the fp32
+    // partial-sum traffic, so wide outputs (many tiles) are only split when a wave would otherwise be mostly empty.
+    const int max_s = total_tiles >= num_sms ? 1 : 8;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= max_s && s <= n_kblocks; ++s) {
+        const int ctas = total_tiles * s;
+        const int waves = (ctas + num_sms - 1) / num_sms;
+        const double cost = waves * ((n_kblocks + s - 1) / s + 6.0) + 0.5 * (s - 1);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    return best;
 }
 
 // out[s][t][...] for s < splits. X: [T, K] bf16 row-major. W_i: [n_rows_i, K] bf16 row-major.
