@@ -1,0 +1,101 @@
+"""CPU tests of the host logic around the path: ranking metrics (known-answer vector of the reference),
+item decoding, user sharding and the world_size-2 all-gather of ranked lists (gloo)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from _common import ROOT, dataset, golden
+from atspeed_b200.metrics import computeTopNAccuracy
+from atspeed_b200.runner import UserRecords, evaluate, gather_records, run_users, shard_users
+
+
+def test_metric_known_answer_of_the_reference():
+    # computed by the unmodified reference (code/utils.py:215-271) in tools/make_golden.py
+    want = golden()["facts"]["metric_known_answer"]
+    got = computeTopNAccuracy([["x", "y"], ["z"], []], [["x", "q", "y"], ["a", "b", "z"], ["a", "b", "c"]], [1, 3])
+    assert [list(x) for x in got] == want == [[0.5, 0.5], [0.25, 1.0], [0.5, 0.7099], [0.5, 0.6667]]
+
+
+def test_dataset_facts_match_the_reference():
+    for name in ("beauty", "games"):
+        f, ds = golden()["facts"][name], dataset(name)
+        assert ds.vocab_size == f["vocab"] and ds.n_users == f["n_users"]
+        assert [list(r) for r in ds.level_ranges()] == f["level_ranges"]
+        assert len(ds.item_sequences()) == f["n_item_seqs"]
+        assert [len(ds.positional_allowed()[d]) for d in range(5)] == f["positional_sizes"]
+
+
+def _fake_search(ds, K, L):
+    def search(prompt):
+        h = int(np.sum(prompt)) % 1000
+        rows = ds.item_sequences()[h:h + K]
+        return {"tokens": rows.astype(np.int32), "scores": -np.arange(K, dtype=np.float32) - h, "n_run": 3,
+                "total_accept_steps": h % 3}
+    return search
+
+
+def test_shard_and_evaluate_single_process():
+    ds = dataset("beauty")
+    users = list(range(40))
+    assert shard_users(users, 1, 4) == users[1::4]
+    K, L = 10, 4
+    rec = run_users(_fake_search(ds, K, L), ds.prompt_ids, users, K, L)
+    full = gather_records(rec, K, L, per_rank=len(users))
+    assert full.users.tolist() == users and full.items.shape == (40, K, L)
+    m = evaluate(ds, full, [5, 10])
+    assert m["users"] == 40 and len(m["recall"]) == 2 and 0.0 <= m["ndcg"][1] <= 1.0
+    # a user whose first prediction is its ground truth scores recall@K > 0
+    u = 3
+    gt = ds.item_token_ids[ds.ground_truth(u)[0]]
+    rec.items[u, 0] = gt
+    m2 = evaluate(ds, gather_records(rec, K, L, per_rank=40), [10])
+    assert m2["recall"][0] > 0
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _common import dataset as _ds
+    ds = _ds("games")
+    K, L = 20, 4
+    users = list(range(0, 50))
+    mine = shard_users(users, rank, world)
+    rec = run_users(_fake_search(ds, K, L), ds.prompt_ids, mine, K, L)
+    full = gather_records(rec, K, L, per_rank=-(-len(users) // world))
+    m = evaluate(ds, full, [10, 20])
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), users=full.users, items=full.items, scores=full.scores,
+             recall=np.asarray(m["recall"]), ndcg=np.asarray(m["ndcg"]))
+    dist.destroy_process_group()
+
+
+def test_user_sharded_all_gather_world_size_2(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    assert a["users"].tolist() == list(range(50))
+    for k in ("users", "items", "scores", "recall", "ndcg"):
+        np.testing.assert_array_equal(a[k], b[k])          # identical ranked lists and metrics on every rank
+    # equals the single-process run
+    ds = dataset("games")
+    rec = run_users(_fake_search(ds, 20, 4), ds.prompt_ids, list(range(50)), 20, 4)
+    np.testing.assert_array_equal(a["items"], rec.items)
+    np.testing.assert_array_equal(a["scores"], rec.scores)
+
+
+def test_userrecords_roundtrip():
+    r = UserRecords.empty(3, 5, 4)
+    r.users[:] = [7, 2, 9]
+    r.items[:] = np.arange(60).reshape(3, 5, 4)
+    r.scores[:] = np.linspace(-3, 0, 15).reshape(3, 5).astype(np.float32)
+    r.meta[:] = np.arange(12).reshape(3, 4)
+    q = UserRecords.unpack(r.pack(), 5, 4)
+    for k in ("users", "items", "scores", "meta"):
+        np.testing.assert_array_equal(getattr(q, k), getattr(r, k))
