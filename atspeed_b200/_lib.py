@@ -27,7 +27,8 @@ class TrieDesc(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("max_new_tokens", C.c_int32), ("max_prompt", C.c_int32),
-                ("num_sms", C.c_int32)]
+                ("num_sms", C.c_int32), ("do_sample", C.c_int32), ("top_k", C.c_int32), ("temperature", C.c_float),
+                ("seed", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -49,6 +50,11 @@ SYMBOLS = {
     "atspeed_session_target": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "atspeed_session_verify": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, C.c_void_p]),
     "atspeed_session_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "atspeed_session_sort_result": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "atspeed_session_set_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "atspeed_noise_stream": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "atspeed_noise_fill": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "atspeed_session_sample_width": (C.c_int, [C.c_void_p]),
     "atspeed_session_result": (C.c_int, [C.c_void_p, c_i32p, c_f32p, c_i32p, C.c_void_p]),
     "atspeed_bssd": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_f32p, c_i32p,
                                C.POINTER(Stats), C.c_void_p]),
@@ -80,7 +86,9 @@ SYMBOLS = {
 # enum atspeed_field
 F_LEVEL_CNT, F_LEVEL_TOK, F_LEVEL_PARENT, F_LEVEL_SCORE, F_SCALARS = 0, 1, 2, 3, 4
 F_PICK_PARENT, F_PICK_TOK, F_PICK_SCORE, F_HIT_POS, F_NPICK = 5, 6, 7, 8, 9
-F_LOGITS_TARGET, F_LOGITS_DRAFT, F_ROW_NODE, F_LEVEL_NODE = 10, 11, 12, 13
+F_LOGITS_TARGET, F_LOGITS_DRAFT, F_ROW_NODE, F_LEVEL_NODE, F_TR_ACC, F_LSE_Q = 10, 11, 12, 13, 14, 15
+SITE_DRAFT, SITE_ACCEPT, SITE_PERM, SITE_RESIDUAL, SITE_BONUS, SITE_STEP = 0, 1, 2, 3, 4, 5
+ABI_VERSION = 2
 MAX_LEVELS, MAX_BEAMS, MAX_K, MAX_NEW, VIS_WORDS = 5, 64, 32, 6, 16
 
 _lib = None
@@ -102,7 +110,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.atspeed_abi_version() != 1:
+    if lib.atspeed_abi_version() != ABI_VERSION:
         raise AtSpeedError("libatspeed_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -84,8 +84,16 @@ def _device_of(model) -> torch.device:
 def get_session(target_model, draft_model, prompt_ids: List[int], max_new_tokens: int,
                 prefix_allowed_tokens_fn: Optional[Callable]) -> Session:
     """Session for (models, K, N, max_new_tokens, constraint); built on first use and cached."""
-    K = int(target_model.generation_config.num_beams)
+    gc = target_model.generation_config
+    K = int(gc.num_beams)
     N = int(draft_model.generation_config.num_beams) if draft_model is not None else K
+    # sampling knobs are read from the TARGET's config, like the reference's single warper (beamSD.py:479-481)
+    do_sample = bool(getattr(gc, "do_sample", False))
+    top_k = getattr(gc, "top_k", None) if do_sample else None
+    temperature = float(getattr(gc, "temperature", None) or 1.0) if do_sample else 1.0
+    if do_sample and not top_k:
+        raise ValueError("do_sample=True needs generation_config.top_k (transformers 4.41's default was 50; "
+                         "5.x defaults to None): the warped candidate set must be bounded (<= 64)")
     tdm = as_device_model(target_model)
     ddm = as_device_model(draft_model) if draft_model is not None else None
     csr = compile_constraint(prefix_allowed_tokens_fn, prompt_ids, max_new_tokens, vocab_size=tdm.spec.vocab)
@@ -93,11 +101,23 @@ def get_session(target_model, draft_model, prompt_ids: List[int], max_new_tokens
     trie = _TRIES.get(tkey)
     if trie is None:
         trie = _TRIES[tkey] = DeviceTrie(csr, tdm.device)
-    key = (id(tdm), id(ddm), K, N, max_new_tokens, id(trie))
+    key = (id(tdm), id(ddm), K, N, max_new_tokens, id(trie), do_sample, top_k, temperature)
     sess = _SESSIONS.get(key)
     if sess is None:
-        sess = _SESSIONS[key] = Session(tdm, ddm, trie, K, N, max_new_tokens)
+        sess = _SESSIONS[key] = Session(tdm, ddm, trie, K, N, max_new_tokens, do_sample=do_sample, top_k=top_k,
+                                        temperature=temperature)
     return sess
+
+
+def _reseed(sess: Session, seed: Optional[int]):
+    """Sampling mode: key the search's noise.  Like the reference, randomness follows torch's global generator
+    (`set_seed(...)` makes runs reproducible): one 62-bit seed is drawn from it per search unless given."""
+    if not sess.do_sample:
+        return None
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    sess.set_seed(seed, 0)
+    return seed
 
 
 def clear_sessions():
@@ -110,11 +130,6 @@ def _prompt_list(inputs: Dict) -> List[int]:
     if ids.dim() != 2 or ids.shape[0] != 1:
         raise ValueError("batch size 1 only (as the reference: beamSD.py:57,224 read batch index 0)")
     return [int(t) for t in ids[0].tolist()]
-
-
-def _check_greedy(model):
-    if getattr(model.generation_config, "do_sample", False):
-        raise NotImplementedError("do_sample=True (AtSpeed-R relaxed acceptance) is not wired through the CUDA path yet")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -194,7 +209,8 @@ def no_delay_target_beam_search(*args, **kwargs):
 @Timer()
 def verify(target_model, target_model_inputs: Dict, draft_outputs: Dict, target_outputs: Dict, draft_beam_size: int,
            beam_size: int, beam_scores=None, beam_sequence=None, logits_processor=None, logits_warper=None) -> Dict:
-    """AtSpeed-S strict verify (beamSD.py:242-456, greedy branch) = kernel (b) + kernel (c)."""
+    """verify (beamSD.py:242-456) = kernel (b) + kernel (c): AtSpeed-S strict top-K (greedy branch) or, with
+    generation_config.do_sample, AtSpeed-R relaxed acceptance (sampling branch)."""
     sess: Session = target_model_inputs["_session"]
     n_matches = sess.verify(draft_outputs["draft_len"])
     out = {"n_matches": n_matches, "target_model_inputs": target_model_inputs, "draft_model_inputs": target_model_inputs}
@@ -219,9 +235,10 @@ def _pack(sess: Session, prompt: List[int], res: Dict, device) -> Dict:
 @Timer()
 @torch.no_grad()
 def BSSD(target_model, draft_model, inputs: Dict, gamma: int, max_new_tokens: int,
-         logits_processor=None, prefix_allowed_tokens_fn=None, trace: bool = False) -> Dict:
-    """Speculative beam search (beamSD.py:458-542). Same arguments and result keys as the reference."""
-    _check_greedy(target_model)
+         logits_processor=None, prefix_allowed_tokens_fn=None, trace: bool = False, seed: Optional[int] = None) -> Dict:
+    """Speculative beam search (beamSD.py:458-542). Same arguments and result keys as the reference.
+    generation_config.do_sample selects AtSpeed-R (relaxed acceptance); `seed` pins its noise (default: drawn from
+    torch's global generator, so `set_seed` reproduces a run)."""
     if logits_processor:
         raise NotImplementedError("extra logits processors are not supported; pass prefix_allowed_tokens_fn")
     prompt = _prompt_list(inputs)
@@ -232,6 +249,7 @@ def BSSD(target_model, draft_model, inputs: Dict, gamma: int, max_new_tokens: in
     marks = []
     state = {"_session": sess, "_target_model": target_model, "_trace": trace}
     with torch.cuda.device(dev):
+        used_seed = _reseed(sess, seed)
         sess.begin(prompt)
         done, accept_steps, rounds = 0, [], []
         while done < max_new_tokens:
@@ -252,6 +270,7 @@ def BSSD(target_model, draft_model, inputs: Dict, gamma: int, max_new_tokens: in
                 rounds.append({"draft": d_out, "target": t_out, "verify": sess.verify_trace(), "n_matches": n_matches})
             done += n_matches + 1
             accept_steps.append(n_matches)
+        sess.sort_result()                                                       # beamSD.py:529-531 (sampling only)
         res = sess.result()
         torch.cuda.current_stream(dev).synchronize()
     out = _pack(sess, prompt, res, dev)
@@ -264,16 +283,18 @@ def BSSD(target_model, draft_model, inputs: Dict, gamma: int, max_new_tokens: in
                 "accept_steps": accept_steps})
     if trace:
         out["rounds"] = rounds
+    if used_seed is not None:
+        out["seed"] = used_seed
     return out
 
 
 @Timer()
 @torch.no_grad()
 def target_generate(model, inputs: Dict, max_new_tokens: int, logits_processor=None,
-                    prefix_allowed_tokens_fn=None) -> Dict:
+                    prefix_allowed_tokens_fn=None, seed: Optional[int] = None) -> Dict:
     """Plain tree-mask beam search on the target (beamSD.py:544-595)."""
-    _check_greedy(model)
     prompt = _prompt_list(inputs)
     sess = get_session(model, None, prompt, max_new_tokens, prefix_allowed_tokens_fn)
+    _reseed(sess, seed)
     res = sess.target_generate(prompt)
     return _pack(sess, prompt, res, sess.device)

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels.h"
+#include "noise.cuh"
 
 namespace atspeed {
 
@@ -35,8 +36,25 @@ struct TreeDev {
     int* miss_pos;
     int* miss_slot;
     uint32_t* miss_vis;    // [MAX_K][VIS_WORDS]
+    // ---- AtSpeed-R (sampling) only ----
+    // the draft's warped per-row candidate lists of every step (its q lives on them: beamSD.py:70, step_probs) and the
+    // log-normaliser of its flat softmax; level l = the step that expanded level l into level l + 1
+    int* dcand_tok;        // [MAX_LEVELS][MAX_BEAMS * MAX_BEAMS]: per level, kernel (a) output with row stride B
+    float* dcand_logp;     // same layout
+    int* dcand_edge;       // same layout
+    int* dcand_cnt;        // [MAX_LEVELS][MAX_BEAMS]
+    float* lse_q;          // [MAX_LEVELS]
+    int* tr_acc;           // [MAX_LEVELS][MAX_BEAMS] acceptance flag of every draft pick (trace)
+};
+// sampling parameters of one launch (by value)
+struct SampleCfg {
+    int B;                 // warped candidates per row = max(top_k, min_tokens_to_keep)
+    float inv_temp;        // 1 / temperature
+    unsigned long long seed;
+    unsigned long long stream_base;   // noise_stream(user_seq, round, 0, 0)
 };
 enum { SC_P = 0, SC_GEN0 = 1, SC_FIRST = 2, SC_ACC = 3, SC_NMATCH = 4, SC_MISS = 5, SC_GATHER = 6, SC_RESULT = 7,
+       SC_FALLBACK = 8 /* rounds whose residual distribution was empty (reference undefined) */,
        SC_COUNT = 16 };
 
 // Forward batch (one per model invocation) + logits-row selection, device arrays.
@@ -76,5 +94,20 @@ int tree_select(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int le
 int tree_verify_strict(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int draft_len, int root_rows,
                        const int* cand_tok, const int* cand_edge, const float* cand_logp, const int* cand_cnt, int P,
                        cudaStream_t st);
+
+// ---- AtSpeed-R ----
+// sampling form of tree_select: N samples without replacement from softmax(logp / T + parent score) over the rows'
+// warped candidates (beamSD.py:65-74); candidates are read from cand_* with row stride B = sc.B
+int tree_select_sample(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int level, int row0, const int* cand_tok,
+                       const int* cand_edge, const float* cand_logp, const int* cand_cnt, int width, int P,
+                       const SampleCfg& sc, unsigned site, cudaStream_t st);
+// kernel (b), relaxed mode (sequence-level speculative sampling, beamSD.py:293-321,332-369)
+int tree_verify_relaxed(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int draft_len, int root_rows,
+                        const int* cand_tok, const int* cand_edge, const float* cand_logp, const int* cand_cnt, int P,
+                        const SampleCfg& sc, cudaStream_t st);
+// sort the beams of `level` by score, descending (beamSD.py:529-531)
+int tree_sort_level(const TreeDev& t, int level, cudaStream_t st);
+// out[i] = noise(seed, stream, i): kind 0 = raw uint32 bits, 1 = uniform (0,1), 2 = Exp(1)
+int noise_fill(unsigned long long seed, unsigned long long stream, int kind, int n, void* out, cudaStream_t st);
 
 }  // namespace atspeed

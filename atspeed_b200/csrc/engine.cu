@@ -77,6 +77,10 @@ struct atspeed_session {
     int num_sms;
     int* pinned;          // pinned host scratch
     long long launches;
+    // sampling mode (AtSpeed-R): noise key, user sequence number of the current search, round within it
+    unsigned long long seed, user_seq, next_user_seq;
+    int round;
+    int sample_B;
     // optional per-launch CUDA-event timing (bench.py roofline / share-of-step); off by default
     bool prof_on;
     std::vector<cudaEvent_t> prof_ev;
@@ -173,6 +177,12 @@ static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_des
     t.miss_pos = c.take<int>(MAX_K);
     t.miss_slot = c.take<int>(MAX_K);
     t.miss_vis = c.take<uint32_t>(MAX_K * VIS_WORDS);
+    t.dcand_tok = c.take<int>(MAX_LEVELS * MAX_BEAMS * MAX_BEAMS);
+    t.dcand_logp = c.take<float>(MAX_LEVELS * MAX_BEAMS * MAX_BEAMS);
+    t.dcand_edge = c.take<int>(MAX_LEVELS * MAX_BEAMS * MAX_BEAMS);
+    t.dcand_cnt = c.take<int>(MAX_LEVELS * MAX_BEAMS);
+    t.lse_q = c.take<float>(MAX_LEVELS);
+    t.tr_acc = c.take<int>(MAX_LEVELS * MAX_BEAMS);
     BatchDev& b = s->batch;
     b.tok = c.take<int>(s->T_max);
     b.pos = c.take<int>(s->T_max);
@@ -196,6 +206,12 @@ static int check_cfg(const atspeed_model_desc* target, const atspeed_model_desc*
     ATS_CHECK_ARG(cfg->max_new_tokens >= 1 && cfg->max_new_tokens <= MAX_NEW && cfg->max_new_tokens < MAX_LEVELS + 1,
                   "max_new_tokens=%d outside [1,%d]", cfg->max_new_tokens, MAX_LEVELS);
     ATS_CHECK_ARG(cfg->max_prompt >= 1, "max_prompt=%d", cfg->max_prompt);
+    if (cfg->do_sample) {
+        ATS_CHECK_ARG(cfg->top_k >= 1 && cfg->top_k <= MAX_BEAMS,
+                      "do_sample needs generation_config.top_k in [1,%d] (transformers 4.41 default 50), got %d", MAX_BEAMS,
+                      cfg->top_k);
+        ATS_CHECK_ARG(cfg->temperature > 0.f, "temperature=%f", cfg->temperature);
+    }
     const int bits = cfg->max_new_tokens * cfg->K + cfg->K + (MAX_LEVELS - 1) * cfg->N + cfg->K;
     ATS_CHECK_ARG(bits <= MAX_TREE_SLOTS, "K=%d N=%d need %d tree slots > %d", cfg->K, cfg->N, bits, MAX_TREE_SLOTS);
     for (const atspeed_model_desc* d : {target, draft}) {
@@ -310,10 +326,26 @@ static BatchDesc batch_desc(const atspeed_session* s) {
     return b;
 }
 
-static int run_topk(atspeed_session* s, ModelRT& m, int R, int B, cudaStream_t st) {
+struct CandOut { int* tok; int* edge; float* logp; int* cnt; };
+static CandOut shared_cand(atspeed_session* s) { return CandOut{s->cand_tok, s->cand_edge, s->cand_logp, s->cand_cnt}; }
+// the draft's step-`level` candidates are kept per level in sampling mode: verify needs q on them
+static CandOut draft_level_cand(atspeed_session* s, int level) {
+    const size_t o = static_cast<size_t>(level) * MAX_BEAMS * MAX_BEAMS;
+    return CandOut{s->tree.dcand_tok + o, s->tree.dcand_edge + o, s->tree.dcand_logp + o, s->tree.dcand_cnt + level * MAX_BEAMS};
+}
+static SampleCfg sample_cfg(const atspeed_session* s) {
+    SampleCfg sc;
+    sc.B = s->sample_B;
+    sc.inv_temp = 1.0f / s->cfg.temperature;
+    sc.seed = s->seed;
+    sc.stream_base = noise_stream(s->user_seq, static_cast<uint32_t>(s->round), 0, 0);
+    return sc;
+}
+
+static int run_topk(atspeed_session* s, ModelRT& m, int R, int B, const CandOut& o, cudaStream_t st) {
     PROF(s, CAT_TOPK, static_cast<double>(R) * m.d.vocab * 4.0,
-         mask_logsoftmax_topk(m.logits, 0, R, m.d.vocab, m.ldl, s->batch.row_node, nullptr, s->trie, B, s->cand_tok,
-                              s->cand_edge, s->cand_logp, s->cand_cnt, s->lse, st));
+         mask_logsoftmax_topk(m.logits, 0, R, m.d.vocab, m.ldl, s->batch.row_node, nullptr, s->trie, B, o.tok, o.edge,
+                              o.logp, o.cnt, s->lse, st));
     s->launches += 1;
     return ATS_OK;
 }
@@ -340,9 +372,19 @@ static int search_step(atspeed_session* s, ModelRT& m, int level, int width, boo
     PROF(s, CAT_BEAM, 0, tree_build_batch(s->tree, s->batch, g, plan, s->prompt_dev, P, T, R, st));
     s->launches += 1;
     ATS_TRY(forward(s, m, batch_desc(s), T, S, s->batch.rows_idx, R, st));
-    ATS_TRY(run_topk(s, m, R, width, st));
-    PROF(s, CAT_BEAM, 0,
-         tree_select(s->tree, g, s->trie, level, 0, width, s->cand_tok, s->cand_edge, s->cand_logp, s->cand_cnt, width, P, st));
+    if (s->cfg.do_sample) {
+        // beamSD.py:65-74: warp (temperature, top-k) the masked log-probs, then `width` samples without replacement
+        const bool is_draft = &m == &s->dft;
+        const CandOut o = is_draft ? draft_level_cand(s, level) : shared_cand(s);
+        ATS_TRY(run_topk(s, m, R, s->sample_B, o, st));
+        PROF(s, CAT_BEAM, 0,
+             tree_select_sample(s->tree, g, s->trie, level, 0, o.tok, o.edge, o.logp, o.cnt, width, P, sample_cfg(s),
+                                is_draft ? SITE_DRAFT : SITE_STEP, st));
+    } else {
+        ATS_TRY(run_topk(s, m, R, width, shared_cand(s), st));
+        PROF(s, CAT_BEAM, 0,
+             tree_select(s->tree, g, s->trie, level, 0, width, s->cand_tok, s->cand_edge, s->cand_logp, s->cand_cnt, width, P, st));
+    }
     s->launches += 1;
     return ATS_OK;
 }
@@ -406,6 +448,12 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
     }
     memset(s->pinned, 0, 64 * sizeof(int));
     s->P = 0;
+    s->seed = cfg->seed; s->user_seq = 0; s->next_user_seq = 0; s->round = 0;
+    {
+        const int min_keep = cfg->K > 1 ? 2 : 1;     // transformers 4.41 _get_logits_warper: min_tokens_to_keep
+        s->sample_B = cfg->top_k > min_keep ? cfg->top_k : min_keep;
+        if (s->sample_B > MAX_BEAMS) s->sample_B = MAX_BEAMS;
+    }
     s->launches = 0;
     s->prof_on = false;
     s->prof_n = 0;
@@ -433,6 +481,8 @@ int atspeed_session_begin(atspeed_session* s, const int32_t* prompt_host, int32_
     ATS_CUDA(cudaMemcpyAsync(s->prompt_dev, prompt_host, sizeof(int) * P, cudaMemcpyHostToDevice, st));
     PROF(s, CAT_BEAM, 0, tree_begin(s->tree, s->batch, s->prompt_dev, P, st));
     s->launches += 1;
+    s->user_seq = s->next_user_seq++;
+    s->round = 0;
     s->pinned[H_FIRST] = 1;    // first
     s->pinned[H_MISS] = 0;    // missing ancestors pending for the draft
     s->pinned[H_LEVEL] = 0;   // result level
@@ -450,6 +500,8 @@ int atspeed_session_begin_device(atspeed_session* s, const int32_t* prompt_dev, 
     ATS_CUDA(cudaMemcpyAsync(s->prompt_dev, prompt_dev, sizeof(int) * P, cudaMemcpyDeviceToDevice, st));
     PROF(s, CAT_BEAM, 0, tree_begin(s->tree, s->batch, s->prompt_dev, P, st));
     s->launches += 1;
+    s->user_seq = s->next_user_seq++;
+    s->round = 0;
     s->pinned[H_FIRST] = 1;
     s->pinned[H_MISS] = 0;
     s->pinned[H_LEVEL] = 0;
@@ -527,7 +579,7 @@ int atspeed_session_target(atspeed_session* s, int32_t draft_len, void* stream) 
     PROF(s, CAT_BEAM, 0, tree_build_batch(s->tree, s->batch, g, plan, s->prompt_dev, P, T, R, st));
     s->launches += 1;
     ATS_TRY(forward(s, s->tgt, batch_desc(s), T, S, s->batch.rows_idx, R, st));
-    ATS_TRY(run_topk(s, s->tgt, R, g.K, st));
+    ATS_TRY(run_topk(s, s->tgt, R, s->cfg.do_sample ? s->sample_B : g.K, shared_cand(s), st));
     return ATS_OK;
 }
 
@@ -536,9 +588,14 @@ int atspeed_session_verify(atspeed_session* s, int32_t draft_len, int32_t* n_mat
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const TreeGeom& g = s->geom;
     const bool first = s->pinned[H_FIRST] != 0;
-    PROF(s, CAT_BEAM, 0,
-         tree_verify_strict(s->tree, g, s->trie, draft_len, first ? 1 : g.K, s->cand_tok, s->cand_edge, s->cand_logp,
-                            s->cand_cnt, s->P, st));
+    if (s->cfg.do_sample)
+        PROF(s, CAT_BEAM, 0,
+             tree_verify_relaxed(s->tree, g, s->trie, draft_len, first ? 1 : g.K, s->cand_tok, s->cand_edge, s->cand_logp,
+                                 s->cand_cnt, s->P, sample_cfg(s), st));
+    else
+        PROF(s, CAT_BEAM, 0,
+             tree_verify_strict(s->tree, g, s->trie, draft_len, first ? 1 : g.K, s->cand_tok, s->cand_edge, s->cand_logp,
+                                s->cand_cnt, s->P, st));
     // kernel (c): move the survivors' ancestor rows into the accepted region, both caches, all layers
     const int max_rows = (draft_len + 1) * g.K;
     for (ModelRT* m : {&s->tgt, s->has_draft ? &s->dft : nullptr}) {
@@ -555,6 +612,7 @@ int atspeed_session_verify(atspeed_session* s, int32_t draft_len, int32_t* n_mat
     s->pinned[H_FIRST] = 0;
     s->pinned[H_MISS] = s->pinned[SC_MISS] > 0 ? 1 : 0;
     s->pinned[H_LEVEL] = 0;
+    s->round += 1;
     return ATS_OK;
 }
 
@@ -570,6 +628,32 @@ int atspeed_session_step(atspeed_session* s, int32_t model, int32_t width, void*
     s->pinned[H_LEVEL] = level + 1;
     return ATS_OK;
 }
+
+int atspeed_session_sort_result(atspeed_session* s, void* stream) {
+    ATS_CHECK_ARG(s, "null session");
+    if (!s->cfg.do_sample) return ATS_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PROF(s, CAT_BEAM, 0, tree_sort_level(s->tree, s->pinned[H_LEVEL], st));
+    s->launches += 1;
+    return ATS_OK;
+}
+
+int atspeed_session_set_seed(atspeed_session* s, uint64_t seed, uint64_t user_seq) {
+    ATS_CHECK_ARG(s, "null session");
+    s->seed = seed;
+    s->next_user_seq = user_seq;
+    return ATS_OK;
+}
+
+uint64_t atspeed_noise_stream(uint64_t user_seq, uint32_t round, uint32_t level, uint32_t site) {
+    return noise_stream(user_seq, round, level, site);
+}
+
+int atspeed_noise_fill(uint64_t seed, uint64_t stream, int32_t kind, int32_t n, void* out_dev, void* stream_handle) {
+    return noise_fill(seed, stream, kind, n, out_dev, static_cast<cudaStream_t>(stream_handle));
+}
+
+int atspeed_session_sample_width(atspeed_session* s) { return s ? s->sample_B : 0; }
 
 int atspeed_session_result(atspeed_session* s, int32_t* tokens_host, float* scores_host, int32_t* count, void* stream) {
     ATS_CHECK_ARG(s && tokens_host && scores_host && count, "null argument");
@@ -613,6 +697,7 @@ static int bssd_loop(atspeed_session* s, int32_t gamma, atspeed_stats* stats, lo
         ++n_run;
         total += m;
     }
+    ATS_TRY(atspeed_session_sort_result(s, stream));
     if (stats) {
         stats->n_run = n_run;
         stats->total_accept_steps = total;
@@ -654,6 +739,7 @@ int atspeed_target_generate(atspeed_session* s, const int32_t* prompt_host, int3
     const int tf0 = s->tgt.forwards;
     ATS_TRY(atspeed_session_begin(s, prompt_host, P, stream));
     for (int i = 0; i < s->cfg.max_new_tokens; ++i) ATS_TRY(atspeed_session_step(s, 0, s->cfg.K, stream));
+    ATS_TRY(atspeed_session_sort_result(s, stream));
     ATS_TRY(atspeed_session_result(s, tokens_host, scores_host, count, stream));
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -686,6 +772,8 @@ int atspeed_session_read(atspeed_session* s, int32_t field, void* host_dst, size
             ATS_CHECK_ARG(s->has_draft, "no draft model");
             src = s->dft.logits; avail = sizeof(float) * s->R_max * s->dft.ldl; break;
         case ATSPEED_F_ROW_NODE: src = s->batch.row_node; avail = sizeof(int) * s->R_max; break;
+        case ATSPEED_F_TR_ACC: src = t.tr_acc; avail = sizeof(int) * MAX_LEVELS * MAX_BEAMS; break;
+        case ATSPEED_F_LSE_Q: src = t.lse_q; avail = sizeof(float) * MAX_LEVELS; break;
         default: set_error("unknown field %d", field); return ATS_ERR_ARG;
     }
     ATS_CHECK_ARG(bytes <= avail, "field %d holds %zu bytes, %zu requested", field, avail, bytes);

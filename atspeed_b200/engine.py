@@ -131,7 +131,8 @@ class Session:
     """One search configuration (model pair, K, N, max_new_tokens, constraint) with its workspace."""
 
     def __init__(self, target: DeviceModel, draft: Optional[DeviceModel], trie: DeviceTrie, K: int, N: int,
-                 max_new_tokens: int = 4, max_prompt: Optional[int] = None):
+                 max_new_tokens: int = 4, max_prompt: Optional[int] = None, do_sample: bool = False,
+                 top_k: Optional[int] = None, temperature: float = 1.0, seed: int = 0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.AtSpeedError("atspeed_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -141,8 +142,10 @@ class Session:
             max_prompt = 512 - max(max_new_tokens - 1, 1) * N
         self.max_prompt = max_prompt
         self.device = target.device
+        self.do_sample = bool(do_sample)
         cfg = _lib.Config(K, N, max_new_tokens, max_prompt,
-                          torch.cuda.get_device_properties(self.device).multi_processor_count)
+                          torch.cuda.get_device_properties(self.device).multi_processor_count,
+                          1 if do_sample else 0, int(top_k or 0), float(temperature or 1.0), int(seed) & (2 ** 64 - 1))
         self.cfg = cfg
         nbytes = C.c_size_t(0)
         dptr = C.byref(draft.desc) if draft is not None else None
@@ -201,6 +204,25 @@ class Session:
                                                     tokens_dev.data_ptr(), scores_dev.data_ptr(), C.byref(st), self._stream()))
         return {"n_run": st.n_run, "total_accept_steps": st.total_accept_steps, "target_forwards": st.target_forwards,
                 "draft_forwards": st.draft_forwards, "kernel_launches": st.kernel_launches}
+
+    # -- sampling mode (AtSpeed-R) ---------------------------------------------------------------------
+    def set_seed(self, seed: int, user_seq: int = 0):
+        _lib.check(self.lib.atspeed_session_set_seed(self.handle, int(seed) & (2 ** 64 - 1), int(user_seq)))
+
+    def sort_result(self):
+        _lib.check(self.lib.atspeed_session_sort_result(self.handle, self._stream()))
+
+    @property
+    def sample_width(self) -> int:
+        return int(self.lib.atspeed_session_sample_width(self.handle))
+
+    def noise(self, seed: int, user_seq: int, rnd: int, level: int, site: int, kind: int, n: int) -> np.ndarray:
+        """The exact noise the kernels consume at (user, round, level, site): kind 0 uint32 bits, 1 uniform, 2 Exp(1)."""
+        stream = self.lib.atspeed_noise_stream(int(user_seq), int(rnd), int(level), int(site))
+        out = torch.empty(n, dtype=torch.int32 if kind == 0 else torch.float32, device=self.device)
+        _lib.check(self.lib.atspeed_noise_fill(int(seed) & (2 ** 64 - 1), stream, kind, n, out.data_ptr(), self._stream()))
+        a = out.cpu().numpy()
+        return a.view(np.uint32) if kind == 0 else a
 
     def profile(self, enable: bool):
         _lib.check(self.lib.atspeed_session_profile(self.handle, 1 if enable else 0))
@@ -262,7 +284,10 @@ class Session:
                 "pick_parent": self.read(_lib.F_PICK_PARENT, (ML, MK), np.int32),
                 "pick_tok": self.read(_lib.F_PICK_TOK, (ML, MK), np.int32),
                 "pick_score": self.read(_lib.F_PICK_SCORE, (ML, MK), np.float32),
-                "hit_pos": self.read(_lib.F_HIT_POS, (ML, MK), np.int32)}
+                "hit_pos": self.read(_lib.F_HIT_POS, (ML, MK), np.int32),
+                "acc": self.read(_lib.F_TR_ACC, (ML, _lib.MAX_BEAMS), np.int32),
+                "lse_q": self.read(_lib.F_LSE_Q, (ML,), np.float32),
+                "fallbacks": int(self.read(_lib.F_SCALARS, (16,), np.int32)[8])}
 
     def info(self):
         info = (C.c_int64 * 8)()

@@ -57,7 +57,8 @@ def parse():
     ap.add_argument("--constraint", default="strict", choices=["strict", "positional"])
     ap.add_argument("--profile-users", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hf-baseline-users", type=int, default=0, help="also time HF generate(num_beams=K) on the GPU")
+    ap.add_argument("--hf-baseline-users", type=int, default=3,
+                    help="also time HF generate(num_beams=K) on the same GPU (N=1 only; 0 = skip)")
     return ap.parse_args()
 
 
@@ -125,6 +126,18 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by tools/ncu_traffic.py from dram__bytes_read.sum + dram__bytes_write.sum); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    j = json.load(open(p)).get(kernel)
+    if not j:
+        return None, None
+    return j["dram_bytes_per_launch"], j
 
 
 def peaks():
@@ -298,8 +311,9 @@ def atspeed_arm(a, rank, world, local_rank):
         g = prof["gemm"]
         peak, how = peaks()
         ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] else 0.0
+        traffic, tinfo = ncu_traffic("gemm_wx_tcgen05")
         roofline = {"kernel": "gemm_wx_tcgen05", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": how,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": tinfo, "peak_source": how,
                     "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]), "launches": g["launches"],
                     "algorithmic_bytes_per_launch": g["bytes"] / max(1, g["launches"])}
     users_total = world * U * a.steps
@@ -325,8 +339,12 @@ def atspeed_arm(a, rank, world, local_rank):
                                              "shared across layers); %.1f s of CPU work" % dt}
         else:
             out["cpu_baseline"] = None
-        if a.hf_baseline_users > 0:
-            out["hf_gpu_baseline"] = hf_baseline(a, ds, fn, dev, step_users[a.warmup][: a.hf_baseline_users])
+        if world == 1 and a.hf_baseline_users > 0:
+            try:
+                out["hf_gpu_baseline"] = hf_baseline(a, ds, fn, dev, step_users[a.warmup][: a.hf_baseline_users])
+                out["hf_gpu_baseline"]["speedup_e2e"] = out["e2e"]["value"] / out["hf_gpu_baseline"]["users_per_s"]
+            except Exception as e:   # informative only: never fail the bench line on the comparison arm
+                out["hf_gpu_baseline"] = {"error": repr(e)[:200]}
         print(json.dumps(out))
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ATSPEED_ABI_VERSION 1
+#define ATSPEED_ABI_VERSION 2
 
 /* limits compiled into the library */
 #define ATSPEED_MAX_K 32          /* target beams  (reference: run_beam_sizes 10/20, code/script/inference.sh:16) */
@@ -73,6 +73,12 @@ typedef struct atspeed_config {
     int32_t max_new_tokens;   /* code/inference.py:147 */
     int32_t max_prompt;       /* longest prompt the session must hold */
     int32_t num_sms;          /* 0 = query the device */
+    /* AtSpeed-R, relaxed (sampling) acceptance -- generation_config.do_sample / top_k / temperature as read at
+     * code/beamSD.py:53,255,479-481 (set by code/inference.py:149-150).  do_sample = 0: AtSpeed-S strict top-K. */
+    int32_t do_sample;
+    int32_t top_k;            /* TopKLogitsWarper k (transformers 4.41 default 50); 1..64 required when do_sample */
+    float temperature;        /* TemperatureLogitsWarper; 1.0 = off */
+    uint64_t seed;            /* key of the counter-based noise (see atspeed_session_set_seed) */
 } atspeed_config;
 
 typedef struct atspeed_session atspeed_session;
@@ -103,7 +109,8 @@ int atspeed_session_draft(atspeed_session* s, int32_t draft_len, void* stream);
  * tree mask, then kernel (a) with B = K on every row of interest.  Asynchronous. */
 int atspeed_session_target(atspeed_session* s, int32_t draft_len, void* stream);
 
-/* verify, greedy branch = AtSpeed-S strict top-K (code/beamSD.py:242-456): kernel (b) + kernel (c) on both
+/* verify (code/beamSD.py:242-456): kernel (b) -- the greedy branch = AtSpeed-S strict top-K, or with
+ * cfg.do_sample the sampling branch = AtSpeed-R relaxed acceptance (:293-321,332-369) -- then kernel (c) on both
  * caches.  Writes the accepted length to *n_matches_host after synchronising the stream. */
 int atspeed_session_verify(atspeed_session* s, int32_t draft_len, int32_t* n_matches_host, void* stream);
 
@@ -111,6 +118,10 @@ int atspeed_session_verify(atspeed_session* s, int32_t draft_len, int32_t* n_mat
  * beams become level `+1` of the tree.  Used for the final step (code/beamSD.py:505-509) and by
  * atspeed_target_generate.  Asynchronous. */
 int atspeed_session_step(atspeed_session* s, int32_t model, int32_t width, void* stream);
+
+/* Sampling mode only (no-op otherwise): order the current beams by score, descending -- the final
+ * `beam_scores.sort(descending=True)` of code/beamSD.py:529-531.  Call once, after the last step.  Asynchronous. */
+int atspeed_session_sort_result(atspeed_session* s, void* stream);
 
 /* Final beams: tokens_host int32[K * max_new_tokens] (generated suffix per beam, score-descending),
  * scores_host float[K], *count = beams returned.  Synchronises the stream. */
@@ -143,6 +154,21 @@ int atspeed_target_generate(atspeed_session* s, const int32_t* prompt_host, int3
                             float* scores_host, int32_t* count, atspeed_stats* stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Randomness of the sampling mode.  The reference draws from torch generators at five sites per round
+ * (code/beamSD.py:72-74,304,336,343,363).  Here every draw is Philox4x32-10(key = seed, counter = (index, stream)):
+ * `stream` = atspeed_noise_stream(user_seq, round, level, site) with site 0 draft multinomial, 1 acceptance
+ * uniforms, 2 random-K-of-accepted keys, 3 residual multinomial, 4 bonus multinomial, 5 plain target step;
+ * `index` = position in the reference's flat [n_prev * V] space (sites 0,3,4,5) or the draft pick position (1,2).
+ * A multinomial without replacement over p is the top-n of p / Exp(1) noise, as in ATen.
+ * ---------------------------------------------------------------------------------------------- */
+/* Re-key the session: the next atspeed_session_begin* uses (seed, user_seq), the one after (seed, user_seq + 1), ... */
+int atspeed_session_set_seed(atspeed_session* s, uint64_t seed, uint64_t user_seq);
+uint64_t atspeed_noise_stream(uint64_t user_seq, uint32_t round, uint32_t level, uint32_t site);
+/* out_dev[i] = noise(seed, stream, i), i < n: kind 0 raw uint32, 1 uniform (0,1) float, 2 Exp(1) float. Asynchronous.
+ * Tests replay these exact numbers into the CPU oracle. */
+int atspeed_noise_fill(uint64_t seed, uint64_t stream, int32_t kind, int32_t n, void* out_dev, void* stream_handle);
+
+/* ------------------------------------------------------------------------------------------------
  * Introspection for parity tests (reads device state back; synchronises)
  * ---------------------------------------------------------------------------------------------- */
 enum atspeed_field {
@@ -159,12 +185,16 @@ enum atspeed_field {
     ATSPEED_F_LOGITS_TARGET = 10,/* float[rows][ld]: last target logits (rows, ld via atspeed_session_info) */
     ATSPEED_F_LOGITS_DRAFT = 11,
     ATSPEED_F_ROW_NODE = 12,     /* int32[R_max]   trie node of each logits row of the last batch */
-    ATSPEED_F_LEVEL_NODE = 13    /* int32[5][64] */
+    ATSPEED_F_LEVEL_NODE = 13,   /* int32[5][64] */
+    ATSPEED_F_TR_ACC = 14,       /* int32[5][64]   relaxed verify: acceptance flag of each draft pick per level */
+    ATSPEED_F_LSE_Q = 15         /* float[5]       log-normaliser of the draft's flat softmax per step */
 };
 int atspeed_session_read(atspeed_session* s, int32_t field, void* host_dst, size_t bytes, void* stream);
 /* info[0]=logits ld, [1]=R_max, [2]=T_max, [3]=S_max(target), [4]=A_cap, [5]=kernel launches so far,
- * [6]=rows of the last target batch, [7]=rows of the last draft batch */
+ * [6]=rows of the last target batch, [7]=rows of the last draft batch.  The sampling mode's warped candidate
+ * count per row B = max(top_k, 2 if K > 1 else 1) is returned by atspeed_session_sample_width. */
 int atspeed_session_info(atspeed_session* s, int64_t* info8);
+int atspeed_session_sample_width(atspeed_session* s);
 
 /* Per-launch CUDA-event timing (the reference's `Timer` blocks, code/beamSD.py:12-37,51,60,220,276, without the
  * forced device syncs): when enabled every kernel launch is bracketed by two events on the caller's stream.

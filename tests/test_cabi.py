@@ -25,7 +25,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in atspeed.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes signature in _lib.SYMBOLS"
     assert sorted(_lib.SYMBOLS) == declared
-    assert lib.atspeed_abi_version() == 1
+    assert lib.atspeed_abi_version() == _lib.ABI_VERSION
 
 
 def test_argument_errors_are_codes_not_crashes():
