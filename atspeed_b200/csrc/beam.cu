@@ -533,7 +533,7 @@ tree_select_sample_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int level, int ro
             const int j = c / B, h = c - j * B;
             const uint32_t idx = static_cast<uint32_t>(j) * static_cast<uint32_t>(V) + static_cast<uint32_t>(cand_tok[(row0 + j) * B + h]);
             const float q = expf(s - lse);
-            k = rank_key(q / noise_exponential(sc.seed, stream, idx), idx);
+            if (q > 0.f) k = rank_key(q / noise_exponential(sc.seed, stream, idx), idx);   // zero-probability entries are never drawn
         }
         keys[c] = k;
     }
@@ -627,7 +627,8 @@ tree_verify_relaxed_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int draft_len, i
                 if (tflat[c] > -INFINITY) {
                     const int k = c / B, h = c - k * B, row = rowbase + cur_idx[k];
                     const uint32_t idx = static_cast<uint32_t>(k) * V + static_cast<uint32_t>(cand_tok[row * B + h]);
-                    key = rank_key(expf(tflat[c] - lse_p) / noise_exponential(sc.seed, lv_stream | SITE_BONUS, idx), idx);
+                    const float pb = expf(tflat[c] - lse_p);
+                    if (pb > 0.f) key = rank_key(pb / noise_exponential(sc.seed, lv_stream | SITE_BONUS, idx), idx);
                 }
                 keys[c] = key;
             }

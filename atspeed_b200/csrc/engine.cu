@@ -649,6 +649,8 @@ uint64_t atspeed_noise_stream(uint64_t user_seq, uint32_t round, uint32_t level,
     return noise_stream(user_seq, round, level, site);
 }
 
+uint32_t atspeed_noise_host_u32(uint64_t seed, uint64_t stream, uint32_t index) { return philox_u32(seed, stream, index); }
+
 int atspeed_noise_fill(uint64_t seed, uint64_t stream, int32_t kind, int32_t n, void* out_dev, void* stream_handle) {
     return noise_fill(seed, stream, kind, n, out_dev, static_cast<cudaStream_t>(stream_handle));
 }

@@ -164,6 +164,9 @@ int atspeed_target_generate(atspeed_session* s, const int32_t* prompt_host, int3
 /* Re-key the session: the next atspeed_session_begin* uses (seed, user_seq), the one after (seed, user_seq + 1), ... */
 int atspeed_session_set_seed(atspeed_session* s, uint64_t seed, uint64_t user_seq);
 uint64_t atspeed_noise_stream(uint64_t user_seq, uint32_t round, uint32_t level, uint32_t site);
+/* The raw 32 random bits of (seed, stream, index), computed on the HOST by the same function the kernels inline
+ * (csrc/noise.cuh): lets CPU-only tests pin the generator against the published Philox4x32-10 test vectors. */
+uint32_t atspeed_noise_host_u32(uint64_t seed, uint64_t stream, uint32_t index);
 /* out_dev[i] = noise(seed, stream, i), i < n: kind 0 raw uint32, 1 uniform (0,1) float, 2 Exp(1) float. Asynchronous.
  * Tests replay these exact numbers into the CPU oracle. */
 int atspeed_noise_fill(uint64_t seed, uint64_t stream, int32_t kind, int32_t n, void* out_dev, void* stream_handle);

@@ -149,36 +149,58 @@ def _topk_lowest_index(flat: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.
     return vals[keep], order[keep]
 
 
+# draw sites (the CUDA path's noise streams are named the same way: csrc/noise.cuh)
+SITE_DRAFT, SITE_ACCEPT, SITE_PERM, SITE_RESIDUAL, SITE_BONUS, SITE_STEP = 0, 1, 2, 3, 4, 5
+
+
+class ReferenceUndefined(RuntimeError):
+    """The reference's behaviour is undefined here (its torch.multinomial call raises / samples disallowed ids)."""
+
+
 @dataclass
 class SamplingCfg:
+    """Randomness of the sampling branch.  Two modes:
+      * generator mode (default): the same torch calls, in the same order, on the same generators as the
+        reference -> reproduces the reference draw for draw under one torch.manual_seed (tests/golden/bssd_relaxed.json);
+      * noise mode (`noise_fn` set): every draw is a pure function of (site, round, level, index), the contract of the
+        CUDA path.  noise_fn(kind, site, round, level, n) -> tensor[n]; kind "exp" (Exp(1) floats), "uniform"
+        (floats in (0,1)) or "bits" (integers).  A multinomial without replacement is the top-n of p / exp-noise
+        (what ATen computes from its generator), restricted to p > 0."""
     temperature: float = 1.0
     top_k: Optional[int] = 50
     generator: Optional[torch.Generator] = None          # device generator of the reference (CPU here)
     cpu_generator: Optional[torch.Generator] = None      # torch.randperm's generator (beamSD.py:343)
-    # explicit draws for record/replay against the CUDA path (each consumed in call order):
-    replay: Optional[dict] = None
+    noise_fn: Optional[Callable] = None
+    # empty residual distribution (SURVEY 8a-5): False = behave like the reference (raise / uniform over everything),
+    # True = the defined behaviour of the CUDA path (draw the missing beams from p itself)
+    defined_fallback: bool = False
+    round: int = 0                                        # maintained by bssd()
+    fallbacks: int = 0
 
-    def multinomial(self, p: torch.Tensor, n: int) -> torch.Tensor:
-        if self.replay is not None:
-            noise = self.replay["exp"].pop(0)
-            assert noise.numel() == p.numel(), (noise.shape, p.shape)
-            q = p / noise.to(p.dtype).view(-1)
-            return _topk_lowest_index(q, n)[1]
+    def multinomial(self, p: torch.Tensor, n: int, site: int = 0, level: int = 0) -> torch.Tensor:
+        if self.noise_fn is not None:
+            noise = self.noise_fn("exp", site, self.round, level, p.numel()).to(p.dtype).view(-1)
+            order = _topk_lowest_index(p / noise, n)[1]
+            return order[p[order] > 0]
         return torch.multinomial(p, n, generator=self.generator)
 
-    def uniform(self, n: int) -> torch.Tensor:
-        if self.replay is not None:
-            return self.replay["uniform"].pop(0).view(-1)
+    def uniform(self, n: int, level: int = 0) -> torch.Tensor:
+        if self.noise_fn is not None:
+            return self.noise_fn("uniform", SITE_ACCEPT, self.round, level, n).view(-1)
         return torch.rand(n, generator=self.generator)
 
-    def randperm(self, n: int) -> torch.Tensor:
-        if self.replay is not None:
-            return self.replay["perm"].pop(0).view(-1)
-        return torch.randperm(n, generator=self.cpu_generator)
+    def random_subset(self, accepted_pos: torch.Tensor, n_picks: int, k: int, level: int = 0) -> torch.Tensor:
+        """Indices (into the accepted list) of a uniformly random k-subset: `torch.randperm(n)[:k]` (beamSD.py:343),
+        or in noise mode the k accepted picks with the smallest (bits, position) keys."""
+        if self.noise_fn is not None:
+            bits = self.noise_fn("bits", SITE_PERM, self.round, level, n_picks).view(-1).to(torch.int64)
+            key = bits[accepted_pos] * (1 << 32) + accepted_pos.to(torch.int64)
+            return torch.argsort(key)[:k]
+        return torch.randperm(len(accepted_pos), generator=self.cpu_generator)[:k]
 
 
 def _expand(logits_rows: torch.Tensor, frontier: List[Node], width: int, fn, prompt, V,
-            sampling: Optional[SamplingCfg], num_beams_for_warp: int):
+            sampling: Optional[SamplingCfg], num_beams_for_warp: int, site: int = SITE_STEP, level: int = 0):
     """One beam-search step over `frontier` (beamSD.py:57-86): full-vocab log_softmax, constraint
     mask applied afterwards, + parent score, flatten, top-`width` (or multinomial), split into
     (parent row, token). Returns children nodes (rank / sample order) and q (sampling only)."""
@@ -191,7 +213,7 @@ def _expand(logits_rows: torch.Tensor, frontier: List[Node], width: int, fn, pro
     probs = None
     if sampling is not None:
         probs = torch.softmax(flat, -1)
-        idx = sampling.multinomial(probs, width)
+        idx = sampling.multinomial(probs, width, site, level)
         vals = flat[idx]
         keep = torch.isfinite(vals)
         vals, idx = vals[keep], idx[keep]
@@ -303,7 +325,7 @@ def _verify_relaxed(rows_of, roots, levels, level_q, level_flat_idx, K, fn, prom
         flat_t = (scores + parent[:, None]).reshape(-1)
         if i == dl:  # bonus level: sample K from the target
             p = torch.softmax(flat_t, -1)
-            idx = sampling.multinomial(p, K)
+            idx = sampling.multinomial(p, K, SITE_BONUS, i)
             kids = [Node(int(j % V), cur[int(j // V)], float(flat_t[j])) for j in idx]
             break
         prev = roots if i == 0 else levels[i - 1]
@@ -320,13 +342,13 @@ def _verify_relaxed(rows_of, roots, levels, level_q, level_flat_idx, K, fn, prom
         q = torch.nan_to_num(q, nan=0.0)
         picks = level_flat_idx[i]
         ratio = p[picks] / q[picks]
-        r = sampling.uniform(len(picks))
+        r = sampling.uniform(len(picks), i)
         acc = r <= ratio
         acc_tok = picks[acc]
         trace.hits.append([int(j) for j in torch.nonzero(acc).view(-1)])
         if int(acc.sum()) >= K:
             m += 1
-            sel = acc_tok[sampling.randperm(len(acc_tok))[:K]].sort()[0]
+            sel = acc_tok[sampling.random_subset(torch.nonzero(acc).view(-1), len(picks), K, i)].sort()[0]
             level = levels[i]
             pos = [int(torch.nonzero(picks == y).view(-1)[0]) for y in sel]
             cur = [level[pp] for pp in pos]
@@ -337,12 +359,18 @@ def _verify_relaxed(rows_of, roots, levels, level_q, level_flat_idx, K, fn, prom
             newp = torch.clamp(p - q, min=0)
             newp[acc_tok] = 0
             if float(newp.sum()) == 0:
-                if i == 0:
+                sampling.fallbacks += 1
+                if sampling.defined_fallback:      # the CUDA path's defined behaviour: draw from p itself
+                    newp = p.clone()
+                    newp[acc_tok] = 0
+                elif i == 0:
                     newp[...] = torch.finfo(newp.dtype).tiny
-                # i > 0: the reference's fill (:355-357) writes into a copy and is a no-op
+                else:
+                    # the reference's fill (:355-357) writes into a copy and is a no-op: its multinomial then raises
+                    raise ReferenceUndefined("empty residual distribution at level %d" % i)
             else:
                 newp = newp / newp.sum()
-            extra = sampling.multinomial(newp, K - int(acc.sum()))
+            extra = sampling.multinomial(newp, K - int(acc.sum()), SITE_RESIDUAL, i)
             sel = torch.cat((acc_tok, extra)).sort()[0]
             kids = [Node(int(y % V), prev[int(y // V)], float(flat_d[y])) for y in sel]
             trace.target_picks.append([(int(y // V), int(y % V), float(flat_d[y])) for y in sel])
@@ -367,9 +395,11 @@ def bssd(target: RefLlama, draft: RefLlama, prompt: Sequence[int], K: int, N: in
     beams = None
     while done < max_new_tokens:
         dl = min(gamma, max_new_tokens - done - 1)
+        if sampling is not None:
+            sampling.round = len(accept)
         if dl == 0:  # one plain target step (beamSD.py:505-509)
             rows = tgt.forward_prompt(root) if first else tgt.forward_nodes(roots, roots)
-            beams, _, _, _ = _expand(rows, roots, K, fn, prompt, V, sampling, len(roots))
+            beams, _, _, _ = _expand(rows, roots, K, fn, prompt, V, sampling, K, SITE_STEP, 0)
             break
         tr = RoundTrace(dl, len(roots))
         # 1. draft: dl beam-search steps of width N
@@ -384,7 +414,7 @@ def bssd(target: RefLlama, draft: RefLlama, prompt: Sequence[int], K: int, N: in
                     rows = dft.forward_nodes(batch, roots)
             else:
                 rows = dft.forward_nodes(frontier, frontier)
-            kids, idx, q, _ = _expand(rows, frontier, N, fn, prompt, V, sampling, len(frontier))
+            kids, idx, q, _ = _expand(rows, frontier, N, fn, prompt, V, sampling, K, SITE_DRAFT, j)
             tr.draft_levels.append([(frontier.index(c.parent), c.tok, c.score) for c in kids])
             levels.append(kids), level_q.append(q), level_idx.append(idx)
             frontier = kids
@@ -428,9 +458,11 @@ def target_generate(target: RefLlama, prompt: Sequence[int], K: int, max_new_tok
     tgt = _ModelState("t", target, prompt)
     root = Node(None, None, 0.0)
     frontier = [root]
+    if sampling is not None:
+        sampling.round = 0
     for step in range(max_new_tokens):
         rows = tgt.forward_prompt(root) if step == 0 else tgt.forward_nodes(frontier, frontier)
-        frontier, _, _, _ = _expand(rows, frontier, K, fn, prompt, V, sampling, len(frontier))
+        frontier, _, _, _ = _expand(rows, frontier, K, fn, prompt, V, sampling, K, SITE_STEP, step)
     if sampling is not None:
         frontier = sorted(frontier, key=lambda b: -b.score)
     return _finish(prompt, frontier, dict(n_target_forward=tgt.n_forward, target_tokens=tgt.tokens_forwarded))

@@ -1,0 +1,218 @@
+"""GPU parity of AtSpeed-R (do_sample=True: sampling draft, relaxed acceptance, residual resampling, bonus level).
+
+The CUDA path's randomness is counter-based (csrc/noise.cuh), so the test can hand the CPU oracle exactly the numbers
+the kernels consumed (atspeed_noise_fill) -- and exactly the LOGITS the CUDA forward produced -- and demand that every
+decision is identical: sampled draft levels, acceptance flags, accepted lengths, carried beams, resampled beams, final
+ranked lists.  (The oracle's sampling branch itself is pinned to the unmodified reference in
+tests/test_oracle_relaxed.py.)  Scores are compared to 2e-4 (log-sum-exp summation order)."""
+import numpy as np
+import pytest
+import torch
+
+from _common import constraint_fn, dataset, stack_weights
+from oracle import bssd_ref
+
+pytestmark = pytest.mark.gpu
+
+
+class _GC:
+    def __init__(self, num_beams, temperature=1.0, top_k=50):
+        self.num_beams, self.do_sample, self.max_new_tokens = num_beams, True, 4
+        self.temperature, self.top_k = temperature, top_k
+
+
+class ModelHandle:
+    def __init__(self, dm, num_beams, temperature=1.0, top_k=50):
+        self._atspeed_device_model = dm
+        self.generation_config = _GC(num_beams, temperature, top_k)
+        self.device = dm.device
+
+
+@pytest.fixture(scope="module")
+def device_models():
+    from atspeed_b200.engine import DeviceModel, ModelSpec
+    cache = {}
+
+    def get(ds_name, which):
+        key = (ds_name, which)
+        if key not in cache:
+            sh, W = stack_weights("ref_bf16", ds_name, which)
+            spec = ModelSpec(sh.vocab, sh.hidden, sh.n_layers, sh.n_heads, sh.head_dim, sh.mlp, sh.eps, sh.rope_theta)
+            cache[key] = DeviceModel(spec, W, "cuda")
+        return cache[key]
+
+    return get
+
+
+class _TapeCache:
+    def __init__(self):
+        self.n = 0
+
+    def __len__(self):
+        return self.n
+
+
+class TapeModel:
+    """Stands in for a RefLlama inside oracle/bssd_ref.py: forward() returns the logits the GPU computed for the
+    corresponding forward (recorded in call order).  A shape mismatch means the two sides took different decisions."""
+
+    def __init__(self, vocab, tape):
+        self.shape = type("S", (), {"vocab": vocab})()
+        self.tape = list(tape)
+
+    def new_cache(self):
+        return _TapeCache()
+
+    def forward(self, tokens, pos, vis, cache, rows=None):
+        cache.n += len(tokens)
+        want = len(tokens) if rows is None else len(rows)
+        assert self.tape, "oracle asked for a forward the GPU did not run"
+        out = self.tape.pop(0)
+        assert out.shape[0] == want, f"oracle wants {want} logits rows, GPU produced {out.shape[0]}"
+        return out
+
+
+def _run_gpu(sess, prompt, gamma, K, N, seed):
+    """Drive the session stage by stage, recording the logits of every forward and the verify traces."""
+    sess.set_seed(seed, 0)
+    sess.begin(prompt)
+    t_tape, d_tape, rounds = [], [], []
+    done, first = 0, True
+    while done < 4:
+        dl = min(gamma, 4 - done - 1)
+        if dl == 0:
+            n_roots = 1 if first else int(sess.levels()["cnt"][0])
+            sess.step(0, K)
+            t_tape.append(torch.from_numpy(sess.logits(0, sess.info()[6])[:n_roots].copy()))
+            break
+        for j in range(dl):
+            cnt_before = sess.levels()["cnt"]
+            sess.step(1, N)
+            n_rows = 1 if (first and j == 0) else int(cnt_before[j])
+            d_tape.append(torch.from_numpy(sess.logits(1, sess.info()[7])[:n_rows].copy()))
+        lv = sess.levels()
+        sess.target_forward(dl)
+        lg = sess.logits(0, sess.info()[6])
+        n_root = 1 if first else K
+        parts = [lg[: (1 if first else int(lv["cnt"][0]))]]
+        if first:
+            t_tape.append(torch.from_numpy(parts[0].copy()))
+            parts = []
+        for l in range(1, dl + 1):
+            base = n_root + (l - 1) * N
+            parts.append(lg[base: base + int(lv["cnt"][l])])
+        t_tape.append(torch.from_numpy(np.concatenate(parts, 0).copy()))
+        m = sess.verify(dl)
+        tr = sess.verify_trace()
+        rounds.append({"levels": lv, "trace": tr, "n_matches": m, "dl": dl})
+        done += m + 1
+        first = False
+    sess.sort_result()
+    return sess.result(), t_tape, d_tape, rounds
+
+
+CASES = [("beauty", "positional", "correlated", 10, 40, 3, 1.0), ("beauty", "strict", "correlated", 10, 40, 3, 1.0),
+         ("games", "positional", "correlated", 20, 40, 3, 1.0), ("beauty", "strict", "independent", 10, 40, 3, 1.0),
+         ("games", "strict", "correlated", 5, 10, 2, 0.7), ("beauty", "positional", "independent", 20, 40, 3, 1.3),
+         ("beauty", "positional", "correlated", 1, 40, 3, 1.0)]
+
+
+@pytest.mark.parametrize("ds_name,kind,draft,K,N,gamma,temp", CASES)
+def test_relaxed_decisions_match_oracle(ds_name, kind, draft, K, N, gamma, temp, device_models):
+    from atspeed_b200 import _lib, beamSD
+    ds = dataset(ds_name)
+    fn = constraint_fn(ds_name, kind)
+    V = ds.vocab_size
+    tm = ModelHandle(device_models(ds_name, "target"), K, temp)
+    dm = ModelHandle(device_models(ds_name, draft), N, temp)
+    stats = {"users": 0, "accepted_levels": 0, "rejected_rounds": 0, "fallbacks": 0, "bonus": 0}
+    for u, seed in ((0, 11), (1, 12), (17, 13), (100, 14), (5, 2025)):
+        prompt = ds.prompt_ids(u)
+        sess = beamSD.get_session(tm, dm, prompt, 4, fn)
+        assert sess.do_sample and sess.sample_width == max(50, 2 if K > 1 else 1)
+        res, t_tape, d_tape, rounds = _run_gpu(sess, prompt, gamma, K, N, seed)
+
+        def noise_fn(kind_, site, rnd, level, n, _seed=seed):
+            code = {"bits": 0, "uniform": 1, "exp": 2}[kind_]
+            a = sess.noise(_seed, 0, rnd, level, site, code, n)
+            return torch.from_numpy(a.astype(np.int64) if code == 0 else a.copy())
+
+        cfg = bssd_ref.SamplingCfg(temperature=temp, top_k=50, noise_fn=noise_fn, defined_fallback=True)
+        ref = bssd_ref.bssd(TapeModel(V, t_tape), TapeModel(V, d_tape), prompt, K, N, gamma, 4, fn, sampling=cfg)
+        P = len(prompt)
+        assert res["tokens"].tolist() == ref.sequences[:, P:].tolist(), (u, seed)
+        np.testing.assert_allclose(res["scores"], ref.scores, atol=2e-4)
+        assert [r["n_matches"] for r in rounds] == ref.accept_steps
+        assert all(res["scores"][i] >= res["scores"][i + 1] for i in range(len(res["scores"]) - 1))
+        for r, tr in zip(rounds, ref.rounds):
+            lv = r["levels"]
+            for l in range(1, r["dl"] + 1):     # sampled draft levels: (parent, token) in sample order
+                n = int(lv["cnt"][l])
+                got = [(int(lv["parent"][l][i]), int(lv["tok"][l][i])) for i in range(n)]
+                assert got == [(p, t) for p, t, _ in tr.draft_levels[l - 1]], (u, l)
+                np.testing.assert_allclose(lv["score"][l][:n], [s for _, _, s in tr.draft_levels[l - 1]], atol=2e-4)
+            for i, hits in enumerate(tr.hits):  # acceptance flags of every draft pick
+                n = int(lv["cnt"][i + 1])
+                assert [j for j in range(n) if r["trace"]["acc"][i][j]] == hits, (u, i)
+            for i, picks in enumerate(tr.target_picks):
+                n = int(r["trace"]["npick"][i])
+                got = [(int(r["trace"]["pick_parent"][i][p]), int(r["trace"]["pick_tok"][i][p])) for p in range(n)]
+                assert got == [(pp, t) for pp, t, _ in picks], (u, i)
+            stats["accepted_levels"] += r["n_matches"]
+            stats["rejected_rounds"] += int(r["n_matches"] < r["dl"])
+            stats["bonus"] += int(r["n_matches"] == r["dl"])
+        n_fb = rounds[-1]["trace"]["fallbacks"] if rounds else 0     # cumulative per user on the device
+        assert cfg.fallbacks == n_fb
+        stats["fallbacks"] += n_fb
+        stats["users"] += 1
+    print(ds_name, kind, draft, K, N, gamma, temp, stats)
+    assert stats["users"] == 5
+
+
+def test_relaxed_through_the_reference_entry_points(device_models):
+    """BSSD / target_generate with generation_config.do_sample=True: reproducible under set_seed, keys present,
+    beams valid and sorted; a different seed gives different samples."""
+    from atspeed_b200 import beamSD
+    from atspeed_b200.constraint import compile_constraint
+    ds = dataset("beauty")
+    fn = constraint_fn("beauty", "strict")
+    tm = ModelHandle(device_models("beauty", "target"), 10)
+    dm = ModelHandle(device_models("beauty", "correlated"), 40)
+    prompt = ds.prompt_ids(2)
+    ids = torch.tensor([prompt], device="cuda")
+    csr = compile_constraint(fn, prompt, 4)
+    outs = []
+    for seed in (2025, 2025, 7):
+        beamSD.set_seed(seed)
+        outs.append(beamSD.BSSD(tm, dm, {"input_ids": ids}, 3, 4, prefix_allowed_tokens_fn=fn))
+    a, b, c = outs
+    assert torch.equal(a["beam_sequence"], b["beam_sequence"]) and torch.equal(a["beam_scores"], b["beam_scores"])
+    assert not torch.equal(a["beam_sequence"], c["beam_sequence"])
+    for k in ("time_cost", "n_run", "draft_time_cost", "target_time_cost", "verify_time_cost", "total_accept_steps",
+              "total_accept_tokens", "ave_accept_tokens"):
+        assert k in a
+    P = len(prompt)
+    sc = a["beam_scores"].cpu().numpy()
+    assert all(sc[i] >= sc[i + 1] for i in range(len(sc) - 1))
+    for row in a["beam_sequence"][:, P:].cpu().tolist():
+        assert csr.walk(row) >= 0
+    tg = beamSD.target_generate(tm, {"input_ids": ids}, 4, prefix_allowed_tokens_fn=fn, seed=5)
+    assert tg["beam_sequence"].shape == (10, P + 4)
+    for row in tg["beam_sequence"][:, P:].cpu().tolist():
+        assert csr.walk(row) >= 0
+
+
+def test_noise_fill_matches_host_generator():
+    from atspeed_b200 import _lib
+    lib = _lib.load()
+    stream = lib.atspeed_noise_stream(3, 2, 1, 4)
+    out = torch.empty(4096, dtype=torch.int32, device="cuda")
+    _lib.check(lib.atspeed_noise_fill(777, stream, 0, 4096, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint32)
+    want = np.array([lib.atspeed_noise_host_u32(777, stream, i) for i in range(4096)], dtype=np.uint32)
+    assert (got == want).all()
+    u = torch.empty(4096, dtype=torch.float32, device="cuda")
+    _lib.check(lib.atspeed_noise_fill(777, stream, 1, 4096, u.data_ptr(), None))
+    un = ((want >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+    assert (u.cpu().numpy() == un).all()
