@@ -6,12 +6,13 @@
 // (b) a 512-bit mask over the accepted/tree slots that follow the prompt -- a few words per token,
 // produced on the device by the beam kernels (beam.cu), never a dense mask.
 //
-// One CTA = 64 queries of one head (4 warps x 16 rows), keys streamed in tiles of 64 through shared
-// memory, flash-style online softmax in fp32.  QK^T and PV run on the legacy warp-level tensor-core
-// path (mma.sync m16n8k16 bf16); P is split into hi+lo bf16 parts so the PV product is accurate to
-// ~2^-16, which keeps this kernel within fp32-softmax tolerance of oracle/llama_ref.py.  The kernel
-// is <5% of a 7B forward at T<=300 (the GEMMs in gemm.cu dominate); a tcgen05 version is listed as
-// next work in DESIGN.md.
+// One CTA = 64 queries of one head (4 warps x 16 rows); the key tiles some query of the CTA can see are
+// streamed 64 keys at a time through a double-buffered cp.async ring, fragments come from ldmatrix
+// (transposing for V), flash-style online softmax in fp32.  QK^T and PV run on the warp-level
+// tensor-core path (mma.sync m16n8k16 bf16): at T <= 512 tokens x <= ~700 keys the whole problem is
+// < 2 GFLOP per layer, far below what would amortise a TMEM round trip; the kernel is latency-bound.
+// P is split into hi+lo bf16 parts so the PV product is accurate to ~2^-16, which keeps this kernel
+// within fp32-softmax tolerance of oracle/llama_ref.py.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -53,22 +54,40 @@ __device__ __forceinline__ uint64_t vis_window(const uint32_t* vrow, int key0, i
     return out;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;     // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
+}
+
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS)
 tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                       const __nv_bfloat16* __restrict__ vcache, const int* __restrict__ prefix_len,
                       const uint32_t* __restrict__ vis, int vis_base, int T, int S, int n_heads, float scale,
                       __nv_bfloat16* __restrict__ out) {
-    constexpr int LDS = D + 8;                     // padded row (bf16 elements): conflict-free fragment loads
+    constexpr int LDS = D + 8;                     // padded row (bf16 elements): conflict-free ldmatrix, rows 16-byte aligned
     extern __shared__ __align__(16) uint8_t att_smem[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
-    __nv_bfloat16* sK = sQ + ATT_BQ * LDS;
-    __nv_bfloat16* sV = sK + ATT_BK * LDS;
+    __nv_bfloat16* sKV = sQ + ATT_BQ * LDS;        // [2 buffers][K | V][ATT_BK][LDS]
     __shared__ uint32_t sVis[ATT_BQ * VIS_WORDS];
     __shared__ int sPl[ATT_BQ];
     __shared__ int sMaxPl;
     __shared__ uint32_t sAny[VIS_WORDS];
+    __shared__ int sTiles[64];                     // key tiles some query of this CTA can see
+    __shared__ int sNTiles;
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int head = blockIdx.y, q0 = blockIdx.x * ATT_BQ;
     const int HD = n_heads * D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
@@ -76,13 +95,13 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     if (threadIdx.x == 0) sMaxPl = 0;
     if (threadIdx.x < VIS_WORDS) sAny[threadIdx.x] = 0;
     __syncthreads();
-    // stage Q tile, prefix lengths and visibility words
+    // stage the Q tile with cp.async (group 0), prefix lengths and visibility words directly
     for (int i = threadIdx.x; i < ATT_BQ * (D / 8); i += ATT_THREADS) {
         const int r = i / (D / 8), c = (i % (D / 8)) * 8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (q0 + r < T) v = *reinterpret_cast<const uint4*>(q + static_cast<long long>(q0 + r) * HD + head * D + c);
-        *reinterpret_cast<uint4*>(&sQ[r * LDS + c]) = v;
+        const bool ok = q0 + r < T;
+        cp_async16(&sQ[r * LDS + c], q + static_cast<long long>(ok ? q0 + r : 0) * HD + head * D + c, ok);
     }
+    cp_async_commit();
     for (int i = threadIdx.x; i < ATT_BQ; i += ATT_THREADS) {
         const int pl = (q0 + i < T) ? prefix_len[q0 + i] : 0;
         sPl[i] = pl;
@@ -95,6 +114,34 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
         if (v) atomicOr(&sAny[w], v);
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        // tiles no query of this CTA can see are skipped (block-uniform list)
+        int n = 0;
+        const int max_pl = sMaxPl;
+        for (int key0 = 0; key0 < S && n < 64; key0 += ATT_BK) {
+            bool need = key0 < max_pl;
+            if (!need && key0 + ATT_BK > vis_base) {
+                const int b0 = key0 - vis_base, b1 = b0 + ATT_BK - 1;
+                for (int w = (b0 < 0 ? 0 : b0 >> 5); w <= (b1 >> 5) && w < VIS_WORDS; ++w) need |= sAny[w] != 0;
+            }
+            if (need) sTiles[n++] = key0;
+        }
+        sNTiles = n;
+    }
+    __syncthreads();
+    const int n_tiles = sNTiles;
+
+    auto load_tile = [&](int buf, int key0) {
+        __nv_bfloat16* sK = sKV + static_cast<size_t>(buf) * 2 * ATT_BK * LDS;
+        __nv_bfloat16* sV = sK + ATT_BK * LDS;
+        for (int i = threadIdx.x; i < ATT_BK * (D / 8); i += ATT_THREADS) {
+            const int r = i / (D / 8), c = (i % (D / 8)) * 8;
+            const bool ok = key0 + r < S;
+            const long long off = static_cast<long long>(ok ? key0 + r : 0) * HD + head * D + c;
+            cp_async16(&sK[r * LDS + c], kcache + off, ok);
+            cp_async16(&sV[r * LDS + c], vcache + off, ok);
+        }
+    };
 
     const int r0 = warp * 16 + g, r1 = r0 + 8;         // the two query rows this thread owns
     const int pl0 = sPl[r0], pl1 = sPl[r1];
@@ -103,28 +150,22 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 
-    const int max_pl = sMaxPl;
-    for (int key0 = 0; key0 < S; key0 += ATT_BK) {
-        // skip tiles no query of this CTA can see (block-uniform decision)
-        bool need = key0 < max_pl;
-        if (!need && key0 + ATT_BK > vis_base) {
-            const int b0 = key0 - vis_base, b1 = b0 + ATT_BK - 1;
-            for (int w = (b0 < 0 ? 0 : b0 >> 5); w <= (b1 >> 5) && w < VIS_WORDS; ++w) need |= sAny[w] != 0;
-        }
-        if (!need) continue;
-        __syncthreads();   // previous tile fully consumed
-        for (int i = threadIdx.x; i < ATT_BK * (D / 8); i += ATT_THREADS) {
-            const int r = i / (D / 8), c = (i % (D / 8)) * 8;
-            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-            if (key0 + r < S) {
-                const long long off = static_cast<long long>(key0 + r) * HD + head * D + c;
-                kv = *reinterpret_cast<const uint4*>(kcache + off);
-                vv = *reinterpret_cast<const uint4*>(vcache + off);
-            }
-            *reinterpret_cast<uint4*>(&sK[r * LDS + c]) = kv;
-            *reinterpret_cast<uint4*>(&sV[r * LDS + c]) = vv;
-        }
+    if (n_tiles > 0) load_tile(0, sTiles[0]);
+    cp_async_commit();
+    // ldmatrix lane addressing (see the fragment layouts of mma.m16n8k16):
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;        // A operand (Q), 16x16 tiles
+    const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;        // B operand (K), 2 n-blocks x 16 k
+    const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_col = (lane >> 4) * 8;        // B operand (V, transposed)
+
+    for (int it = 0; it < n_tiles; ++it) {
+        const int key0 = sTiles[it];
+        const int buf = it & 1;
+        if (it + 1 < n_tiles) load_tile(buf ^ 1, sTiles[it + 1]);     // overlaps this tile's math
+        cp_async_commit();
+        cp_async_wait<1>();                                            // this tile (and Q) have landed
         __syncthreads();
+        const __nv_bfloat16* sK = sKV + static_cast<size_t>(buf) * 2 * ATT_BK * LDS;
+        const __nv_bfloat16* sV = sK + ATT_BK * LDS;
 
         // ---- S = Q K^T for this warp's 16 rows x 64 keys ----
         float s[ATT_BK / 8][4];
@@ -132,17 +173,14 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
         for (int nb = 0; nb < ATT_BK / 8; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-            const __nv_bfloat16* qa = &sQ[(warp * 16 + g) * LDS + kk * 16 + 2 * t4];
-            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(qa);
-            const uint32_t a1 = *reinterpret_cast<const uint32_t*>(qa + 8 * LDS);
-            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(qa + 8);
-            const uint32_t a3 = *reinterpret_cast<const uint32_t*>(qa + 8 * LDS + 8);
+            uint32_t a[4];
+            ldmatrix_x4(a, &sQ[(warp * 16 + a_row) * LDS + kk * 16 + a_col]);
 #pragma unroll
-            for (int nb = 0; nb < ATT_BK / 8; ++nb) {
-                const __nv_bfloat16* kb = &sK[(nb * 8 + g) * LDS + kk * 16 + 2 * t4];
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kb);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kb + 8);
-                mma_bf16_16816(s[nb], a0, a1, a2, a3, b0, b1);
+            for (int nb = 0; nb < ATT_BK / 8; nb += 2) {
+                uint32_t b[4];
+                ldmatrix_x4(b, &sK[(nb * 8 + b_row) * LDS + kk * 16 + b_col]);
+                mma_bf16_16816(s[nb], a[0], a[1], a[2], a[3], b[0], b[1]);
+                mma_bf16_16816(s[nb + 1], a[0], a[1], a[2], a[3], b[2], b[3]);
             }
         }
         // ---- mask + online softmax ----
@@ -204,18 +242,19 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
             const uint32_t al0 = pack_bf16(plo[0], plo[1]), al1 = pack_bf16(plo[2], plo[3]);
             const uint32_t al2 = pack_bf16(plo[4], plo[5]), al3 = pack_bf16(plo[6], plo[7]);
 #pragma unroll
-            for (int nb = 0; nb < D / 8; ++nb) {
-                // B[k = key][n = d]: pairs of consecutive keys for one d
-                const __nv_bfloat16* vb = &sV[(kk * 16 + 2 * t4) * LDS + nb * 8 + g];
-                __nv_bfloat162 p0, p1;
-                p0.x = vb[0];           p0.y = vb[LDS];
-                p1.x = vb[8 * LDS];     p1.y = vb[9 * LDS];
-                const uint32_t b0 = *reinterpret_cast<uint32_t*>(&p0), b1 = *reinterpret_cast<uint32_t*>(&p1);
-                mma_bf16_16816(o[nb], ah0, ah1, ah2, ah3, b0, b1);
-                mma_bf16_16816(o[nb], al0, al1, al2, al3, b0, b1);
+            for (int nb = 0; nb < D / 8; nb += 2) {
+                // B[k = key][n = d] from V stored [key][d]: transposing ldmatrix, two d-blocks per instruction
+                uint32_t b[4];
+                ldmatrix_x4_trans(b, &sV[(kk * 16 + v_row) * LDS + nb * 8 + v_col]);
+                mma_bf16_16816(o[nb], ah0, ah1, ah2, ah3, b[0], b[1]);
+                mma_bf16_16816(o[nb], al0, al1, al2, al3, b[0], b[1]);
+                mma_bf16_16816(o[nb + 1], ah0, ah1, ah2, ah3, b[2], b[3]);
+                mma_bf16_16816(o[nb + 1], al0, al1, al2, al3, b[2], b[3]);
             }
         }
+        __syncthreads();   // this buffer is refilled by the next iteration's prefetch
     }
+    cp_async_wait<0>();
     // ---- normalise and store (bf16) ----
     const float inv0 = l0 > 0.f ? 1.0f / l0 : 0.f, inv1 = l1 > 0.f ? 1.0f / l1 : 0.f;
     const int tq0 = q0 + r0, tq1 = q0 + r1;
@@ -236,17 +275,17 @@ int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __
     ATS_CHECK_ARG(T >= 1 && S >= 1, "attention: T=%d S=%d", T, S);
     dim3 grid((T + ATT_BQ - 1) / ATT_BQ, n_heads);
     const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
-    const size_t smem = static_cast<size_t>(ATT_BQ + 2 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
+    const size_t smem = static_cast<size_t>(ATT_BQ + 4 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
 #define ATS_ATT(DD)                                                                                              \
     do {                                                                                                         \
         static bool attr_set = false;                                                                            \
         if (!attr_set) {                                                                                         \
             ATS_CUDA(cudaFuncSetAttribute(tree_attention_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          64 * 1024));                                                           \
+                                          96 * 1024));                                                           \
             attr_set = true;                                                                                     \
         }                                                                                                        \
-        tree_attention_kernel<DD><<<grid, ATT_THREADS, smem, st>>>(q, kcache, vcache, b.prefix_len, b.vis,       \
-                                                                   b.vis_base, T, S, n_heads, scale, out);      \
+        ATS_CUDA(launch_pdl(tree_attention_kernel<DD>, grid, dim3(ATT_THREADS), smem, st, q, kcache, vcache,      \
+                            b.prefix_len, b.vis, b.vis_base, T, S, n_heads, scale, out));                       \
     } while (0)
     switch (head_dim) {
         case 16: ATS_ATT(16); break;
@@ -258,7 +297,6 @@ int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __
             return ATS_ERR_ARG;
     }
 #undef ATS_ATT
-    ATS_LAUNCH_CHECK();
     return ATS_OK;
 }
 

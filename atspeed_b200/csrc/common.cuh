@@ -63,10 +63,31 @@ constexpr int MAX_NEW = 6;         // max_new_tokens
 constexpr int VIS_WORDS = 16;      // 512 tree/accepted KV slots addressable by a beam's visibility mask
 constexpr int MAX_TREE_SLOTS = VIS_WORDS * 32;
 
+bool pdl_enabled();   // gemm.cu; ATSPEED_PDL=0 turns programmatic dependent launch off
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): every kernel of the forward is launched with the
+// programmatic-stream-serialization attribute, lets its successor start early (launch_dependents) and waits for its
+// predecessor's memory (wait) before touching anything the predecessor wrote or still reads.  Launch latency and
+// prologues overlap the previous kernel's tail; the GEMM additionally prefetches weights before its wait.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -21,6 +21,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 __global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ tok, int hidden,
                                   int vocab, __nv_bfloat16* __restrict__ h) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x;
     int id = tok[t];
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -37,8 +39,7 @@ __global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, const
 
 int embed_rows(const __nv_bfloat16* table, const int* tok, int T, int hidden, int vocab, __nv_bfloat16* h,
                cudaStream_t st) {
-    embed_rows_kernel<<<T, 128, 0, st>>>(table, tok, hidden, vocab, h);
-    ATS_LAUNCH_CHECK();
+    ATS_CUDA(launch_pdl(embed_rows_kernel, dim3(T), dim3(128), 0, st, table, tok, hidden, vocab, h));
     return ATS_OK;
 }
 
@@ -47,6 +48,8 @@ __global__ void rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ h, const _
                                     int hidden, float eps, __nv_bfloat16* __restrict__ x,
                                     const int* __restrict__ row_index) {
     __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x;
     const int row = row_index ? row_index[r] : r;
     const __nv_bfloat16* src = h + static_cast<long long>(row) * hidden;
@@ -66,22 +69,24 @@ __global__ void rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ h, const _
 
 int rmsnorm_rows(const __nv_bfloat16* h, const __nv_bfloat16* g, int T, int hidden, float eps, __nv_bfloat16* x,
                  const int* row_index, cudaStream_t st) {
-    rmsnorm_rows_kernel<<<T, 256, 0, st>>>(h, g, hidden, eps, x, row_index);
-    ATS_LAUNCH_CHECK();
+    ATS_CUDA(launch_pdl(rmsnorm_rows_kernel, dim3(T), dim3(256), 0, st, h, g, hidden, eps, x, row_index));
     return ATS_OK;
 }
 
-__global__ void residual_rmsnorm_kernel(__nv_bfloat16* __restrict__ h, const float* __restrict__ part, int splits,
+__global__ void residual_rmsnorm_kernel(__nv_bfloat16* __restrict__ h, const float* __restrict__ part, SplitMap sm,
                                         long long split_stride, int ldp, const __nv_bfloat16* __restrict__ g,
                                         int hidden, float eps, __nv_bfloat16* __restrict__ x) {
     extern __shared__ float row_buf[];   // hidden floats: the updated residual stream of this row
     __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x;
     __nv_bfloat16* hrow = h + static_cast<long long>(t) * hidden;
     const float* prow = part + static_cast<long long>(t) * ldp;
     float ss = 0.f;
     for (int i = threadIdx.x; i < hidden; i += blockDim.x) {
         float acc = prow[i];
+        const int splits = sm.slices(i);
         for (int s = 1; s < splits; ++s) acc += prow[s * split_stride + i];
         const float o = bf16_round(acc);
         const float hn = bf16_round(__bfloat162float(hrow[i]) + o);
@@ -104,10 +109,12 @@ __global__ void residual_rmsnorm_kernel(__nv_bfloat16* __restrict__ h, const flo
 // loads (memory-level parallelism instead of a dependent scalar loop).
 template <int THREADS, int CH>
 __global__ void __launch_bounds__(THREADS)
-residual_rmsnorm_vec_kernel(__nv_bfloat16* __restrict__ h, const float* __restrict__ part, int splits,
+residual_rmsnorm_vec_kernel(__nv_bfloat16* __restrict__ h, const float* __restrict__ part, SplitMap sm,
                             long long split_stride, int ldp, const __nv_bfloat16* __restrict__ g, int hidden, float eps,
                             __nv_bfloat16* __restrict__ x) {
     __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x;
     __nv_bfloat16* hrow = h + static_cast<long long>(t) * hidden;
     const float* prow = part + static_cast<long long>(t) * ldp;
@@ -119,6 +126,7 @@ residual_rmsnorm_vec_kernel(__nv_bfloat16* __restrict__ h, const float* __restri
         const int i = threadIdx.x + c * THREADS;
         if (i < nchunk) {
             float4 acc = __ldg(reinterpret_cast<const float4*>(prow) + i);
+            const int splits = sm.slices(4 * i);
             for (int s = 1; s < splits; ++s) {
                 const float4 o = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride) + i);
                 acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
@@ -161,17 +169,19 @@ residual_rmsnorm_vec_kernel(__nv_bfloat16* __restrict__ h, const float* __restri
     }
 }
 
-int residual_rmsnorm(__nv_bfloat16* h, const float* part, int splits, long long split_stride, int ldp,
+int residual_rmsnorm(__nv_bfloat16* h, const float* part, const SplitMap& sm, long long split_stride, int ldp,
                      const __nv_bfloat16* g, int T, int hidden, float eps, __nv_bfloat16* x, cudaStream_t st) {
     if ((hidden & 3) == 0 && (ldp & 3) == 0 && (split_stride & 3) == 0 && hidden <= 512 * 4 * 4 &&
         (reinterpret_cast<uintptr_t>(part) & 15) == 0) {
         if (hidden <= 256 * 4)
-            residual_rmsnorm_vec_kernel<256, 1><<<T, 256, 0, st>>>(h, part, splits, split_stride, ldp, g, hidden, eps, x);
+            ATS_CUDA(launch_pdl(residual_rmsnorm_vec_kernel<256, 1>, dim3(T), dim3(256), 0, st, h, part, sm, split_stride, ldp,
+                                g, hidden, eps, x));
         else if (hidden <= 512 * 4 * 2)
-            residual_rmsnorm_vec_kernel<512, 2><<<T, 512, 0, st>>>(h, part, splits, split_stride, ldp, g, hidden, eps, x);
+            ATS_CUDA(launch_pdl(residual_rmsnorm_vec_kernel<512, 2>, dim3(T), dim3(512), 0, st, h, part, sm, split_stride, ldp,
+                                g, hidden, eps, x));
         else
-            residual_rmsnorm_vec_kernel<512, 4><<<T, 512, 0, st>>>(h, part, splits, split_stride, ldp, g, hidden, eps, x);
-        ATS_LAUNCH_CHECK();
+            ATS_CUDA(launch_pdl(residual_rmsnorm_vec_kernel<512, 4>, dim3(T), dim3(512), 0, st, h, part, sm, split_stride, ldp,
+                                g, hidden, eps, x));
         return ATS_OK;
     }
     ATS_CHECK_ARG(hidden * 4 <= 96 * 1024, "residual_rmsnorm: hidden=%d too large", hidden);
@@ -180,18 +190,19 @@ int residual_rmsnorm(__nv_bfloat16* h, const float* part, int splits, long long 
         ATS_CUDA(cudaFuncSetAttribute(residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    residual_rmsnorm_kernel<<<T, 256, hidden * sizeof(float), st>>>(h, part, splits, split_stride, ldp, g, hidden,
-                                                                     eps, x);
-    ATS_LAUNCH_CHECK();
+    ATS_CUDA(launch_pdl(residual_rmsnorm_kernel, dim3(T), dim3(256), hidden * sizeof(float), st, h, part, sm, split_stride,
+                        ldp, g, hidden, eps, x));
     return ATS_OK;
 }
 
-__global__ void qkv_rope_append_kernel(const float* __restrict__ part, int splits, long long split_stride, int ldp,
+__global__ void qkv_rope_append_kernel(const float* __restrict__ part, SplitMap sm, long long split_stride, int ldp,
                                        const int* __restrict__ pos, const int* __restrict__ slot, int n_heads,
                                        int head_dim, const float* __restrict__ rope_cos,
                                        const float* __restrict__ rope_sin, int max_pos,
                                        __nv_bfloat16* __restrict__ qbuf, __nv_bfloat16* __restrict__ kcache,
                                        __nv_bfloat16* __restrict__ vcache) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x;
     const int HD = n_heads * head_dim, half = head_dim >> 1;
     int p = pos[t];
@@ -205,10 +216,11 @@ __global__ void qkv_rope_append_kernel(const float* __restrict__ part, int split
         const int c0 = hd * head_dim + i, c1 = c0 + half;
         float q0 = prow[c0], q1 = prow[c1], k0 = prow[HD + c0], k1 = prow[HD + c1];
         float v0 = prow[2 * HD + c0], v1 = prow[2 * HD + c1];
-        for (int s = 1; s < splits; ++s) {
-            const float* ps = prow + s * split_stride;
-            q0 += ps[c0]; q1 += ps[c1]; k0 += ps[HD + c0]; k1 += ps[HD + c1];
-            v0 += ps[2 * HD + c0]; v1 += ps[2 * HD + c1];
+        const int cols[6] = {c0, c1, HD + c0, HD + c1, 2 * HD + c0, 2 * HD + c1};
+        float* vals[6] = {&q0, &q1, &k0, &k1, &v0, &v1};
+        for (int k = 0; k < 6; ++k) {
+            const int splits = sm.slices(cols[k]);
+            for (int s = 1; s < splits; ++s) *vals[k] += prow[s * split_stride + cols[k]];
         }
         q0 = bf16_round(q0); q1 = bf16_round(q1); k0 = bf16_round(k0); k1 = bf16_round(k1);
         const float c = ct[i], s_ = sn[i];
@@ -228,11 +240,13 @@ __global__ void qkv_rope_append_kernel(const float* __restrict__ part, int split
 
 // Vectorised variant: one thread = 4 consecutive rotary pairs (i..i+3, i+half..i+half+3) of one head.
 __global__ void __launch_bounds__(256)
-qkv_rope_append_vec_kernel(const float* __restrict__ part, int splits, long long split_stride, int ldp,
+qkv_rope_append_vec_kernel(const float* __restrict__ part, SplitMap sm, long long split_stride, int ldp,
                            const int* __restrict__ pos, const int* __restrict__ slot, int n_heads, int head_dim,
                            const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int max_pos,
                            __nv_bfloat16* __restrict__ qbuf, __nv_bfloat16* __restrict__ kcache,
                            __nv_bfloat16* __restrict__ vcache) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x;
     const int HD = n_heads * head_dim, half = head_dim >> 1, q4 = half >> 2;
     const int e = blockIdx.y * blockDim.x + threadIdx.x;
@@ -247,11 +261,11 @@ qkv_rope_append_vec_kernel(const float* __restrict__ part, int splits, long long
     const int cols[6] = {c0, c1, HD + c0, HD + c1, 2 * HD + c0, 2 * HD + c1};
 #pragma unroll
     for (int k = 0; k < 6; ++k) a[k] = __ldg(reinterpret_cast<const float4*>(prow + cols[k]));
-    for (int s = 1; s < splits; ++s) {
-        const float* ps = prow + s * split_stride;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const float4 o = __ldg(reinterpret_cast<const float4*>(ps + cols[k]));
+    for (int k = 0; k < 6; ++k) {
+        const int splits = sm.slices(cols[k]);
+        for (int s = 1; s < splits; ++s) {
+            const float4 o = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + cols[k]));
             a[k].x += o.x; a[k].y += o.y; a[k].z += o.z; a[k].w += o.w;
         }
     }
@@ -281,7 +295,7 @@ qkv_rope_append_vec_kernel(const float* __restrict__ part, int splits, long long
     *reinterpret_cast<uint2*>(vcache + srow + c1) = pack4(a[5].x, a[5].y, a[5].z, a[5].w);
 }
 
-int qkv_rope_append(const float* part, int splits, long long split_stride, int ldp, const BatchDesc& b, int T,
+int qkv_rope_append(const float* part, const SplitMap& sm, long long split_stride, int ldp, const BatchDesc& b, int T,
                     int n_heads, int head_dim, const float* rope_cos, const float* rope_sin, int max_pos,
                     __nv_bfloat16* qbuf, __nv_bfloat16* kcache, __nv_bfloat16* vcache, cudaStream_t st) {
     ATS_CHECK_ARG((head_dim & 1) == 0, "head_dim=%d must be even", head_dim);
@@ -289,25 +303,27 @@ int qkv_rope_append(const float* part, int splits, long long split_stride, int l
         (reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0) {
         const int work = n_heads * (head_dim >> 3);
         dim3 grid(T, (work + 255) / 256);
-        qkv_rope_append_vec_kernel<<<grid, 256, 0, st>>>(part, splits, split_stride, ldp, b.pos, b.slot, n_heads, head_dim,
-                                                         rope_cos, rope_sin, max_pos, qbuf, kcache, vcache);
-        ATS_LAUNCH_CHECK();
+        ATS_CUDA(launch_pdl(qkv_rope_append_vec_kernel, grid, dim3(256), 0, st, part, sm, split_stride, ldp, b.pos, b.slot,
+                            n_heads, head_dim, rope_cos, rope_sin, max_pos, qbuf, kcache, vcache));
         return ATS_OK;
     }
-    qkv_rope_append_kernel<<<T, 256, 0, st>>>(part, splits, split_stride, ldp, b.pos, b.slot, n_heads, head_dim,
-                                              rope_cos, rope_sin, max_pos, qbuf, kcache, vcache);
-    ATS_LAUNCH_CHECK();
+    ATS_CUDA(launch_pdl(qkv_rope_append_kernel, dim3(T), dim3(256), 0, st, part, sm, split_stride, ldp, b.pos, b.slot,
+                        n_heads, head_dim, rope_cos, rope_sin, max_pos, qbuf, kcache, vcache));
     return ATS_OK;
 }
 
-__global__ void silu_mul_kernel(const float* __restrict__ part, int splits, long long split_stride, int ldp, int mlp,
+__global__ void silu_mul_kernel(const float* __restrict__ part, SplitMap sm, long long split_stride, int ldp, int mlp,
                                 __nv_bfloat16* __restrict__ m) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x;
     const float* prow = part + static_cast<long long>(t) * ldp;
     __nv_bfloat16* dst = m + static_cast<long long>(t) * mlp;
     for (int i = threadIdx.x; i < mlp; i += blockDim.x) {
         float g = prow[i], u = prow[mlp + i];
-        for (int s = 1; s < splits; ++s) { g += prow[s * split_stride + i]; u += prow[s * split_stride + mlp + i]; }
+        const int sg = sm.slices(i), su = sm.slices(mlp + i);
+        for (int s = 1; s < sg; ++s) g += prow[s * split_stride + i];
+        for (int s = 1; s < su; ++s) u += prow[s * split_stride + mlp + i];
         g = bf16_round(g); u = bf16_round(u);
         const float a = bf16_round(g / (1.0f + expf(-g)));
         dst[i] = __float2bfloat16_rn(a * u);
@@ -315,18 +331,23 @@ __global__ void silu_mul_kernel(const float* __restrict__ part, int splits, long
 }
 
 __global__ void __launch_bounds__(256)
-silu_mul_vec_kernel(const float* __restrict__ part, int splits, long long split_stride, int ldp, int mlp,
+silu_mul_vec_kernel(const float* __restrict__ part, SplitMap sm, long long split_stride, int ldp, int mlp,
                     __nv_bfloat16* __restrict__ m) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x;
     const int i = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
     if (i >= mlp) return;
     const float* prow = part + static_cast<long long>(t) * ldp;
     float4 g = __ldg(reinterpret_cast<const float4*>(prow + i));
     float4 u = __ldg(reinterpret_cast<const float4*>(prow + mlp + i));
-    for (int s = 1; s < splits; ++s) {
+    const int sg = sm.slices(i), su = sm.slices(mlp + i);
+    for (int s = 1; s < sg; ++s) {
         const float4 g2 = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + i));
-        const float4 u2 = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + mlp + i));
         g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+    }
+    for (int s = 1; s < su; ++s) {
+        const float4 u2 = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + mlp + i));
         u.x += u2.x; u.y += u2.y; u.z += u2.z; u.w += u2.w;
     }
     auto f = [](float gg, float uu) {
@@ -339,15 +360,31 @@ silu_mul_vec_kernel(const float* __restrict__ part, int splits, long long split_
     *reinterpret_cast<uint2*>(m + static_cast<long long>(t) * mlp + i) = r;
 }
 
-int silu_mul(const float* part, int splits, long long split_stride, int ldp, int T, int mlp, __nv_bfloat16* m,
+int silu_mul(const float* part, const SplitMap& sm, long long split_stride, int ldp, int T, int mlp, __nv_bfloat16* m,
              cudaStream_t st) {
     if ((mlp & 3) == 0 && (ldp & 3) == 0 && (split_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0) {
         dim3 grid(T, (mlp / 4 + 255) / 256);
-        silu_mul_vec_kernel<<<grid, 256, 0, st>>>(part, splits, split_stride, ldp, mlp, m);
-        ATS_LAUNCH_CHECK();
+        ATS_CUDA(launch_pdl(silu_mul_vec_kernel, grid, dim3(256), 0, st, part, sm, split_stride, ldp, mlp, m));
         return ATS_OK;
     }
-    silu_mul_kernel<<<T, 256, 0, st>>>(part, splits, split_stride, ldp, mlp, m);
+    ATS_CUDA(launch_pdl(silu_mul_kernel, dim3(T), dim3(256), 0, st, part, sm, split_stride, ldp, mlp, m));
+    return ATS_OK;
+}
+
+__global__ void reduce_slices_kernel(const float* __restrict__ part, SplitMap sm, long long split_stride, int ldp, int cols,
+                                     float* __restrict__ out, int ldo) {
+    const int t = blockIdx.x;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float acc = part[static_cast<long long>(t) * ldp + c];
+        const int n = sm.slices(c);
+        for (int s = 1; s < n; ++s) acc += part[s * split_stride + static_cast<long long>(t) * ldp + c];
+        out[static_cast<long long>(t) * ldo + c] = acc;
+    }
+}
+
+int reduce_slices(const float* part, const SplitMap& sm, long long split_stride, int ldp, int T, int cols, float* out,
+                  int ldo, cudaStream_t st) {
+    reduce_slices_kernel<<<T, 256, 0, st>>>(part, sm, split_stride, ldp, cols, out, ldo);
     ATS_LAUNCH_CHECK();
     return ATS_OK;
 }

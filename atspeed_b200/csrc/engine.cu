@@ -24,7 +24,6 @@ const char* last_error() { return g_err; }
 
 struct LayerRT {
     GemmWeights qkv, o, gu, down;
-    int s_qkv, s_o, s_gu, s_down;   // split-K factors
     const __nv_bfloat16 *ln1, *ln2;
 };
 
@@ -119,19 +118,27 @@ static double gemm_bytes(const GemmWeights& g, int T) {
     return 2.0 * (rows * g.K + static_cast<double>(T) * g.K + static_cast<double>(T) * rows);
 }
 
+static GemmWeights shape_only(int K, std::initializer_list<int> rows) {
+    GemmWeights g;
+    memset(&g, 0, sizeof(g));
+    g.K = K;
+    int col = 0;
+    for (int r : rows) { g.rows[g.n] = r; g.colbase[g.n] = col; col += r; ++g.n; }
+    return g;
+}
+
+// fp32 partial-sum workspace: the widest (slices x T_max x columns) any projection of the model can need
 static size_t part_elems(const atspeed_model_desc& d, int T_max, int num_sms) {
     const int HD = d.n_heads * d.head_dim;
-    const int kb_h = (d.hidden + 63) / 64, kb_hd = (HD + 63) / 64, kb_m = (d.mlp + 63) / 64;
-    auto tiles = [](int rows) { return (rows + 127) / 128; };
     size_t e = 0;
-    auto upd = [&](int total_tiles, int kb, int cols) {
-        const size_t v = static_cast<size_t>(gemm_plan_splits(total_tiles, kb, num_sms)) * T_max * cols;
+    auto upd = [&](const GemmWeights& g, int cols) {
+        const size_t v = static_cast<size_t>(gemm_max_slices(g, T_max, num_sms)) * T_max * cols;
         if (v > e) e = v;
     };
-    upd(3 * tiles(HD), kb_h, 3 * HD);
-    upd(tiles(d.hidden), kb_hd, d.hidden);
-    upd(2 * tiles(d.mlp), kb_h, 2 * d.mlp);
-    upd(tiles(d.hidden), kb_m, d.hidden);
+    upd(shape_only(d.hidden, {HD, HD, HD}), 3 * HD);
+    upd(shape_only(HD, {d.hidden}), d.hidden);
+    upd(shape_only(d.hidden, {d.mlp, d.mlp}), 2 * d.mlp);
+    upd(shape_only(d.mlp, {d.hidden}), d.hidden);
     return e;
 }
 
@@ -252,7 +259,7 @@ static int build_gemm(GemmWeights& g, int K, std::initializer_list<std::pair<con
 
 static int build_model(ModelRT& m, int num_sms) {
     const atspeed_model_desc& d = m.d;
-    auto tiles = [](int rows) { return (rows + 127) / 128; };
+    (void)num_sms;
     m.layers.resize(d.n_layers);
     for (int l = 0; l < d.n_layers; ++l) {
         const void* const* w = d.layer_weights + static_cast<size_t>(l) * 9;
@@ -261,10 +268,6 @@ static int build_model(ModelRT& m, int num_sms) {
         ATS_TRY(build_gemm(L.o, m.HD, {{w[3], d.hidden}}));
         ATS_TRY(build_gemm(L.gu, d.hidden, {{w[4], d.mlp}, {w[5], d.mlp}}));
         ATS_TRY(build_gemm(L.down, d.mlp, {{w[6], d.hidden}}));
-        L.s_qkv = gemm_plan_splits(3 * tiles(m.HD), (d.hidden + 63) / 64, num_sms);
-        L.s_o = gemm_plan_splits(tiles(d.hidden), (m.HD + 63) / 64, num_sms);
-        L.s_gu = gemm_plan_splits(2 * tiles(d.mlp), (d.hidden + 63) / 64, num_sms);
-        L.s_down = gemm_plan_splits(tiles(d.hidden), (d.mlp + 63) / 64, num_sms);
         L.ln1 = static_cast<const __nv_bfloat16*>(w[7]);
         L.ln2 = static_cast<const __nv_bfloat16*>(w[8]);
     }
@@ -280,6 +283,21 @@ static int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, in
     ATS_CHECK_ARG(R >= 1 && R <= s->R_max, "forward: R=%d exceeds R_max=%d", R, s->R_max);
     ATS_CHECK_ARG(S <= s->S_max, "forward: S=%d exceeds S_max=%d", S, s->S_max);
     const auto* embed = static_cast<const __nv_bfloat16*>(d.embed);
+    // work decomposition of the four projection shapes at this T (identical for every layer) + activation operand maps
+    const LayerRT& L0 = m.layers[0];
+    GemmPlan p_qkv, p_o, p_gu, p_down, p_lm;
+    ATS_TRY(gemm_make_plan(L0.qkv, T, s->num_sms, true, &p_qkv));
+    ATS_TRY(gemm_make_plan(L0.o, T, s->num_sms, true, &p_o));
+    ATS_TRY(gemm_make_plan(L0.gu, T, s->num_sms, true, &p_gu));
+    ATS_TRY(gemm_make_plan(L0.down, T, s->num_sms, true, &p_down));
+    ATS_TRY(gemm_make_plan(m.lm, R, s->num_sms, false, &p_lm));
+    const SplitMap sm_qkv = gemm_split_map(L0.qkv, p_qkv), sm_o = gemm_split_map(L0.o, p_o),
+                   sm_gu = gemm_split_map(L0.gu, p_gu), sm_down = gemm_split_map(L0.down, p_down);
+    XMap xm_x, xm_a, xm_m, xm_sel;
+    ATS_TRY(gemm_make_xmap(&xm_x, m.x, T, d.hidden));
+    ATS_TRY(gemm_make_xmap(&xm_a, m.a, T, m.HD));
+    ATS_TRY(gemm_make_xmap(&xm_m, m.m, T, d.mlp));
+    ATS_TRY(gemm_make_xmap(&xm_sel, m.xsel, R, d.hidden));
     PROF(s, CAT_ELEM, 0, embed_rows(embed, b.tok, T, d.hidden, d.vocab, m.h, st));
     PROF(s, CAT_ELEM, 0, rmsnorm_rows(m.h, m.layers[0].ln1, T, d.hidden, d.rms_eps, m.x, nullptr, st));
     s->launches += 2;
@@ -289,30 +307,30 @@ static int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, in
         __nv_bfloat16* vc = kc + m.kv_plane;
         const int c_qkv = 3 * m.HD, c_gu = 2 * d.mlp;
         PROF(s, CAT_GEMM, gemm_bytes(L.qkv, T),
-             gemm_wx(L.qkv, m.x, T, m.part, c_qkv, static_cast<long long>(T) * c_qkv, L.s_qkv, st));
+             gemm_wx(L.qkv, xm_x, p_qkv, m.part, c_qkv, static_cast<long long>(T) * c_qkv, st));
         PROF(s, CAT_ELEM, 0,
-             qkv_rope_append(m.part, L.s_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
+             qkv_rope_append(m.part, sm_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
                              d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
         PROF(s, CAT_ATTN, 0, tree_attention(m.q, kc, vc, b, T, S, d.n_heads, d.head_dim, m.a, st));
         PROF(s, CAT_GEMM, gemm_bytes(L.o, T),
-             gemm_wx(L.o, m.a, T, m.part, d.hidden, static_cast<long long>(T) * d.hidden, L.s_o, st));
+             gemm_wx(L.o, xm_a, p_o, m.part, d.hidden, static_cast<long long>(T) * d.hidden, st));
         PROF(s, CAT_ELEM, 0,
-             residual_rmsnorm(m.h, m.part, L.s_o, static_cast<long long>(T) * d.hidden, d.hidden, L.ln2, T, d.hidden,
+             residual_rmsnorm(m.h, m.part, sm_o, static_cast<long long>(T) * d.hidden, d.hidden, L.ln2, T, d.hidden,
                               d.rms_eps, m.x, st));
         PROF(s, CAT_GEMM, gemm_bytes(L.gu, T),
-             gemm_wx(L.gu, m.x, T, m.part, c_gu, static_cast<long long>(T) * c_gu, L.s_gu, st));
-        PROF(s, CAT_ELEM, 0, silu_mul(m.part, L.s_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
+             gemm_wx(L.gu, xm_x, p_gu, m.part, c_gu, static_cast<long long>(T) * c_gu, st));
+        PROF(s, CAT_ELEM, 0, silu_mul(m.part, sm_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
         PROF(s, CAT_GEMM, gemm_bytes(L.down, T),
-             gemm_wx(L.down, m.m, T, m.part, d.hidden, static_cast<long long>(T) * d.hidden, L.s_down, st));
+             gemm_wx(L.down, xm_m, p_down, m.part, d.hidden, static_cast<long long>(T) * d.hidden, st));
         const __nv_bfloat16* next_ln = l + 1 < d.n_layers ? m.layers[l + 1].ln1 : nullptr;
         PROF(s, CAT_ELEM, 0,
-             residual_rmsnorm(m.h, m.part, L.s_down, static_cast<long long>(T) * d.hidden, d.hidden, next_ln, T,
+             residual_rmsnorm(m.h, m.part, sm_down, static_cast<long long>(T) * d.hidden, d.hidden, next_ln, T,
                               d.hidden, d.rms_eps, m.x, st));
         s->launches += 9;
     }
     PROF(s, CAT_ELEM, 0,
          rmsnorm_rows(m.h, static_cast<const __nv_bfloat16*>(d.final_norm), R, d.hidden, d.rms_eps, m.xsel, rows_idx, st));
-    PROF(s, CAT_GEMM, gemm_bytes(m.lm, R), gemm_wx(m.lm, m.xsel, R, m.logits, m.ldl, 0, 1, st));
+    PROF(s, CAT_GEMM, gemm_bytes(m.lm, R), gemm_wx(m.lm, xm_sel, p_lm, m.logits, m.ldl, 0, st));
     s->launches += 2;
     m.last_rows = R;
     m.forwards++;
@@ -821,22 +839,53 @@ int atspeed_kv_gather(const void* src_base, void* dst_base, int64_t src_plane_st
                               dst_rows, n_rows_dev, rows, static_cast<cudaStream_t>(stream));
 }
 
-int atspeed_gemm_bf16(const void* x, int32_t T, int32_t K, const void* w0, int32_t rows0, const void* w1, int32_t rows1,
-                      const void* w2, int32_t rows2, float* out, int32_t ldo, int32_t splits, void* stream) {
-    ATS_CHECK_ARG(x && w0 && out, "null argument");
-    GemmWeights g;
-    g.n = 0; g.K = K;
+static int standalone_gemm(const void* x, int32_t T, int32_t K, const void* const* ws, const int* rs, GemmWeights* g,
+                           GemmPlan* pl, XMap* xm) {
+    memset(g, 0, sizeof(*g));
+    g->K = K;
     int col = 0;
+    for (int i = 0; i < 3 && ws[i]; ++i) {
+        g->rows[i] = rs[i]; g->colbase[i] = col;
+        ATS_TRY(make_tmap_bf16_kmajor(&g->tmap[i], ws[i], rs[i], K, 128));
+        col += rs[i];
+        g->n = i + 1;
+    }
+    int dev = 0, sms = 148;
+    ATS_CUDA(cudaGetDevice(&dev));
+    ATS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ATS_TRY(gemm_make_plan(*g, T, sms, true, pl));
+    return x ? gemm_make_xmap(xm, x, T, K) : ATS_OK;
+}
+
+int atspeed_gemm_scratch_bytes(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_t rows2, size_t* bytes) {
+    ATS_CHECK_ARG(bytes, "null bytes");
+    GemmWeights g = shape_only(K, {rows0});
+    if (rows1 > 0) { g.rows[1] = rows1; g.colbase[1] = rows0; g.n = 2; }
+    if (rows2 > 0) { g.rows[2] = rows2; g.colbase[2] = rows0 + rows1; g.n = 3; }
+    int dev = 0, sms = 148;
+    ATS_CUDA(cudaGetDevice(&dev));
+    ATS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GemmPlan pl;
+    ATS_TRY(gemm_make_plan(g, T, sms, true, &pl));
+    *bytes = static_cast<size_t>(pl.max_slices) * T * (rows0 + rows1 + rows2) * sizeof(float);
+    return ATS_OK;
+}
+
+int atspeed_gemm_bf16(const void* x, int32_t T, int32_t K, const void* w0, int32_t rows0, const void* w1, int32_t rows1,
+                      const void* w2, int32_t rows2, float* scratch, float* out, int32_t ldo, void* stream) {
+    ATS_CHECK_ARG(x && w0 && scratch, "null argument");
     const void* ws[3] = {w0, w1, w2};
     const int rs[3] = {rows0, rows1, rows2};
-    for (int i = 0; i < 3 && ws[i]; ++i) {
-        g.rows[i] = rs[i]; g.colbase[i] = col;
-        ATS_TRY(make_tmap_bf16_kmajor(&g.tmap[i], ws[i], rs[i], K, 128));
-        col += rs[i];
-        g.n = i + 1;
-    }
-    ATS_CHECK_ARG(ldo >= col, "ldo=%d < total columns %d", ldo, col);
-    return gemm_wx(g, x, T, out, ldo, static_cast<long long>(T) * ldo, splits, static_cast<cudaStream_t>(stream));
+    GemmWeights g;
+    GemmPlan pl;
+    XMap xm;
+    ATS_TRY(standalone_gemm(x, T, K, ws, rs, &g, &pl, &xm));
+    const int cols = g.colbase[g.n - 1] + g.rows[g.n - 1];
+    ATS_CHECK_ARG(!out || ldo >= cols, "ldo=%d < total columns %d", ldo, cols);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ATS_TRY(gemm_wx(g, xm, pl, scratch, cols, static_cast<long long>(T) * cols, st));
+    if (out) ATS_TRY(reduce_slices(scratch, gemm_split_map(g, pl), static_cast<long long>(T) * cols, cols, T, cols, out, ldo, st));
+    return ATS_OK;
 }
 
 int atspeed_tree_attention(const void* q, const void* kcache, const void* vcache, const int32_t* prefix_len,

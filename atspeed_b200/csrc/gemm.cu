@@ -17,6 +17,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (tcgen05.ld 32 lanes each -> coalesced fp32 stores along the feature axis).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -103,18 +105,26 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
 
 struct GemmParams {
     float* out;
-    long long split_stride;   // elements between split slices
+    long long slice_stride;   // elements between partial-sum slices
     int ldo;                  // row stride (elements) of out
     int T, T_pad;             // tokens, padded to 16
-    int K;
     int n_kblocks;            // ceil(K / 64)
     int n_rows[3];            // rows (features) of each weight
-    int tiles[3];             // 128-row tiles of each weight
+    int tiles[3];             // BM-row tiles of each weight
     int colbase[3];           // output column of each weight's row 0
+    int BM;                   // 128, or 256 = two stacked 128-row MMAs sharing one activation tile
+    int U;                    // work units (tile, k-block) per CTA; CTA c owns units [c*U, (c+1)*U)
+    int total_units;
     int stages;
-    int tmem_cols;
+    int tmem_cols, acc_stride;
 };
 
+// Work decomposition ("stream-K with consumer-side fix-up").  The (tile, k-block) units of the whole GEMM are
+// numbered tile-major and cut into gridDim.x equal contiguous ranges, one per persistent CTA, so every SM streams the
+// same number of weight bytes whatever the tile count (no partial last wave).  A tile whose k-range is cut across CTAs
+// gets one fp32 partial-sum slice per CTA: slice index = cta - first_cta_of_tile.  The consumer kernels
+// (elementwise.cu) know the same arithmetic (SplitMap) and add a tile's slices in index order, so the result is
+// deterministic.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
@@ -123,29 +133,38 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ __align__(8) uint64_t accum_full, accum_empty;
     __shared__ uint32_t tmem_base_smem;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b_tile_bytes = p.T_pad * BLOCK_K * 2;
-    const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
+    // let the next kernel of the stream start its own prologue / weight prefetch as early as resources allow (PDL)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    // which weight / tile
-    int tile = blockIdx.x, wid = 0;
-    if (tile >= p.tiles[0]) { tile -= p.tiles[0]; wid = 1; }
-    if (wid == 1 && tile >= p.tiles[1]) { tile -= p.tiles[1]; wid = 2; }
-    const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
-    const int m0 = tile * BLOCK_M;
-    // balanced split-K partition: every split gets >= 1 k-block (host guarantees splits <= n_kblocks)
-    const int kb_begin = static_cast<int>((static_cast<long long>(p.n_kblocks) * blockIdx.y) / gridDim.y);
-    const int kb_end = static_cast<int>((static_cast<long long>(p.n_kblocks) * (blockIdx.y + 1)) / gridDim.y);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_bytes = p.BM * BLOCK_K * 2;
+    const int b_tile_bytes = p.T_pad * BLOCK_K * 2;
+    const int stage_bytes = a_bytes + b_tile_bytes;
+    const int KB = p.n_kblocks;
+    const int u_begin = blockIdx.x * p.U;
+    const int u_end = min(u_begin + p.U, p.total_units);
+    const int n_units = u_end - u_begin;          // host guarantees >= 1
+
+    auto tile_of = [&](int tile, int& wid, int& m0) {
+        wid = 0;
+        if (tile >= p.tiles[0]) { tile -= p.tiles[0]; wid = 1; }
+        if (wid == 1 && tile >= p.tiles[1]) { tile -= p.tiles[1]; wid = 2; }
+        m0 = tile * p.BM;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&accum_bar, 1);
+        mbar_init(&accum_full, 1);
+        mbar_init(&accum_empty, 4);               // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(tmW); tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmX1); }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmW0); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmX1);
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(static_cast<uint32_t>(p.tmem_cols)));
@@ -159,15 +178,34 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
+            auto load_a = [&](int u, int s) {
+                int wid, m0;
+                tile_of(u / KB, wid, m0);
+                const int kb = u - (u / KB) * KB;
+                const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
                 uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
-                uint8_t* b_dst = a_dst + A_TILE_BYTES;
                 mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
                 tma_load_2d(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);
+                if (p.BM == 256) tma_load_2d(tmW, &full_bar[s], a_dst + A_TILE_BYTES, kb * BLOCK_K, m0 + BLOCK_M);
+            };
+            auto load_b = [&](int u, int s) {
+                const int kb = u - (u / KB) * KB;
+                uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
                 tma_load_2d(&tmX, &full_bar[s], b_dst, kb * BLOCK_K, 0);
                 if (p.T_pad > 256) tma_load_2d(&tmX1, &full_bar[s], b_dst + 256 * BLOCK_K * 2, kb * BLOCK_K, 256);
+            };
+            // The weights do not depend on the previous kernel: fill the ring with weight tiles first, then wait for
+            // the producer of the activations (griddepcontrol.wait), then add the activation tiles.
+            const int npre = n_units < p.stages ? n_units : p.stages;
+            for (int i = 0; i < npre; ++i) load_a(u_begin + i, i);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            for (int i = 0; i < npre; ++i) load_b(u_begin + i, i);
+            int s = npre == p.stages ? 0 : npre;
+            uint32_t ph = npre == p.stages ? 1 : 0;
+            for (int u = u_begin + npre; u < u_end; ++u) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                load_a(u, s);
+                load_b(u, s);
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
@@ -178,41 +216,70 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             const uint32_t n1 = p.T_pad > 256 ? p.T_pad - 256 : 0;
             const uint32_t idesc0 = make_idesc(n0), idesc1 = make_idesc(n1 ? n1 : 16);
             int s = 0; uint32_t ph = 0;
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
+            int seg = 0;
+            for (int u = u_begin; u < u_end; ++u) {
+                const int kb = u % KB;
+                const bool seg_start = (u == u_begin) || kb == 0;
+                if (seg_start && seg > 0) {
+                    // the epilogue must have drained the previous segment's accumulator before it is overwritten
+                    mbar_wait(&accum_empty, (seg - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 mbar_wait(&full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-                const uint32_t b_addr = a_addr + A_TILE_BYTES;
+                const uint32_t b_addr = a_addr + a_bytes;
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
+                    const uint32_t acc = (!seg_start || k > 0) ? 1u : 0u;
                     const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
-                    umma_bf16(tmem_base, da, make_smem_desc(b_addr + k * UMMA_K * 2), idesc0, acc);
+                    const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
+                    umma_bf16(tmem_base, da, db, idesc0, acc);
+                    if (p.BM == 256)
+                        umma_bf16(tmem_base + p.acc_stride, make_smem_desc(a_addr + A_TILE_BYTES + k * UMMA_K * 2), db, idesc0, acc);
                     if (n1) umma_bf16(tmem_base + 256, da, make_smem_desc(b_addr + 256 * BLOCK_K * 2 + k * UMMA_K * 2),
                                       idesc1, acc);
                 }
                 umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
                 if (++s == p.stages) { s = 0; ph ^= 1; }
+                if (u + 1 == u_end || (u + 1) % KB == 0) {   // segment complete
+                    umma_commit(&accum_full);
+                    ++seg;
+                }
             }
-            umma_commit(&accum_bar);          // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global fp32 =====
-        mbar_wait(&accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ===== epilogue: TMEM -> registers -> global fp32 partial-sum slice =====
+        asm volatile("griddepcontrol.wait;" ::: "memory");    // `out` may still be read by the previous consumer
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;           // output feature
-        const bool row_ok = row < p.n_rows[wid];
-        float* out = p.out + static_cast<long long>(blockIdx.y) * p.split_stride + p.colbase[wid] + row;
-        for (int c = 0; c < p.T_pad; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row_ok) {
+        int seg = 0;
+        for (int u = u_begin; u < u_end; ++seg) {
+            const int tile = u / KB;
+            const int seg_end = min((tile + 1) * KB, u_end);
+            int wid, m0;
+            tile_of(tile, wid, m0);
+            const int slice = blockIdx.x - (tile * KB) / p.U;
+            mbar_wait(&accum_full, seg & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int half = 0; half < (p.BM >> 7); ++half) {
+                const int row = m0 + half * BLOCK_M + q * 32 + lane;           // output feature
+                const bool row_ok = row < p.n_rows[wid];
+                float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
+                const uint32_t tbase = tmem_base + half * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+                for (int c = 0; c < p.T_pad; c += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tbase + static_cast<uint32_t>(c), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
+                        for (int j = 0; j < 16; ++j)
+                            if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
+                    }
+                }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
+            u = seg_end;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -260,52 +327,108 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, lon
     return ATS_OK;
 }
 
-int gemm_plan_splits(int total_tiles, int n_kblocks, int num_sms) {
-    // Pick the split-K factor with the cheapest estimated schedule: waves x (k-blocks per CTA + a fixed per-CTA cost of
-    // ~6 k-block times for prologue/epilogue), measured on B200 with tools/gemm_bench.py.  Splitting multiplies the fp32
-    // partial-sum traffic, so wide outputs (many tiles) are only split when a wave would otherwise be mostly empty.
-    const int max_s = total_tiles >= num_sms ? 1 : 8;
-    int best = 1;
-    double best_cost = 1e30;
-    for (int s = 1; s <= max_s && s <= n_kblocks; ++s) {
-        const int ctas = total_tiles * s;
-        const int waves = (ctas + num_sms - 1) / num_sms;
-        const double cost = waves * ((n_kblocks + s - 1) / s + 6.0) + 0.5 * (s - 1);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
-    }
-    return best;
-}
-
-// out[s][t][...] for s < splits. X: [T, K] bf16 row-major. W_i: [n_rows_i, K] bf16 row-major.
-int gemm_wx(const GemmWeights& w, const void* x, int T, float* out, int ldo, long long split_stride, int splits,
-            cudaStream_t stream) {
+// Choose the tile height, the persistent grid and the unit range of every CTA for one GEMM shape.
+//   allow_cut : tiles may be cut along K across CTAs (partial-sum slices; consumers reduce via SplitMap).  When false
+//               (lm_head: its consumer, kernel (a), reads plain fp32 logits) whole tiles are dealt out instead.
+int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, GemmPlan* pl) {
     ATS_CHECK_ARG(T >= 1 && T <= 512, "gemm: T=%d out of range [1,512]", T);
     ATS_CHECK_ARG(w.n >= 1 && w.n <= 3, "gemm: %d weight matrices", w.n);
-    GemmParams p;
-    memset(&p, 0, sizeof(p));
-    p.out = out; p.ldo = ldo; p.split_stride = split_stride;
-    p.T = T; p.T_pad = (T + 15) & ~15; p.K = w.K;
-    p.n_kblocks = (w.K + BLOCK_K - 1) / BLOCK_K;
-    ATS_CHECK_ARG(splits >= 1 && splits <= p.n_kblocks, "gemm: splits=%d vs %d k-blocks", splits, p.n_kblocks);
-    int total_tiles = 0;
+    ATS_CHECK_ARG(num_sms >= 1, "gemm: num_sms=%d", num_sms);
+    memset(pl, 0, sizeof(*pl));
+    pl->T = T;
+    pl->T_pad = (T + 15) & ~15;
+    pl->KB = (w.K + BLOCK_K - 1) / BLOCK_K;
+    int tiles128 = 0;
+    for (int i = 0; i < w.n; ++i) tiles128 += (w.rows[i] + 127) / 128;
+    // Two stacked 128-row MMAs per activation tile halve the L2->SM re-reads of the activations (the limiter at
+    // T >~ 100, profiles/r01_ncu_full_v2.txt); they need 2 x T_pad TMEM columns and only pay off on wide outputs.
+    const char* force = getenv("ATSPEED_GEMM_BM");
+    pl->BM = (pl->T_pad <= 256 && tiles128 >= 48 && pl->T_pad >= 32) ? 256 : 128;
+    if (force && atoi(force) == 128) pl->BM = 128;
+    if (force && atoi(force) == 256 && pl->T_pad <= 256) pl->BM = 256;
+    pl->total_tiles = 0;
     for (int i = 0; i < 3; ++i) {
-        p.n_rows[i] = i < w.n ? w.rows[i] : 0;
-        p.tiles[i] = i < w.n ? (w.rows[i] + BLOCK_M - 1) / BLOCK_M : 0;
-        p.colbase[i] = i < w.n ? w.colbase[i] : 0;
-        total_tiles += p.tiles[i];
+        pl->tiles[i] = i < w.n ? (w.rows[i] + pl->BM - 1) / pl->BM : 0;
+        pl->tilebase[i] = pl->total_tiles;
+        pl->total_tiles += pl->tiles[i];
     }
-    const int stage_bytes = A_TILE_BYTES + p.T_pad * BLOCK_K * 2;
+    const int units = pl->total_tiles * pl->KB;
+    if (const char* e = getenv("ATSPEED_GEMM_CTAS")) { if (atoi(e) > 0) num_sms = atoi(e); }   // experiments only
+    if (allow_cut) {
+        int grid = units < num_sms ? units : num_sms;
+        pl->U = (units + grid - 1) / grid;
+    } else {
+        const int per = (pl->total_tiles + num_sms - 1) / num_sms;
+        pl->U = per * pl->KB;
+    }
+    pl->grid = (units + pl->U - 1) / pl->U;
+    pl->max_slices = 1;
+    for (int t = 0; t < pl->total_tiles; ++t) {
+        const int n = (t * pl->KB + pl->KB - 1) / pl->U - (t * pl->KB) / pl->U + 1;
+        if (n > pl->max_slices) pl->max_slices = n;
+    }
+    const int stage_bytes = pl->BM * BLOCK_K * 2 + pl->T_pad * BLOCK_K * 2;
     int stages = (220 * 1024) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages > p.n_kblocks) stages = p.n_kblocks < 2 ? 2 : p.n_kblocks;
+    if (const char* e = getenv("ATSPEED_GEMM_STAGES")) { if (atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
+    if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
     ATS_CHECK_ARG(stages >= 2, "gemm: T=%d leaves room for %d pipeline stages", T, stages);
-    p.stages = stages;
-    p.tmem_cols = p.T_pad <= 32 ? 32 : p.T_pad <= 64 ? 64 : p.T_pad <= 128 ? 128 : p.T_pad <= 256 ? 256 : 512;
-    // activations: tokens 0..255 through tmX (box = min(T_pad,256) rows), tokens 256..T_pad-1 through tmX1
+    pl->stages = stages;
+    const int need = pl->BM == 256 ? 2 * pl->T_pad : pl->T_pad;
+    int acc = 32;
+    while (acc < (pl->BM == 256 ? pl->T_pad : need)) acc <<= 1;
+    pl->acc_stride = acc;
+    pl->tmem_cols = pl->BM == 256 ? 2 * acc : acc;
+    ATS_CHECK_ARG(pl->tmem_cols <= 512, "gemm: %d TMEM columns", pl->tmem_cols);
+    return ATS_OK;
+}
+
+// upper bound of partial-sum slices over every T the plan function can be asked for (workspace sizing)
+int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms) {
+    int best = 1;
+    for (int T : {1, 32, 64, 128, 256, T_max}) {
+        if (T > T_max) continue;
+        GemmPlan pl;
+        if (gemm_make_plan(w, T, num_sms, true, &pl) == ATS_OK && pl.max_slices > best) best = pl.max_slices;
+    }
+    return best + 1;
+}
+
+SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& pl) {
+    SplitMap m;
+    m.n = w.n;
+    for (int i = 0; i < 3; ++i) { m.colbase[i] = i < w.n ? w.colbase[i] : 0x7fffffff; m.tilebase[i] = pl.tilebase[i]; }
+    m.BM = pl.BM; m.KB = pl.KB; m.U = pl.U;
+    return m;
+}
+
+int gemm_make_xmap(XMap* xm, const void* x, int T, int K) {
+    const int T_pad = (T + 15) & ~15;
+    // activations: tokens 0..255 through tm0 (box = min(T_pad,256) rows), tokens 256..T_pad-1 through tm1
     // (box = T_pad-256 rows); rows past T are zero-filled by TMA, and each box always delivers its full byte count.
-    CUtensorMap tmX, tmX1;
-    ATS_TRY(make_tmap_bf16_kmajor(&tmX, x, T, w.K, p.T_pad > 256 ? 256 : p.T_pad));
-    ATS_TRY(make_tmap_bf16_kmajor(&tmX1, x, T, w.K, p.T_pad > 256 ? p.T_pad - 256 : 16));
+    ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, T_pad > 256 ? 256 : T_pad));
+    ATS_TRY(make_tmap_bf16_kmajor(&xm->tm1, x, T, K, T_pad > 256 ? T_pad - 256 : 16));
+    xm->T = T; xm->K = K;
+    return ATS_OK;
+}
+
+// out[slice][t][...]. X: [T, K] bf16 row-major (through xm). W_i: [n_rows_i, K] bf16 row-major.
+int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, float* out, int ldo, long long slice_stride,
+            cudaStream_t stream) {
+    ATS_CHECK_ARG(xm.T == pl.T && xm.K == w.K, "gemm: activation map (%d x %d) does not match the plan (%d x %d)", xm.T,
+                  xm.K, pl.T, w.K);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.ldo = ldo; p.slice_stride = slice_stride;
+    p.T = pl.T; p.T_pad = pl.T_pad; p.n_kblocks = pl.KB;
+    for (int i = 0; i < 3; ++i) {
+        p.n_rows[i] = i < w.n ? w.rows[i] : 0;
+        p.tiles[i] = pl.tiles[i];
+        p.colbase[i] = i < w.n ? w.colbase[i] : 0;
+    }
+    p.BM = pl.BM; p.U = pl.U; p.total_units = pl.total_tiles * pl.KB;
+    p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.acc_stride = pl.acc_stride;
+    const int stage_bytes = pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
     const size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + 1024;
     static int max_dyn = 0;
     if (!max_dyn) {
@@ -316,11 +439,26 @@ int gemm_wx(const GemmWeights& w, const void* x, int T, float* out, int ldo, lon
         max_dyn = want;
     }
     ATS_CHECK_ARG(static_cast<int>(smem_bytes) <= max_dyn, "gemm: %zu bytes of shared memory > %d", smem_bytes, max_dyn);
-    dim3 grid(total_tiles, splits);
-    gemm_wx_tcgen05<<<grid, GEMM_THREADS, smem_bytes, stream>>>(w.tmap[0], w.tmap[w.n > 1 ? 1 : 0],
-                                                                  w.tmap[w.n > 2 ? 2 : 0], tmX, tmX1, p);
-    ATS_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue + weight prefetch overlap the
+    attr[0].val.programmaticStreamSerializationAllowed = 1;            // previous kernel; see griddepcontrol.wait
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, w.tmap[0], w.tmap[w.n > 1 ? 1 : 0], w.tmap[w.n > 2 ? 2 : 0],
+                                xm.tm0, xm.tm1, p));
     return ATS_OK;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ATSPEED_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
 }
 
 }  // namespace atspeed

@@ -13,9 +13,38 @@ struct GemmWeights {
     CUtensorMap tmap[3];   // [rows_i, K] bf16, K-major, box 64 x 128, SWIZZLE_128B
 };
 int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, long long cols, int box_rows);
-int gemm_plan_splits(int total_tiles, int n_kblocks, int num_sms);
-int gemm_wx(const GemmWeights& w, const void* x, int T, float* out, int ldo, long long split_stride, int splits,
+// One launch's work decomposition (host-computed, see gemm.cu): persistent CTAs each own a contiguous range of
+// (tile, k-block) units; tiles cut across CTAs produce one fp32 partial-sum slice per CTA.
+struct GemmPlan {
+    int T, T_pad, KB;
+    int BM;                 // 128 or 256 output features per tile
+    int tiles[3], tilebase[3], total_tiles;
+    int U;                  // units per CTA
+    int grid;
+    int max_slices;         // most slices any tile of this launch has
+    int stages, tmem_cols, acc_stride;
+};
+// What a consumer of the partial sums needs to know: how many slices hold column `col`.
+struct SplitMap {
+    int n;
+    int colbase[3], tilebase[3];
+    int BM, KB, U;
+#ifdef __CUDACC__
+    __device__ __forceinline__ int slices(int col) const {
+        const int i = col >= colbase[2] ? 2 : (col >= colbase[1] ? 1 : 0);
+        const int u0 = (tilebase[i] + (col - colbase[i]) / BM) * KB;
+        return (u0 + KB - 1) / U - u0 / U + 1;
+    }
+#endif
+};
+struct XMap { CUtensorMap tm0, tm1; int T, K; };   // activation operand [T, K] bf16 (two boxes: tokens < 256, >= 256)
+int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, GemmPlan* plan);
+int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms);
+SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& plan);
+int gemm_make_xmap(XMap* xm, const void* x, int T, int K);
+int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, float* out, int ldo, long long slice_stride,
             cudaStream_t stream);
+bool pdl_enabled();   // ATSPEED_PDL=0 disables programmatic dependent launch (debugging)
 
 // ---- elementwise.cu -----------------------------------------------------------------------------
 // Forward-batch descriptor, all device arrays of length >= T (built by beam.cu kernels).
@@ -34,17 +63,20 @@ int embed_rows(const __nv_bfloat16* table, const int* tok, int T, int hidden, in
 int rmsnorm_rows(const __nv_bfloat16* h, const __nv_bfloat16* g, int T, int hidden, float eps, __nv_bfloat16* x,
                  const int* row_index, cudaStream_t st);
 // h = bf16(h + bf16(sum_s part[s])) ; x = rmsnorm(h) * g  (g == nullptr: residual only)
-int residual_rmsnorm(__nv_bfloat16* h, const float* part, int splits, long long split_stride, int ldp,
+int residual_rmsnorm(__nv_bfloat16* h, const float* part, const SplitMap& sm, long long split_stride, int ldp,
                      const __nv_bfloat16* g, int T, int hidden, float eps, __nv_bfloat16* x, cudaStream_t st);
 // q,k,v = bf16(sum_s part[s]); RoPE(q,k) at pos; q -> qbuf [T, H*D]; k,v -> cache rows slot[t]
 // rope_cos/rope_sin: [max_pos][head_dim/2] fp32 tables holding bf16-rounded values (computed on the host exactly
 // as HF's LlamaRotaryEmbedding does, so the device never evaluates powf/cosf/sinf).
-int qkv_rope_append(const float* part, int splits, long long split_stride, int ldp, const BatchDesc& b, int T,
+int qkv_rope_append(const float* part, const SplitMap& sm, long long split_stride, int ldp, const BatchDesc& b, int T,
                     int n_heads, int head_dim, const float* rope_cos, const float* rope_sin, int max_pos,
                     __nv_bfloat16* qbuf, __nv_bfloat16* kcache, __nv_bfloat16* vcache, cudaStream_t st);
 // m = bf16(bf16(silu(g)) * u) with g,u = bf16(sum_s part[s]) at columns [0,mlp) and [mlp,2mlp)
-int silu_mul(const float* part, int splits, long long split_stride, int ldp, int T, int mlp, __nv_bfloat16* m,
+int silu_mul(const float* part, const SplitMap& sm, long long split_stride, int ldp, int T, int mlp, __nv_bfloat16* m,
              cudaStream_t st);
+// out[t][c] = sum of the slices of column c (stand-alone GEMM entry point / tests)
+int reduce_slices(const float* part, const SplitMap& sm, long long split_stride, int ldp, int T, int cols, float* out,
+                  int ldo, cudaStream_t st);
 
 // ---- attention.cu -------------------------------------------------------------------------------
 int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,

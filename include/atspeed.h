@@ -233,10 +233,14 @@ int atspeed_kv_gather(const void* src_base, void* dst_base, int64_t src_plane_st
                       int32_t n_planes, int32_t row_bytes, const int32_t* src_rows, const int32_t* dst_rows,
                       const int32_t* n_rows_dev, int32_t rows, void* stream);
 
-/* The tcgen05 GEMM of the forward: out[s][t][colbase_i + n] = sum_k x[t][k] * w_i[n][k] (fp32 split-K slices).
- * x bf16 [T, K]; up to three weights w_i bf16 [rows_i, K]; out fp32 [splits][T][ldo]. */
+/* The tcgen05 GEMM of the forward (csrc/gemm.cu): y[t][colbase_i + n] = sum_k x[t][k] * w_i[n][k].
+ * x bf16 [T, K]; up to three weights w_i bf16 [rows_i, K] sharing x.  The kernel leaves fp32 partial-sum slices in
+ * `scratch` (atspeed_gemm_scratch_bytes; tiles cut along K across its persistent CTAs); when `out` is non-NULL the
+ * slices are then reduced in fixed order into out fp32 [T][ldo] (in the forward that reduction is fused into the
+ * consuming row-wise kernel). */
+int atspeed_gemm_scratch_bytes(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_t rows2, size_t* bytes);
 int atspeed_gemm_bf16(const void* x, int32_t T, int32_t K, const void* w0, int32_t rows0, const void* w1, int32_t rows1,
-                      const void* w2, int32_t rows2, float* out, int32_t ldo, int32_t splits, void* stream);
+                      const void* w2, int32_t rows2, float* scratch, float* out, int32_t ldo, void* stream);
 
 /* Tree attention of the forward (see csrc/attention.cu). q/out bf16 [T, n_heads*head_dim]; caches bf16
  * [S, n_heads*head_dim]; prefix_len int32[T]; vis uint32[T][16] relative to vis_base. */

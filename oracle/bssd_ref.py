@@ -194,7 +194,7 @@ class SamplingCfg:
         or in noise mode the k accepted picks with the smallest (bits, position) keys."""
         if self.noise_fn is not None:
             bits = self.noise_fn("bits", SITE_PERM, self.round, level, n_picks).view(-1).to(torch.int64)
-            key = bits[accepted_pos] * (1 << 32) + accepted_pos.to(torch.int64)
+            key = bits[accepted_pos] * 1024 + accepted_pos.to(torch.int64)     # (bits, position) order; bits < 2**32
             return torch.argsort(key)[:k]
         return torch.randperm(len(accepted_pos), generator=self.cpu_generator)[:k]
 

@@ -140,27 +140,34 @@ def test_relaxed_decisions_match_oracle(ds_name, kind, draft, K, N, gamma, temp,
         cfg = bssd_ref.SamplingCfg(temperature=temp, top_k=50, noise_fn=noise_fn, defined_fallback=True)
         ref = bssd_ref.bssd(TapeModel(V, t_tape), TapeModel(V, d_tape), prompt, K, N, gamma, 4, fn, sampling=cfg)
         P = len(prompt)
-        assert res["tokens"].tolist() == ref.sequences[:, P:].tolist(), (u, seed)
-        np.testing.assert_allclose(res["scores"], ref.scores, atol=2e-4)
-        assert [r["n_matches"] for r in rounds] == ref.accept_steps
-        assert all(res["scores"][i] >= res["scores"][i + 1] for i in range(len(res["scores"]) - 1))
-        for r, tr in zip(rounds, ref.rounds):
+        # walk the rounds in order so that a failure names the FIRST decision that differs
+        for ri, (r, tr) in enumerate(zip(rounds, ref.rounds)):
             lv = r["levels"]
             for l in range(1, r["dl"] + 1):     # sampled draft levels: (parent, token) in sample order
                 n = int(lv["cnt"][l])
                 got = [(int(lv["parent"][l][i]), int(lv["tok"][l][i])) for i in range(n)]
-                assert got == [(p, t) for p, t, _ in tr.draft_levels[l - 1]], (u, l)
+                want = [(p, t) for p, t, _ in tr.draft_levels[l - 1]]
+                assert got == want, f"user {u} round {ri} draft level {l}: first diff at " \
+                                    f"{next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), min(len(got), len(want)))}" \
+                                    f" of {len(got)}/{len(want)}: {got[:6]} vs {want[:6]}"
                 np.testing.assert_allclose(lv["score"][l][:n], [s for _, _, s in tr.draft_levels[l - 1]], atol=2e-4)
             for i, hits in enumerate(tr.hits):  # acceptance flags of every draft pick
                 n = int(lv["cnt"][i + 1])
-                assert [j for j in range(n) if r["trace"]["acc"][i][j]] == hits, (u, i)
+                got = [j for j in range(n) if r["trace"]["acc"][i][j]]
+                assert got == hits, f"user {u} round {ri} level {i} accepted picks: {got} vs {hits}"
             for i, picks in enumerate(tr.target_picks):
                 n = int(r["trace"]["npick"][i])
                 got = [(int(r["trace"]["pick_parent"][i][p]), int(r["trace"]["pick_tok"][i][p])) for p in range(n)]
-                assert got == [(pp, t) for pp, t, _ in picks], (u, i)
+                assert got == [(pp, t) for pp, t, _ in picks], f"user {u} round {ri} level {i} carried/final beams"
+                np.testing.assert_allclose(r["trace"]["pick_score"][i][:n], [s for _, _, s in picks], atol=2e-4)
+            assert r["n_matches"] == tr.n_matches, f"user {u} round {ri}"
             stats["accepted_levels"] += r["n_matches"]
             stats["rejected_rounds"] += int(r["n_matches"] < r["dl"])
             stats["bonus"] += int(r["n_matches"] == r["dl"])
+        assert [r["n_matches"] for r in rounds] == ref.accept_steps
+        assert res["tokens"].tolist() == ref.sequences[:, P:].tolist(), (u, seed)
+        np.testing.assert_allclose(res["scores"], ref.scores, atol=2e-4)
+        assert all(res["scores"][i] >= res["scores"][i + 1] for i in range(len(res["scores"]) - 1))
         n_fb = rounds[-1]["trace"]["fallbacks"] if rounds else 0     # cumulative per user on the device
         assert cfg.fallbacks == n_fb
         stats["fallbacks"] += n_fb

@@ -22,18 +22,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "68m":
 NBUF = 6
 
 
-def plan(tiles, kb, sms=148):   # mirrors gemm_plan_splits in csrc/gemm.cu
-    best, bc = 1, 1e30
-    for s_ in range(1, (1 if tiles >= sms else 8) + 1):
-        if s_ > kb:
-            break
-        waves = -(-tiles * s_ // sms)
-        cost = waves * (-(-kb // s_) + 6.0) + 0.5 * (s_ - 1)
-        if cost < bc - 1e-9:
-            best, bc = s_, cost
-    return best
-
-
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 print(f"{'gemm':<8} {'T':>4} {'us':>8} {'GB/s':>8} {'frac':>6}   (algorithmic bytes = W + X + bf16 Y)")
 for name, (K, rows) in SHAPES.items():
@@ -41,15 +29,17 @@ for name, (K, rows) in SHAPES.items():
     for T in (10, 50, 90, 130, 220, 289):
         x = (torch.randn(T, K, device=dev) * 0.5).to(torch.bfloat16)
         ldo = sum(rows)
-        tiles, kb = sum((r + 127) // 128 for r in rows), (K + 63) // 64
-        spl = int(os.environ.get("SPLITS", "0")) or plan(tiles, kb)
-        out = torch.empty(spl, T, ldo, device=dev, dtype=torch.float32)
+        r3 = list(rows) + [0] * (3 - len(rows))
+        nb = C.c_size_t(0)
+        assert lib.atspeed_gemm_scratch_bytes(T, K, r3[0], r3[1], r3[2], C.byref(nb)) == 0
+        out = torch.empty(nb.value // 4, device=dev, dtype=torch.float32)
+        spl = nb.value // 4 // (T * ldo)
 
         def run(i):
             w = ws[i % NBUF]
             p = [t.data_ptr() for t in w] + [None] * (3 - len(w))
             r = list(rows) + [0] * (3 - len(rows))
-            rc = lib.atspeed_gemm_bf16(x.data_ptr(), T, K, p[0], r[0], p[1], r[1], p[2], r[2], out.data_ptr(), ldo, spl, st)
+            rc = lib.atspeed_gemm_bf16(x.data_ptr(), T, K, p[0], r[0], p[1], r[1], p[2], r[2], out.data_ptr(), None, ldo, st)
             assert rc == 0, lib.atspeed_last_error()
 
         for i in range(NBUF):
@@ -66,4 +56,4 @@ for name, (K, rows) in SHAPES.items():
         us = e0.elapsed_time(e1) * 1e3 / n
         byts = 2.0 * (sum(rows) * K + T * K + T * sum(rows))
         gbs = byts / us / 1e3
-        print(f"{name:<8} {T:>4} {us:>8.1f} {gbs:>8.0f} {gbs / peak:>6.2f}  splits={spl}")
+        print(f"{name:<8} {T:>4} {us:>8.1f} {gbs:>8.0f} {gbs / peak:>6.2f}  max_slices={spl}")

@@ -1,0 +1,72 @@
+"""GEMM experiment sweep (GPU box): plan overrides through env vars, a few shapes, one table."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from atspeed_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+dev = torch.device("cuda")
+SHAPES = {"qkv": (4096, (4096, 4096, 4096)), "o": (4096, (4096,)), "gate_up": (4096, (11008, 11008)),
+          "down": (11008, (4096,)), "lm_head": (4096, (32859,))}
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+NBUF = 6
+
+
+def bench(name, T, env):
+    for k in ("ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    K, rows = SHAPES[name]
+    ws = WS[name]
+    x = (torch.randn(T, K, device=dev) * 0.5).to(torch.bfloat16)
+    r3 = list(rows) + [0] * (3 - len(rows))
+    nb = C.c_size_t(0)
+    assert lib.atspeed_gemm_scratch_bytes(T, K, r3[0], r3[1], r3[2], C.byref(nb)) == 0
+    out = torch.empty(nb.value // 4, device=dev, dtype=torch.float32)
+
+    def run(i):
+        w = ws[i % NBUF]
+        p = [t.data_ptr() for t in w] + [None] * (3 - len(w))
+        rc = lib.atspeed_gemm_bf16(x.data_ptr(), T, K, p[0], r3[0], p[1], r3[1], p[2], r3[2], out.data_ptr(), None, sum(rows), st)
+        assert rc == 0, lib.atspeed_last_error()
+
+    for i in range(NBUF):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 30
+    torch.cuda._sleep(int(6e6))
+    e0.record()
+    for i in range(n):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n
+    byts = 2.0 * (sum(rows) * K + T * K + T * sum(rows))
+    return us, byts / us / 1e3
+
+
+WS = {n: [[(torch.randn(r, K, device=dev) * 0.02).to(torch.bfloat16) for r in rows] for _ in range(NBUF)]
+      for n, (K, rows) in SHAPES.items()}
+CONFIGS = [("default", {}), ("bm128", {"ATSPEED_GEMM_BM": "128"}), ("bm256", {"ATSPEED_GEMM_BM": "256"}),
+           ("bm128 st6", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_STAGES": "6"}),
+           ("bm128 st4 x296", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_STAGES": "5", "ATSPEED_GEMM_CTAS": "296"}),
+           ("bm256 st3 x296", {"ATSPEED_GEMM_BM": "256", "ATSPEED_GEMM_STAGES": "3", "ATSPEED_GEMM_CTAS": "296"}),
+           ("bm128 x132", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_CTAS": "132"}),
+           ("bm256 nopdl", {"ATSPEED_GEMM_BM": "256", "ATSPEED_PDL": "0"}),
+           ("bm128 nopdl", {"ATSPEED_GEMM_BM": "128", "ATSPEED_PDL": "0"})]
+print(f"{'config':<18}" + "".join(f"{n + ' T=' + str(T):>16}" for n in SHAPES for T in (10, 220)))
+for cname, env in CONFIGS:
+    row = f"{cname:<18}"
+    for n in SHAPES:
+        for T in (10, 220):
+            try:
+                us, gbs = bench(n, T, env)
+                row += f"{us:>9.1f}/{gbs / 1e3:>4.2f}T "
+            except Exception as e:
+                row += f"{'err':>16}"
+    print(row, flush=True)
