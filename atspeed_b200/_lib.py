@@ -17,7 +17,7 @@ class ModelDesc(C.Structure):
                 ("head_dim", C.c_int32), ("mlp", C.c_int32), ("rms_eps", C.c_float),
                 ("embed", C.c_void_p), ("final_norm", C.c_void_p), ("lm_head", C.c_void_p),
                 ("layer_weights", C.POINTER(C.c_void_p)),
-                ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("max_pos", C.c_int32)]
+                ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("max_pos", C.c_int32), ("weights_f32", C.c_int32)]
 
 
 class TrieDesc(C.Structure):

@@ -35,6 +35,10 @@ struct ModelRT {
     // activations (device, carved from the workspace)
     __nv_bfloat16 *h, *x, *q, *a, *m, *xsel, *kv;
     float *part, *logits;
+    // fp32 exact-parity mode (d.weights_f32): fp32 activations and KV cache instead of the bf16 ones above
+    bool f32;
+    float *fh, *fx, *fq, *fa, *fm, *fxsel, *fqkv, *fgu, *fkv;
+    int elem_bytes;       // bytes per KV / activation element (2 or 4)
     long long kv_plane;   // elements per K (or V) plane of one layer
     int ldl;              // logits row stride
     int last_rows;
@@ -146,6 +150,24 @@ static void carve_model(Carver& c, ModelRT& m, const atspeed_model_desc& d, int 
     m.d = d;
     m.HD = d.n_heads * d.head_dim;
     m.ldl = (d.vocab + 7) & ~7;
+    m.f32 = d.weights_f32 != 0;
+    m.elem_bytes = m.f32 ? 4 : 2;
+    m.last_rows = 0;
+    m.forwards = 0;
+    m.kv_plane = static_cast<long long>(S_max) * m.HD;
+    if (m.f32) {
+        m.fh = c.take<float>(static_cast<size_t>(T_max) * d.hidden);
+        m.fx = c.take<float>(static_cast<size_t>(T_max) * d.hidden);
+        m.fq = c.take<float>(static_cast<size_t>(T_max) * m.HD);
+        m.fa = c.take<float>(static_cast<size_t>(T_max) * m.HD);
+        m.fm = c.take<float>(static_cast<size_t>(T_max) * d.mlp);
+        m.fxsel = c.take<float>(static_cast<size_t>(R_max) * d.hidden);
+        m.fqkv = c.take<float>(static_cast<size_t>(T_max) * 3 * m.HD);
+        m.fgu = c.take<float>(static_cast<size_t>(T_max) * 2 * d.mlp);
+        m.logits = c.take<float>(static_cast<size_t>(R_max) * m.ldl);
+        m.fkv = c.take<float>(static_cast<size_t>(d.n_layers) * 2 * m.kv_plane);
+        return;
+    }
     m.h = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * d.hidden);
     m.x = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * d.hidden);
     m.q = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * m.HD);
@@ -154,10 +176,7 @@ static void carve_model(Carver& c, ModelRT& m, const atspeed_model_desc& d, int 
     m.xsel = c.take<__nv_bfloat16>(static_cast<size_t>(R_max) * d.hidden);
     m.part = c.take<float>(part_elems(d, T_max, num_sms));
     m.logits = c.take<float>(static_cast<size_t>(R_max) * m.ldl);
-    m.kv_plane = static_cast<long long>(S_max) * m.HD;
     m.kv = c.take<__nv_bfloat16>(static_cast<size_t>(d.n_layers) * 2 * m.kv_plane);
-    m.last_rows = 0;
-    m.forwards = 0;
 }
 
 static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_desc* target, const atspeed_model_desc* draft) {
@@ -223,10 +242,14 @@ static int check_cfg(const atspeed_model_desc* target, const atspeed_model_desc*
     ATS_CHECK_ARG(bits <= MAX_TREE_SLOTS, "K=%d N=%d need %d tree slots > %d", cfg->K, cfg->N, bits, MAX_TREE_SLOTS);
     for (const atspeed_model_desc* d : {target, draft}) {
         if (!d) continue;
-        ATS_CHECK_ARG(d->hidden % 8 == 0 && d->mlp % 8 == 0 && (d->n_heads * d->head_dim) % 8 == 0,
-                      "hidden/mlp/heads*head_dim must be multiples of 8");
-        ATS_CHECK_ARG(d->head_dim == 16 || d->head_dim == 32 || d->head_dim == 64 || d->head_dim == 128,
-                      "head_dim=%d unsupported", d->head_dim);
+        if (!d->weights_f32) {
+            ATS_CHECK_ARG(d->hidden % 8 == 0 && d->mlp % 8 == 0 && (d->n_heads * d->head_dim) % 8 == 0,
+                          "hidden/mlp/heads*head_dim must be multiples of 8");
+            ATS_CHECK_ARG(d->head_dim == 16 || d->head_dim == 32 || d->head_dim == 64 || d->head_dim == 128,
+                          "head_dim=%d unsupported", d->head_dim);
+        } else {
+            ATS_CHECK_ARG(d->head_dim % 2 == 0, "head_dim=%d must be even", d->head_dim);
+        }
         ATS_CHECK_ARG(d->vocab == target->vocab, "draft and target vocabularies differ");
     }
     return ATS_OK;
@@ -251,6 +274,7 @@ static int build_gemm(GemmWeights& g, int K, std::initializer_list<std::pair<con
         g.rows[g.n] = w.second;
         g.colbase[g.n] = col;
         ATS_TRY(make_tmap_bf16_kmajor(&g.tmap[g.n], w.first, w.second, K, 128));
+        ATS_TRY(make_tmap_bf16_kmajor(&g.tmap256[g.n], w.first, w.second, K, 256));
         col += w.second;
         ++g.n;
     }
@@ -259,6 +283,7 @@ static int build_gemm(GemmWeights& g, int K, std::initializer_list<std::pair<con
 
 static int build_model(ModelRT& m, int num_sms) {
     const atspeed_model_desc& d = m.d;
+    if (m.f32) return ATS_OK;      // the fp32 parity forward reads d.layer_weights directly (no tensor maps)
     (void)num_sms;
     m.layers.resize(d.n_layers);
     for (int l = 0; l < d.n_layers; ++l) {
@@ -275,6 +300,39 @@ static int build_model(ModelRT& m, int num_sms) {
     return ATS_OK;
 }
 
+// fp32 exact-parity forward (csrc/forward_f32.cu): same batch descriptors and KV-slot layout as the bf16 forward
+static int forward_f32(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, const int* rows_idx, int R,
+                       cudaStream_t st) {
+    const atspeed_model_desc& d = m.d;
+    const int HD = m.HD;
+    auto W = [&](int l, int j) { return static_cast<const float*>(d.layer_weights[static_cast<size_t>(l) * 9 + j]); };
+    PROF(s, CAT_ELEM, 0, f32_embed(static_cast<const float*>(d.embed), b.tok, T, d.hidden, d.vocab, m.fh, st));
+    s->launches += 1;
+    for (int l = 0; l < d.n_layers; ++l) {
+        float* kc = m.fkv + static_cast<long long>(l) * 2 * m.kv_plane;
+        float* vc = kc + m.kv_plane;
+        PROF(s, CAT_ELEM, 0, f32_rmsnorm(m.fh, W(l, 7), T, d.hidden, d.rms_eps, m.fx, nullptr, st));
+        for (int j = 0; j < 3; ++j)
+            PROF(s, CAT_GEMM, 0, f32_gemm(m.fx, W(l, j), T, HD, d.hidden, m.fqkv + j * HD, 3 * HD, false, st));
+        PROF(s, CAT_ELEM, 0,
+             f32_rope_append(m.fqkv, b, T, d.n_heads, d.head_dim, d.rope_cos, d.rope_sin, d.max_pos, m.fq, kc, vc, st));
+        PROF(s, CAT_ATTN, 0, f32_tree_attention(m.fq, kc, vc, b, T, S, d.n_heads, d.head_dim, m.fa, st));
+        PROF(s, CAT_GEMM, 0, f32_gemm(m.fa, W(l, 3), T, d.hidden, HD, m.fh, d.hidden, true, st));        // h += o_proj(a)
+        PROF(s, CAT_ELEM, 0, f32_rmsnorm(m.fh, W(l, 8), T, d.hidden, d.rms_eps, m.fx, nullptr, st));
+        PROF(s, CAT_GEMM, 0, f32_gemm(m.fx, W(l, 4), T, d.mlp, d.hidden, m.fgu, 2 * d.mlp, false, st));
+        PROF(s, CAT_GEMM, 0, f32_gemm(m.fx, W(l, 5), T, d.mlp, d.hidden, m.fgu + d.mlp, 2 * d.mlp, false, st));
+        PROF(s, CAT_ELEM, 0, f32_silu_mul(m.fgu, T, d.mlp, m.fm, st));
+        PROF(s, CAT_GEMM, 0, f32_gemm(m.fm, W(l, 6), T, d.hidden, d.mlp, m.fh, d.hidden, true, st));     // h += down(m)
+        s->launches += 12;
+    }
+    PROF(s, CAT_ELEM, 0, f32_rmsnorm(m.fh, static_cast<const float*>(d.final_norm), R, d.hidden, d.rms_eps, m.fxsel, rows_idx, st));
+    PROF(s, CAT_GEMM, 0, f32_gemm(m.fxsel, static_cast<const float*>(d.lm_head), R, d.vocab, d.hidden, m.logits, m.ldl, false, st));
+    s->launches += 2;
+    m.last_rows = R;
+    m.forwards++;
+    return ATS_OK;
+}
+
 // One forward of `m` over the batch in `b` (T tokens; attention scans KV slots [0, S)), logits for R rows.
 static int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, const int* rows_idx, int R,
                    cudaStream_t st) {
@@ -282,6 +340,7 @@ static int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, in
     ATS_CHECK_ARG(T >= 1 && T <= s->T_max, "forward: T=%d exceeds T_max=%d", T, s->T_max);
     ATS_CHECK_ARG(R >= 1 && R <= s->R_max, "forward: R=%d exceeds R_max=%d", R, s->R_max);
     ATS_CHECK_ARG(S <= s->S_max, "forward: S=%d exceeds S_max=%d", S, s->S_max);
+    if (m.f32) return forward_f32(s, m, b, T, S, rows_idx, R, st);
     const auto* embed = static_cast<const __nv_bfloat16*>(d.embed);
     // work decomposition of the four projection shapes at this T (identical for every layer) + activation operand maps
     const LayerRT& L0 = m.layers[0];
@@ -619,8 +678,9 @@ int atspeed_session_verify(atspeed_session* s, int32_t draft_len, int32_t* n_mat
     for (ModelRT* m : {&s->tgt, s->has_draft ? &s->dft : nullptr}) {
         if (!m) continue;
         PROF(s, CAT_GATHER, 0,
-             kv_gather_rows(m->kv, m->kv_plane * 2 /*bytes per element*/, m->d.n_layers * 2, m->HD * 2, s->tree.gather_src,
-                            s->tree.gather_dst, s->tree.scal + SC_GATHER, max_rows, st));
+             kv_gather_rows(m->f32 ? static_cast<void*>(m->fkv) : static_cast<void*>(m->kv), m->kv_plane * m->elem_bytes,
+                            m->d.n_layers * 2, m->HD * m->elem_bytes, s->tree.gather_src, s->tree.gather_dst,
+                            s->tree.scal + SC_GATHER, max_rows, st));
         s->launches += 1;
     }
     s->launches += 1;
@@ -847,6 +907,7 @@ static int standalone_gemm(const void* x, int32_t T, int32_t K, const void* cons
     for (int i = 0; i < 3 && ws[i]; ++i) {
         g->rows[i] = rs[i]; g->colbase[i] = col;
         ATS_TRY(make_tmap_bf16_kmajor(&g->tmap[i], ws[i], rs[i], K, 128));
+        ATS_TRY(make_tmap_bf16_kmajor(&g->tmap256[i], ws[i], rs[i], K, 256));
         col += rs[i];
         g->n = i + 1;
     }

@@ -117,6 +117,8 @@ struct GemmParams {
     int total_units;
     int stages;
     int tmem_cols, acc_stride;
+    int n_bufs, buf_stride;   // accumulator double buffering in TMEM: segment s uses buffer s % n_bufs
+    int b_box_bytes;          // bytes the activation TMA box(es) deliver per stage (== T_pad * 128 except in timing experiments)
 };
 
 // Work decomposition ("stream-K with consumer-side fix-up").  The (tile, k-block) units of the whole GEMM are
@@ -133,7 +135,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t accum_full, accum_empty;
+    __shared__ __align__(8) uint64_t accum_full[2], accum_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
     // let the next kernel of the stream start its own prologue / weight prefetch as early as resources allow (PDL)
@@ -157,8 +159,10 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&accum_full, 1);
-        mbar_init(&accum_empty, 4);               // one arrival per epilogue warp
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&accum_full[b], 1);
+            mbar_init(&accum_empty[b], 4);        // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -184,9 +188,10 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 const int kb = u - (u / KB) * KB;
                 const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
                 uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
-                mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+                mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(a_bytes + p.b_box_bytes));
+                // BM = 256: tmW has a 256-row box -- ONE operation fills both stacked 128-row tiles (a TMA operation costs
+                // ~0.3 us of a CTA's issue stream whatever its size: fewer, larger boxes stream faster)
                 tma_load_2d(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);
-                if (p.BM == 256) tma_load_2d(tmW, &full_bar[s], a_dst + A_TILE_BYTES, kb * BLOCK_K, m0 + BLOCK_M);
             };
             auto load_b = [&](int u, int s) {
                 const int kb = u - (u / KB) * KB;
@@ -220,11 +225,13 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             for (int u = u_begin; u < u_end; ++u) {
                 const int kb = u % KB;
                 const bool seg_start = (u == u_begin) || kb == 0;
-                if (seg_start && seg > 0) {
-                    // the epilogue must have drained the previous segment's accumulator before it is overwritten
-                    mbar_wait(&accum_empty, (seg - 1) & 1);
+                const int buf = seg % p.n_bufs, use = seg / p.n_bufs;      // `use`-th time this accumulator buffer is filled
+                if (seg_start && use > 0) {
+                    // the epilogue must have drained this buffer's previous segment before it is overwritten
+                    mbar_wait(&accum_empty[buf], (use - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
+                const uint32_t tacc = tmem_base + buf * p.buf_stride;
                 mbar_wait(&full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
@@ -234,16 +241,16 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     const uint32_t acc = (!seg_start || k > 0) ? 1u : 0u;
                     const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
                     const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
-                    umma_bf16(tmem_base, da, db, idesc0, acc);
+                    umma_bf16(tacc, da, db, idesc0, acc);
                     if (p.BM == 256)
-                        umma_bf16(tmem_base + p.acc_stride, make_smem_desc(a_addr + A_TILE_BYTES + k * UMMA_K * 2), db, idesc0, acc);
-                    if (n1) umma_bf16(tmem_base + 256, da, make_smem_desc(b_addr + 256 * BLOCK_K * 2 + k * UMMA_K * 2),
+                        umma_bf16(tacc + p.acc_stride, make_smem_desc(a_addr + A_TILE_BYTES + k * UMMA_K * 2), db, idesc0, acc);
+                    if (n1) umma_bf16(tacc + 256, da, make_smem_desc(b_addr + 256 * BLOCK_K * 2 + k * UMMA_K * 2),
                                       idesc1, acc);
                 }
                 umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
                 if (++s == p.stages) { s = 0; ph ^= 1; }
                 if (u + 1 == u_end || (u + 1) % KB == 0) {   // segment complete
-                    umma_commit(&accum_full);
+                    umma_commit(&accum_full[buf]);
                     ++seg;
                 }
             }
@@ -259,13 +266,14 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             int wid, m0;
             tile_of(tile, wid, m0);
             const int slice = blockIdx.x - (tile * KB) / p.U;
-            mbar_wait(&accum_full, seg & 1);
+            const int buf = seg % p.n_bufs, use = seg / p.n_bufs;
+            mbar_wait(&accum_full[buf], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int half = 0; half < (p.BM >> 7); ++half) {
                 const int row = m0 + half * BLOCK_M + q * 32 + lane;           // output feature
                 const bool row_ok = row < p.n_rows[wid];
                 float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
-                const uint32_t tbase = tmem_base + half * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+                const uint32_t tbase = tmem_base + buf * p.buf_stride + half * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
                 for (int c = 0; c < p.T_pad; c += 16) {
                     uint32_t r[16];
                     tmem_ld16(tbase + static_cast<uint32_t>(c), r);
@@ -278,7 +286,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
             u = seg_end;
         }
     }
@@ -343,7 +351,10 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     // Two stacked 128-row MMAs per activation tile halve the L2->SM re-reads of the activations (the limiter at
     // T >~ 100, profiles/r01_ncu_full_v2.txt); they need 2 x T_pad TMEM columns and only pay off on wide outputs.
     const char* force = getenv("ATSPEED_GEMM_BM");
-    pl->BM = (pl->T_pad <= 256 && tiles128 >= 48 && pl->T_pad >= 32) ? 256 : 128;
+    // (gemm_sweep: at T_pad <= 128 BM = 256 streams 4.7-5.9 TB/s where BM = 128 stalls at 3.3-3.8 -- one CTA per SM keeps too
+    // few TMA boxes in flight; beyond that the [T_pad, 64] activation box dominates and the extra partial-sum traffic of
+    // 256-row tiles costs more than it saves)
+    pl->BM = (pl->T_pad <= 128 && tiles128 >= 2) ? 256 : 128;
     if (force && atoi(force) == 128) pl->BM = 128;
     if (force && atoi(force) == 256 && pl->T_pad <= 256) pl->BM = 256;
     pl->total_tiles = 0;
@@ -357,6 +368,15 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     if (allow_cut) {
         int grid = units < num_sms ? units : num_sms;
         pl->U = (units + grid - 1) / grid;
+        // small projections (the 68M draft): a CTA needs a few k-blocks to amortise its prologue / epilogue, and every extra
+        // cut is one more slice for the consumer
+        const int min_u = pl->KB < 8 ? pl->KB : 8;
+        if (pl->U < min_u) pl->U = min_u;
+        // Narrow outputs at large T (o / down projections): the partial-sum slices and their epilogues cost as much as the
+        // weights, so prefer a whole number of k-splits per tile (one segment per CTA, `s` slices) when that still fills
+        // >= 80 % of the SMs (gemm_sweep: o 26 -> 21 us, down 41 -> 31 us at T = 220).
+        const int s = num_sms / pl->total_tiles;
+        if (pl->T_pad > 128 && s >= 2 && s <= pl->KB && pl->total_tiles * s * 10 >= num_sms * 8) pl->U = (pl->KB + s - 1) / s;
     } else {
         const int per = (pl->total_tiles + num_sms - 1) / num_sms;
         pl->U = per * pl->KB;
@@ -374,11 +394,14 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
     ATS_CHECK_ARG(stages >= 2, "gemm: T=%d leaves room for %d pipeline stages", T, stages);
     pl->stages = stages;
-    const int need = pl->BM == 256 ? 2 * pl->T_pad : pl->T_pad;
     int acc = 32;
-    while (acc < (pl->BM == 256 ? pl->T_pad : need)) acc <<= 1;
+    while (acc < pl->T_pad) acc <<= 1;                       // columns of one 128-row accumulator (power of two)
     pl->acc_stride = acc;
-    pl->tmem_cols = pl->BM == 256 ? 2 * acc : acc;
+    const int per_buf = pl->BM == 256 ? 2 * acc : acc;
+    pl->n_bufs = 2 * per_buf <= 512 ? 2 : 1;                 // double-buffer so an epilogue overlaps the next segment
+    if (const char* e = getenv("ATSPEED_GEMM_BUFS")) { if (atoi(e) == 1) pl->n_bufs = 1; }
+    pl->buf_stride = per_buf;
+    pl->tmem_cols = pl->n_bufs * per_buf;
     ATS_CHECK_ARG(pl->tmem_cols <= 512, "gemm: %d TMEM columns", pl->tmem_cols);
     return ATS_OK;
 }
@@ -406,7 +429,10 @@ int gemm_make_xmap(XMap* xm, const void* x, int T, int K) {
     const int T_pad = (T + 15) & ~15;
     // activations: tokens 0..255 through tm0 (box = min(T_pad,256) rows), tokens 256..T_pad-1 through tm1
     // (box = T_pad-256 rows); rows past T are zero-filled by TMA, and each box always delivers its full byte count.
-    ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, T_pad > 256 ? 256 : T_pad));
+    int box0 = T_pad > 256 ? 256 : T_pad;
+    if (const char* e = getenv("ATSPEED_GEMM_BBOX")) { if (atoi(e) >= 16 && atoi(e) < box0 && T_pad <= 256) box0 = atoi(e); }  // TIMING ONLY
+    xm->box0 = box0;
+    ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, box0));
     ATS_TRY(make_tmap_bf16_kmajor(&xm->tm1, x, T, K, T_pad > 256 ? T_pad - 256 : 16));
     xm->T = T; xm->K = K;
     return ATS_OK;
@@ -428,6 +454,8 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, float* out
     }
     p.BM = pl.BM; p.U = pl.U; p.total_units = pl.total_tiles * pl.KB;
     p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.acc_stride = pl.acc_stride;
+    p.n_bufs = pl.n_bufs; p.buf_stride = pl.buf_stride;
+    p.b_box_bytes = (pl.T_pad > 256 ? pl.T_pad : xm.box0) * BLOCK_K * 2;
     const int stage_bytes = pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
     const size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + 1024;
     static int max_dyn = 0;
@@ -450,8 +478,8 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, float* out
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // previous kernel; see griddepcontrol.wait
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, w.tmap[0], w.tmap[w.n > 1 ? 1 : 0], w.tmap[w.n > 2 ? 2 : 0],
-                                xm.tm0, xm.tm1, p));
+    const CUtensorMap* tw = pl.BM == 256 ? w.tmap256 : w.tmap;
+    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1, p));
     return ATS_OK;
 }
 

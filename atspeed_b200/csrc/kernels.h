@@ -11,6 +11,7 @@ struct GemmWeights {
     int rows[3];           // output features of each
     int colbase[3];        // first output column of each
     CUtensorMap tmap[3];   // [rows_i, K] bf16, K-major, box 64 x 128, SWIZZLE_128B
+    CUtensorMap tmap256[3];   // same tensors, box 64 x 256: one TMA operation per 256-row tile (BM = 256)
 };
 int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, long long cols, int box_rows);
 // One launch's work decomposition (host-computed, see gemm.cu): persistent CTAs each own a contiguous range of
@@ -22,7 +23,7 @@ struct GemmPlan {
     int U;                  // units per CTA
     int grid;
     int max_slices;         // most slices any tile of this launch has
-    int stages, tmem_cols, acc_stride;
+    int stages, tmem_cols, acc_stride, n_bufs, buf_stride;
 };
 // What a consumer of the partial sums needs to know: how many slices hold column `col`.
 struct SplitMap {
@@ -37,7 +38,7 @@ struct SplitMap {
     }
 #endif
 };
-struct XMap { CUtensorMap tm0, tm1; int T, K; };   // activation operand [T, K] bf16 (two boxes: tokens < 256, >= 256)
+struct XMap { CUtensorMap tm0, tm1; int T, K, box0; };   // activation operand [T, K] bf16 (two boxes: tokens < 256, >= 256)
 int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, GemmPlan* plan);
 int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms);
 SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& plan);
@@ -77,6 +78,16 @@ int silu_mul(const float* part, const SplitMap& sm, long long split_stride, int 
 // out[t][c] = sum of the slices of column c (stand-alone GEMM entry point / tests)
 int reduce_slices(const float* part, const SplitMap& sm, long long split_stride, int ldp, int T, int cols, float* out,
                   int ldo, cudaStream_t st);
+
+// ---- forward_f32.cu: fp32 exact-parity forward (weights handed over as fp32) -----------------------------
+int f32_embed(const float* table, const int* tok, int T, int hidden, int vocab, float* h, cudaStream_t st);
+int f32_rmsnorm(const float* h, const float* g, int T, int hidden, float eps, float* x, const int* row_index, cudaStream_t st);
+int f32_gemm(const float* x, const float* w, int T, int N, int K, float* out, int ldo, bool accumulate, cudaStream_t st);
+int f32_rope_append(const float* qkv, const BatchDesc& b, int T, int n_heads, int head_dim, const float* rope_cos,
+                    const float* rope_sin, int max_pos, float* qbuf, float* kcache, float* vcache, cudaStream_t st);
+int f32_tree_attention(const float* q, const float* kcache, const float* vcache, const BatchDesc& b, int T, int S, int n_heads,
+                       int head_dim, float* out, cudaStream_t st);
+int f32_silu_mul(const float* gu, int T, int mlp, float* m, cudaStream_t st);
 
 // ---- attention.cu -------------------------------------------------------------------------------
 int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,

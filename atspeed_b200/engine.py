@@ -35,30 +35,37 @@ _HF_NAMES = {"wq": "self_attn.q_proj", "wk": "self_attn.k_proj", "wv": "self_att
              "ln2": "post_attention_layernorm"}
 
 
-def rope_tables(head_dim: int, theta: float, max_pos: int):
+def rope_tables(head_dim: int, theta: float, max_pos: int, round_bf16: bool = True):
     """cos/sin exactly as HF LlamaRotaryEmbedding computes them (fp32 on the host), rounded to bf16 the way a
-    bf16 model sees them, returned as fp32 [max_pos, head_dim/2]."""
+    bf16 model sees them (or left in fp32 for the fp32 parity mode), returned as fp32 [max_pos, head_dim/2]."""
     inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
     fr = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv_freq[None, :]
+    if not round_bf16:
+        return fr.cos().contiguous(), fr.sin().contiguous()
     return fr.cos().to(torch.bfloat16).float().contiguous(), fr.sin().to(torch.bfloat16).float().contiguous()
 
 
 class DeviceModel:
-    """A LLaMA decoder's weights as bf16 CUDA tensors plus the atspeed_model_desc pointing at them."""
+    """A LLaMA decoder's weights as CUDA tensors plus the atspeed_model_desc pointing at them.
+    dtype bfloat16 = the production path (tcgen05 GEMMs); float32 = the exact-parity mode (fp32 SIMT forward,
+    csrc/forward_f32.cu), meant for the small parity configurations."""
 
-    def __init__(self, spec: ModelSpec, weights: Dict, device, max_pos: int = 1024):
+    def __init__(self, spec: ModelSpec, weights: Dict, device, max_pos: int = 1024, dtype=torch.bfloat16):
         self.spec, self.device = spec, torch.device(device)
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise _lib.AtSpeedError(f"unsupported weight dtype {dtype}: bfloat16 or float32")
+        self.dtype = dtype
 
         def dev(t):
             t = t.detach()
-            if t.dtype != torch.bfloat16 or t.device != self.device or not t.is_contiguous():
-                t = t.to(self.device, torch.bfloat16).contiguous()
+            if t.dtype != dtype or t.device != self.device or not t.is_contiguous():
+                t = t.to(self.device, dtype).contiguous()
             return t
 
         self.embed, self.norm, self.lm_head = dev(weights["embed"]), dev(weights["norm"]), dev(weights["lm_head"])
         self.layers = [{k: dev(ly[k]) for k in _LAYER_KEYS} for ly in weights["layers"]]
         assert len(self.layers) == spec.n_layers
-        cos, sin = rope_tables(spec.head_dim, spec.rope_theta, max_pos)
+        cos, sin = rope_tables(spec.head_dim, spec.rope_theta, max_pos, round_bf16=dtype == torch.bfloat16)
         self.rope_cos, self.rope_sin = cos.to(self.device), sin.to(self.device)
         self._ptrs = (C.c_void_p * (spec.n_layers * 9))()
         for i, ly in enumerate(self.layers):
@@ -70,13 +77,15 @@ class DeviceModel:
         d.embed, d.final_norm, d.lm_head = self.embed.data_ptr(), self.norm.data_ptr(), self.lm_head.data_ptr()
         d.layer_weights = C.cast(self._ptrs, C.POINTER(C.c_void_p))
         d.rope_cos, d.rope_sin, d.max_pos = self.rope_cos.data_ptr(), self.rope_sin.data_ptr(), max_pos
+        d.weights_f32 = 1 if dtype == torch.float32 else 0
         self.desc = d
 
     @classmethod
-    def from_hf(cls, model, device=None, max_pos: int = 1024) -> "DeviceModel":
+    def from_hf(cls, model, device=None, max_pos: int = 1024, dtype=None) -> "DeviceModel":
         """From a transformers LlamaForCausalLM (the object the reference passes as target_model /
-        draft_model, code/inference.py:76-100). fp16/fp32 weights are converted to bf16 copies; bf16 CUDA
-        weights are used in place (zero copy)."""
+        draft_model, code/inference.py:76-100).  bf16 CUDA weights are used in place (zero copy), fp16 weights are
+        converted to bf16 copies; an fp32 model keeps fp32 and runs the exact-parity fp32 forward unless `dtype`
+        says otherwise."""
         cfg = model.config
         n_kv = getattr(cfg, "num_key_value_heads", None) or cfg.num_attention_heads
         if n_kv != cfg.num_attention_heads:
@@ -98,7 +107,9 @@ class DeviceModel:
         for i in range(spec.n_layers):
             W["layers"].append({k: sd[f"model.layers.{i}.{n}.weight"] for k, n in _HF_NAMES.items()})
         device = device if device is not None else W["embed"].device
-        return cls(spec, W, device, max_pos)
+        if dtype is None:
+            dtype = torch.float32 if W["embed"].dtype == torch.float32 else torch.bfloat16
+        return cls(spec, W, device, max_pos, dtype)
 
 
 def as_device_model(model, device=None) -> DeviceModel:

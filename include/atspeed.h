@@ -44,7 +44,9 @@ int atspeed_abi_version(void);
  * ---------------------------------------------------------------------------------------------- */
 
 /* A LLaMA decoder as laid out by HF `LlamaForCausalLM.state_dict()` (what `model(**inputs)` runs at
- * code/beamSD.py:52,221): all weights bf16, row-major [out_features, in_features], on the device. */
+ * code/beamSD.py:52,221): row-major [out_features, in_features] tensors on the device, all bf16 (production: tcgen05
+ * GEMMs, bf16 activations) or -- weights_f32 = 1 -- all fp32: the exact-parity mode (plain fp32 SIMT kernels,
+ * csrc/forward_f32.cu) that reproduces the reference's ranked lists bit for bit on the small parity configurations. */
 typedef struct atspeed_model_desc {
     int32_t vocab, hidden, n_layers, n_heads, head_dim, mlp;
     float rms_eps;
@@ -57,6 +59,7 @@ typedef struct atspeed_model_desc {
     const float* rope_cos;    /* [max_pos, head_dim/2] fp32, bf16-rounded values (LlamaRotaryEmbedding) */
     const float* rope_sin;
     int32_t max_pos;
+    int32_t weights_f32;      /* 0: every weight pointer is bf16; 1: every weight pointer is fp32 (rope tables unrounded) */
 } atspeed_model_desc;
 
 /* The compiled constraint (code/generation_trie.py Trie / code/data.py:84-104 positional fn): CSR child table. */

@@ -17,7 +17,7 @@ NBUF = 6
 
 
 def bench(name, T, env):
-    for k in ("ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL"):
+    for k in ("ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL", "ATSPEED_GEMM_BUFS", "ATSPEED_GEMM_BBOX"):
         os.environ.pop(k, None)
     os.environ.update(env)
     K, rows = SHAPES[name]
@@ -52,21 +52,22 @@ def bench(name, T, env):
 
 WS = {n: [[(torch.randn(r, K, device=dev) * 0.02).to(torch.bfloat16) for r in rows] for _ in range(NBUF)]
       for n, (K, rows) in SHAPES.items()}
-CONFIGS = [("default", {}), ("bm128", {"ATSPEED_GEMM_BM": "128"}), ("bm256", {"ATSPEED_GEMM_BM": "256"}),
-           ("bm128 st6", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_STAGES": "6"}),
-           ("bm128 st4 x296", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_STAGES": "5", "ATSPEED_GEMM_CTAS": "296"}),
-           ("bm256 st3 x296", {"ATSPEED_GEMM_BM": "256", "ATSPEED_GEMM_STAGES": "3", "ATSPEED_GEMM_CTAS": "296"}),
-           ("bm128 x132", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_CTAS": "132"}),
-           ("bm256 nopdl", {"ATSPEED_GEMM_BM": "256", "ATSPEED_PDL": "0"}),
-           ("bm128 nopdl", {"ATSPEED_GEMM_BM": "128", "ATSPEED_PDL": "0"})]
-print(f"{'config':<18}" + "".join(f"{n + ' T=' + str(T):>16}" for n in SHAPES for T in (10, 220)))
+TS = (10, 50, 130, 220)
+CONFIGS = [("default", {}), ("1 tmem buf", {"ATSPEED_GEMM_BUFS": "1"}), ("bm128", {"ATSPEED_GEMM_BM": "128"}),
+           ("bm256", {"ATSPEED_GEMM_BM": "256"}), ("bm128 x132", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_CTAS": "132"}),
+           ("bm128 2/SM", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_STAGES": "2", "ATSPEED_GEMM_CTAS": "296"})]
+if len(sys.argv) > 1 and sys.argv[1] == "bbox":
+    CONFIGS = [("default", {}), ("bbox112", {"ATSPEED_GEMM_BBOX": "112"}), ("bbox64", {"ATSPEED_GEMM_BBOX": "64"}),
+               ("bbox16", {"ATSPEED_GEMM_BBOX": "16"})]
+    TS = (130, 220)
+print(f"{'config':<14}" + "".join(f"{n[:7] + ' ' + str(T):>13}" for n in SHAPES for T in TS))
 for cname, env in CONFIGS:
-    row = f"{cname:<18}"
+    row = f"{cname:<14}"
     for n in SHAPES:
-        for T in (10, 220):
+        for T in TS:
             try:
                 us, gbs = bench(n, T, env)
-                row += f"{us:>9.1f}/{gbs / 1e3:>4.2f}T "
+                row += f"{us:>7.1f}/{gbs / 1e3:>4.2f} "
             except Exception as e:
-                row += f"{'err':>16}"
+                row += f"{'err':>13}"
     print(row, flush=True)
