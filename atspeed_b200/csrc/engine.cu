@@ -918,6 +918,25 @@ static int standalone_gemm(const void* x, int32_t T, int32_t K, const void* cons
     return x ? gemm_make_xmap(xm, x, T, K) : ATS_OK;
 }
 
+int atspeed_gemm_plan(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_t rows2, int32_t num_sms, int32_t allow_cut,
+                      int32_t* info16, int32_t* slices_of_col) {
+    ATS_CHECK_ARG(info16 && rows0 > 0, "null info / rows0=%d", rows0);
+    GemmWeights g = shape_only(K, {rows0});
+    if (rows1 > 0) { g.rows[1] = rows1; g.colbase[1] = rows0; g.n = 2; }
+    if (rows2 > 0) { g.rows[2] = rows2; g.colbase[2] = rows0 + rows1; g.n = 3; }
+    GemmPlan pl;
+    ATS_TRY(gemm_make_plan(g, T, num_sms, allow_cut != 0, &pl));
+    const int v[16] = {pl.BM, pl.KB, pl.total_tiles, pl.U, pl.grid, pl.max_slices, pl.stages, pl.tmem_cols, pl.n_bufs, pl.T_pad,
+                       pl.tiles[0], pl.tiles[1], pl.tiles[2], 0, 0, 0};
+    for (int i = 0; i < 16; ++i) info16[i] = v[i];
+    if (slices_of_col) {
+        const SplitMap sm = gemm_split_map(g, pl);
+        const int cols = rows0 + (rows1 > 0 ? rows1 : 0) + (rows2 > 0 ? rows2 : 0);
+        for (int c = 0; c < cols; ++c) slices_of_col[c] = sm.slices(c);
+    }
+    return ATS_OK;
+}
+
 int atspeed_gemm_scratch_bytes(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_t rows2, size_t* bytes) {
     ATS_CHECK_ARG(bytes, "null bytes");
     GemmWeights g = shape_only(K, {rows0});

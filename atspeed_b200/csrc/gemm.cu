@@ -182,35 +182,38 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            auto load_a = [&](int u, int s) {
-                int wid, m0;
-                tile_of(u / KB, wid, m0);
-                const int kb = u - (u / KB) * KB;
+            // (tile, kb) of the next unit to load, advanced incrementally: the loops of the two single-thread roles are on
+            // the kernel's critical path, so they contain no integer division
+            int tile = u_begin / KB, kb = u_begin - tile * KB, wid, m0;
+            tile_of(tile, wid, m0);
+            auto advance = [&]() {
+                if (++kb == KB) { kb = 0; ++tile; tile_of(tile, wid, m0); }
+            };
+            auto load_a = [&](int s) {
                 const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
                 uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
                 mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(a_bytes + p.b_box_bytes));
-                // BM = 256: tmW has a 256-row box -- ONE operation fills both stacked 128-row tiles (a TMA operation costs
-                // ~0.3 us of a CTA's issue stream whatever its size: fewer, larger boxes stream faster)
-                tma_load_2d(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);
+                tma_load_2d(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);      // BM = 256: the map's box is 256 rows
             };
-            auto load_b = [&](int u, int s) {
-                const int kb = u - (u / KB) * KB;
+            auto load_b = [&](int s, int kbb) {
                 uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
-                tma_load_2d(&tmX, &full_bar[s], b_dst, kb * BLOCK_K, 0);
-                if (p.T_pad > 256) tma_load_2d(&tmX1, &full_bar[s], b_dst + 256 * BLOCK_K * 2, kb * BLOCK_K, 256);
+                tma_load_2d(&tmX, &full_bar[s], b_dst, kbb * BLOCK_K, 0);
+                if (p.T_pad > 256) tma_load_2d(&tmX1, &full_bar[s], b_dst + 256 * BLOCK_K * 2, kbb * BLOCK_K, 256);
             };
             // The weights do not depend on the previous kernel: fill the ring with weight tiles first, then wait for
             // the producer of the activations (griddepcontrol.wait), then add the activation tiles.
             const int npre = n_units < p.stages ? n_units : p.stages;
-            for (int i = 0; i < npre; ++i) load_a(u_begin + i, i);
+            const int kb_first = kb;
+            for (int i = 0; i < npre; ++i) { load_a(i); advance(); }
             asm volatile("griddepcontrol.wait;" ::: "memory");
-            for (int i = 0; i < npre; ++i) load_b(u_begin + i, i);
+            for (int i = 0, kbb = kb_first; i < npre; ++i) { load_b(i, kbb); if (++kbb == KB) kbb = 0; }
             int s = npre == p.stages ? 0 : npre;
             uint32_t ph = npre == p.stages ? 1 : 0;
             for (int u = u_begin + npre; u < u_end; ++u) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                load_a(u, s);
-                load_b(u, s);
+                load_a(s);
+                load_b(s, kb);
+                advance();
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
@@ -221,14 +224,14 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             const uint32_t n1 = p.T_pad > 256 ? p.T_pad - 256 : 0;
             const uint32_t idesc0 = make_idesc(n0), idesc1 = make_idesc(n1 ? n1 : 16);
             int s = 0; uint32_t ph = 0;
-            int seg = 0;
+            int kb = u_begin % KB;
+            int buf = 0;                       // accumulator buffer of the current segment (alternates when double-buffered)
+            uint32_t use[2] = {0, 0};          // how many segments each buffer has held so far
             for (int u = u_begin; u < u_end; ++u) {
-                const int kb = u % KB;
                 const bool seg_start = (u == u_begin) || kb == 0;
-                const int buf = seg % p.n_bufs, use = seg / p.n_bufs;      // `use`-th time this accumulator buffer is filled
-                if (seg_start && use > 0) {
+                if (seg_start && use[buf] > 0) {
                     // the epilogue must have drained this buffer's previous segment before it is overwritten
-                    mbar_wait(&accum_empty[buf], (use - 1) & 1);
+                    mbar_wait(&accum_empty[buf], (use[buf] - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t tacc = tmem_base + buf * p.buf_stride;
@@ -249,9 +252,11 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 }
                 umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
                 if (++s == p.stages) { s = 0; ph ^= 1; }
-                if (u + 1 == u_end || (u + 1) % KB == 0) {   // segment complete
+                if (++kb == KB) kb = 0;
+                if (u + 1 == u_end || kb == 0) {             // segment complete
                     umma_commit(&accum_full[buf]);
-                    ++seg;
+                    ++use[buf];
+                    if (p.n_bufs == 2) buf ^= 1;
                 }
             }
         }
@@ -266,7 +271,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             int wid, m0;
             tile_of(tile, wid, m0);
             const int slice = blockIdx.x - (tile * KB) / p.U;
-            const int buf = seg % p.n_bufs, use = seg / p.n_bufs;
+            const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
             mbar_wait(&accum_full[buf], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int half = 0; half < (p.BM >> 7); ++half) {

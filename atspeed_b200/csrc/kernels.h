@@ -30,13 +30,11 @@ struct SplitMap {
     int n;
     int colbase[3], tilebase[3];
     int BM, KB, U;
-#ifdef __CUDACC__
-    __device__ __forceinline__ int slices(int col) const {
+    __host__ __device__ __forceinline__ int slices(int col) const {
         const int i = col >= colbase[2] ? 2 : (col >= colbase[1] ? 1 : 0);
         const int u0 = (tilebase[i] + (col - colbase[i]) / BM) * KB;
         return (u0 + KB - 1) / U - u0 / U + 1;
     }
-#endif
 };
 struct XMap { CUtensorMap tm0, tm1; int T, K, box0; };   // activation operand [T, K] bf16 (two boxes: tokens < 256, >= 256)
 int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, GemmPlan* plan);

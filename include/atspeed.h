@@ -241,6 +241,12 @@ int atspeed_kv_gather(const void* src_base, void* dst_base, int64_t src_plane_st
  * `scratch` (atspeed_gemm_scratch_bytes; tiles cut along K across its persistent CTAs); when `out` is non-NULL the
  * slices are then reduced in fixed order into out fp32 [T][ldo] (in the forward that reduction is fused into the
  * consuming row-wise kernel). */
+/* Host-side work decomposition of one GEMM launch (no GPU needed; tests/test_gemm_plan.py): info16 = {BM, KB,
+ * total_tiles, units_per_cta U, grid, max_slices, stages, tmem_cols, n_bufs, T_pad, tiles0, tiles1, tiles2, 0, 0, 0};
+ * slices_of_col (optional, int32[rows0+rows1+rows2]) receives the number of partial-sum slices the consumers add for
+ * each output column (the device-side SplitMap arithmetic evaluated on the host). */
+int atspeed_gemm_plan(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_t rows2, int32_t num_sms, int32_t allow_cut,
+                      int32_t* info16, int32_t* slices_of_col);
 int atspeed_gemm_scratch_bytes(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_t rows2, size_t* bytes);
 int atspeed_gemm_bf16(const void* x, int32_t T, int32_t K, const void* w0, int32_t rows0, const void* w1, int32_t rows1,
                       const void* w2, int32_t rows2, float* scratch, float* out, int32_t ldo, void* stream);

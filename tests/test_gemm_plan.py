@@ -1,0 +1,53 @@
+"""CPU test of the GEMM's host-side work decomposition (csrc/gemm.cu gemm_make_plan + the SplitMap arithmetic the consumer
+kernels evaluate on the device): the persistent CTAs' unit ranges must tile the (tile, k-block) space exactly, and the
+number of partial-sum slices a consumer adds for a column must equal the number of CTAs whose range touches that column's
+tile -- otherwise a consumer would read an unwritten slice or drop a written one."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+SHAPES = [(4096, (4096, 4096, 4096)), (4096, (4096,)), (4096, (11008, 11008)), (11008, (4096,)), (4096, (32859,)),
+          (768, (768, 768, 768)), (768, (3072, 3072)), (3072, (768,)), (768, (33014,)), (64, (64, 64, 64)), (128, (64,)),
+          (256, (512, 512)), (192, (200, 72))]
+
+
+@pytest.mark.parametrize("K,rows", SHAPES)
+@pytest.mark.parametrize("T", [1, 10, 16, 50, 90, 128, 130, 220, 256, 289, 512])
+@pytest.mark.parametrize("cut", [1, 0])
+def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut):
+    from atspeed_b200 import _lib
+    lib = _lib.load()
+    r = list(rows) + [0] * (3 - len(rows))
+    info = (C.c_int32 * 16)()
+    cols = sum(rows)
+    sl = (C.c_int32 * cols)()
+    for sms in (148, 132, 7):
+        rc = lib.atspeed_gemm_plan(T, K, r[0], r[1], r[2], sms, cut, info, sl)
+        assert rc == 0, lib.atspeed_last_error()
+        BM, KB, tiles, U, grid, max_slices, stages, tmem, bufs, T_pad = (int(info[i]) for i in range(10))
+        tl = [int(info[10 + i]) for i in range(3)]
+        assert BM in (128, 256) and KB == -(-K // 64) and T_pad == -(-T // 16) * 16
+        assert tiles == sum(-(-x // BM) for x in rows) == sum(tl)
+        units = tiles * KB
+        assert grid <= sms or not cut        # persistent: at most one CTA per SM when tiles may be cut
+        assert (grid - 1) * U < units <= grid * U, "every CTA owns at least one unit and the ranges cover all units"
+        assert 2 <= stages <= 12 and tmem <= 512 and tmem & (tmem - 1) == 0
+        assert stages * (BM * 128 + T_pad * 128) <= 220 * 1024
+        assert (BM // 128) * bufs * T_pad <= 512
+        if not cut:
+            assert U % KB == 0 and max_slices == 1
+        # slices per column == number of CTA ranges [c*U, (c+1)*U) that intersect the tile's units [t*KB, (t+1)*KB)
+        slices = np.frombuffer(sl, dtype=np.int32)
+        col, t = 0, 0
+        worst = 0
+        for w in rows:
+            for i in range(-(-w // BM)):
+                lo, hi = t * KB, (t + 1) * KB - 1
+                n = hi // U - lo // U + 1
+                worst = max(worst, n)
+                c0, c1 = col + i * BM, col + min(w, (i + 1) * BM)
+                assert (slices[c0:c1] == n).all(), (t, n, slices[c0:c1][:4])
+                t += 1
+            col += w
+        assert worst == max_slices

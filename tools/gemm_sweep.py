@@ -17,7 +17,7 @@ NBUF = 6
 
 
 def bench(name, T, env):
-    for k in ("ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL", "ATSPEED_GEMM_BUFS", "ATSPEED_GEMM_BBOX"):
+    for k in ("ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL", "ATSPEED_GEMM_BUFS", "ATSPEED_GEMM_BBOX", "ATSPEED_GEMM_PACKED", "ATSPEED_GEMM_DBG", "ATSPEED_GEMM_CHAINS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     K, rows = SHAPES[name]
@@ -56,7 +56,24 @@ TS = (10, 50, 130, 220)
 CONFIGS = [("default", {}), ("1 tmem buf", {"ATSPEED_GEMM_BUFS": "1"}), ("bm128", {"ATSPEED_GEMM_BM": "128"}),
            ("bm256", {"ATSPEED_GEMM_BM": "256"}), ("bm128 x132", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_CTAS": "132"}),
            ("bm128 2/SM", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_STAGES": "2", "ATSPEED_GEMM_CTAS": "296"})]
-if len(sys.argv) > 1 and sys.argv[1] == "bbox":
+if len(sys.argv) > 1 and sys.argv[1] == "chains":
+    CONFIGS = [("default", {}), ("c1 b2", {"ATSPEED_GEMM_CHAINS": "1", "ATSPEED_GEMM_BUFS": "2"}),
+               ("c2 b1", {"ATSPEED_GEMM_CHAINS": "2", "ATSPEED_GEMM_BUFS": "1"}),
+               ("c2 b2", {"ATSPEED_GEMM_CHAINS": "2", "ATSPEED_GEMM_BUFS": "2"}),
+               ("c4 b1", {"ATSPEED_GEMM_CHAINS": "4", "ATSPEED_GEMM_BUFS": "1"}),
+               ("bm128 c2 b2", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_CHAINS": "2", "ATSPEED_GEMM_BUFS": "2"}),
+               ("bm128 c4 b1", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_CHAINS": "4", "ATSPEED_GEMM_BUFS": "1"}),
+               ("bm128 c4 b2", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_CHAINS": "4", "ATSPEED_GEMM_BUFS": "2"}),
+               ("bm256 c2 b1", {"ATSPEED_GEMM_BM": "256", "ATSPEED_GEMM_CHAINS": "2", "ATSPEED_GEMM_BUFS": "1"})]
+    TS = (10, 50, 90, 130, 220)
+elif len(sys.argv) > 1 and sys.argv[1] == "dbg":
+    CONFIGS = [("default", {}), ("no epi stores", {"ATSPEED_GEMM_DBG": "1"}), ("no mma", {"ATSPEED_GEMM_DBG": "2"}),
+               ("neither", {"ATSPEED_GEMM_DBG": "3"}), ("neither bm256", {"ATSPEED_GEMM_DBG": "3", "ATSPEED_GEMM_BM": "256"}),
+               ("neither bm128", {"ATSPEED_GEMM_DBG": "3", "ATSPEED_GEMM_BM": "128"})]
+elif len(sys.argv) > 1 and sys.argv[1] == "packed":
+    CONFIGS = [("default", {}), ("packed", {"ATSPEED_GEMM_PACKED": "1"}), ("packed bm128", {"ATSPEED_GEMM_PACKED": "1", "ATSPEED_GEMM_BM": "128"}),
+               ("packed bm256", {"ATSPEED_GEMM_PACKED": "1", "ATSPEED_GEMM_BM": "256"})]
+elif len(sys.argv) > 1 and sys.argv[1] == "bbox":
     CONFIGS = [("default", {}), ("bbox112", {"ATSPEED_GEMM_BBOX": "112"}), ("bbox64", {"ATSPEED_GEMM_BBOX": "64"}),
                ("bbox16", {"ATSPEED_GEMM_BBOX": "16"})]
     TS = (130, 220)
