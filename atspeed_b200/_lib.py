@@ -28,7 +28,7 @@ class TrieDesc(C.Structure):
 class Config(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("max_new_tokens", C.c_int32), ("max_prompt", C.c_int32),
                 ("num_sms", C.c_int32), ("do_sample", C.c_int32), ("top_k", C.c_int32), ("temperature", C.c_float),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("max_users", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -59,6 +59,10 @@ SYMBOLS = {
     "atspeed_session_result": (C.c_int, [C.c_void_p, c_i32p, c_f32p, c_i32p, C.c_void_p]),
     "atspeed_bssd": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_f32p, c_i32p,
                                C.POINTER(Stats), C.c_void_p]),
+    "atspeed_bssd_batch": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p, c_f32p, c_i32p,
+                                     C.c_void_p, C.c_void_p]),
+    "atspeed_bssd_batch_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, c_i32p, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
     "atspeed_bssd_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.POINTER(Stats), C.c_void_p]),
     "atspeed_session_begin_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

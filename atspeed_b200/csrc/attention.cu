@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                       const __nv_bfloat16* __restrict__ vcache, const int* __restrict__ prefix_len,
                       const uint32_t* __restrict__ vis, int vis_base, int T, int S, int n_heads, float scale,
-                      __nv_bfloat16* __restrict__ out) {
+                      __nv_bfloat16* __restrict__ out, CohortKV ckv) {
     constexpr int LDS = D + 8;                     // padded row (bf16 elements): conflict-free ldmatrix, rows 16-byte aligned
     extern __shared__ __align__(16) uint8_t att_smem[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
@@ -88,7 +88,25 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 
     pdl_launch_dependents();
     pdl_wait();
-    const int head = blockIdx.y, q0 = blockIdx.x * ATT_BQ;
+    const int head = blockIdx.y;
+    int q0 = blockIdx.x * ATT_BQ;
+    if (ckv.n > 0) {
+        // cohort forward: a CTA's 64 queries belong to ONE user (own KV cache, prompt length and extent); blockIdx.x
+        // enumerates the users' 64-query blocks in order
+        int b = blockIdx.x, u = 0;
+        for (; u < ckv.n; ++u) {
+            const int nb = (ckv.T[u] + ATT_BQ - 1) / ATT_BQ;
+            if (b < nb) break;
+            b -= nb;
+        }
+        if (u >= ckv.n) return;
+        q0 = ckv.tok0[u] + b * ATT_BQ;
+        T = ckv.tok0[u] + ckv.T[u];            // rows >= T are padding of this user's last block
+        S = ckv.S[u];
+        vis_base = ckv.vis_base[u];
+        kcache += ckv.kv_off[u];
+        vcache += ckv.kv_off[u];
+    }
     const int HD = n_heads * D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
 
@@ -273,7 +291,12 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                    const BatchDesc& b, int T, int S, int n_heads, int head_dim, __nv_bfloat16* out, cudaStream_t st) {
     ATS_CHECK_ARG(T >= 1 && S >= 1, "attention: T=%d S=%d", T, S);
-    dim3 grid((T + ATT_BQ - 1) / ATT_BQ, n_heads);
+    int q_blocks = (T + ATT_BQ - 1) / ATT_BQ;
+    if (b.ckv.n > 0) {
+        q_blocks = 0;
+        for (int u = 0; u < b.ckv.n; ++u) q_blocks += (b.ckv.T[u] + ATT_BQ - 1) / ATT_BQ;
+    }
+    dim3 grid(q_blocks, n_heads);
     const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
     const size_t smem = static_cast<size_t>(ATT_BQ + 4 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
 #define ATS_ATT(DD)                                                                                              \
@@ -285,7 +308,7 @@ int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __
             attr_set = true;                                                                                     \
         }                                                                                                        \
         ATS_CUDA(launch_pdl(tree_attention_kernel<DD>, grid, dim3(ATT_THREADS), smem, st, q, kcache, vcache,      \
-                            b.prefix_len, b.vis, b.vis_base, T, S, n_heads, scale, out));                       \
+                            b.prefix_len, b.vis, b.vis_base, T, S, n_heads, scale, out, b.ckv));                \
     } while (0)
     switch (head_dim) {
         case 16: ATS_ATT(16); break;

@@ -43,8 +43,9 @@ int tree_begin(const TreeDev& t, const BatchDev& b, const int* prompt, int P, cu
 // ---------------------------------------------------------------------------------------------
 // forward batch = [prompt] [missing] [levels l_from..l_to]; logits rows = [root row] [levels rows_from..l_to]
 // ---------------------------------------------------------------------------------------------
-__global__ void tree_build_batch_kernel(TreeDev t, BatchDev b, TreeGeom g, BatchPlan plan, const int* __restrict__ prompt,
-                                        int P, int T_cap, int R_cap) {
+__device__ void tree_build_batch_body(const TreeDev& t, const BatchDev& b, const TreeGeom& g, const BatchPlan& plan,
+                                      const int* __restrict__ prompt, int P, int T_cap, int R_cap, int tok0, int row0,
+                                      int user) {
     const int gen0 = t.scal[SC_GEN0];
     const int miss_n = t.scal[SC_MISS];
     const int trash0 = g.tree_slot(P, MAX_LEVELS, 0);    // K trash slots after the last level, for padded entries
@@ -85,9 +86,11 @@ __global__ void tree_build_batch_kernel(TreeDev t, BatchDev b, TreeGeom g, Batch
                 vis[(slot - P) >> 5] = 1u << ((slot - P) & 31);
             }
         }
-        b.tok[x] = tok; b.pos[x] = pos; b.slot[x] = slot; b.prefix_len[x] = prefix;
+        const int xo = tok0 + x;
+        b.tok[xo] = tok; b.pos[xo] = pos; b.slot[xo] = slot; b.prefix_len[xo] = prefix;
+        if (user >= 0) b.tok_user[xo] = user;
 #pragma unroll
-        for (int w = 0; w < VIS_WORDS; ++w) b.vis[x * VIS_WORDS + w] = vis[w];
+        for (int w = 0; w < VIS_WORDS; ++w) b.vis[xo * VIS_WORDS + w] = vis[w];
     }
     // logits rows
     for (int r = threadIdx.x; r < R_cap; r += blockDim.x) {
@@ -108,9 +111,14 @@ __global__ void tree_build_batch_kernel(TreeDev t, BatchDev b, TreeGeom g, Batch
             }
             if (l <= plan.l_to) { idx = base + y; node = y < t.cnt[l] ? t.node[L_IDX(l, y)] : -1; }
         }
-        b.rows_idx[r] = idx;
-        b.row_node[r] = node;
+        b.rows_idx[row0 + r] = tok0 + idx;
+        b.row_node[row0 + r] = node;
     }
+}
+
+__global__ void tree_build_batch_kernel(TreeDev t, BatchDev b, TreeGeom g, BatchPlan plan, const int* __restrict__ prompt,
+                                        int P, int T_cap, int R_cap) {
+    tree_build_batch_body(t, b, g, plan, prompt, P, T_cap, R_cap, 0, 0, -1);
 }
 
 int tree_build_batch(const TreeDev& t, const BatchDev& b, const TreeGeom& g, const BatchPlan& plan, const int* prompt,
@@ -166,10 +174,9 @@ __device__ __forceinline__ int warp_merge(int n_rows, const int* row_of, const f
     return n_out;
 }
 
-__global__ void __launch_bounds__(64)
-tree_select_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int level, int row0, int B, const int* __restrict__ cand_tok,
-                   const int* __restrict__ cand_edge, const float* __restrict__ cand_logp,
-                   const int* __restrict__ cand_cnt, int width, int P) {
+__device__ void tree_select_body(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int level, int row0, int B,
+                                 const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                                 const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int width, int P) {
     __shared__ Pick picks[MAX_BEAMS];
     __shared__ int row_of[MAX_BEAMS];
     __shared__ float parent[MAX_BEAMS];
@@ -198,6 +205,13 @@ tree_select_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int level, int row0, int
         t.vis[L_IDX(nl, p) * VIS_WORDS + ((slot - P) >> 5)] |= 1u << ((slot - P) & 31);
     }
     if (threadIdx.x == 0) { t.cnt[nl] = n; t.scal[SC_RESULT] = nl; }
+}
+
+__global__ void __launch_bounds__(64)
+tree_select_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int level, int row0, int B, const int* __restrict__ cand_tok,
+                   const int* __restrict__ cand_edge, const float* __restrict__ cand_logp,
+                   const int* __restrict__ cand_cnt, int width, int P) {
+    tree_select_body(t, g, trie, level, row0, B, cand_tok, cand_edge, cand_logp, cand_cnt, width, P);
 }
 
 int tree_select(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int level, int row0, int B,
@@ -327,10 +341,9 @@ __device__ void round_tail(const TreeDev& t, const TreeGeom& g, const TrieCSR& t
 // ---------------------------------------------------------------------------------------------
 // kernel (b): AtSpeed-S strict top-K verify over the whole draft tree in one launch
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
-tree_verify_strict_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int draft_len, int root_rows,
-                          const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
-                          const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int P) {
+__device__ void tree_verify_strict_body(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int draft_len, int root_rows,
+                                        const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                                        const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int P) {
     __shared__ Pick picks[MAX_BEAMS];
     __shared__ int row_of[MAX_BEAMS];
     __shared__ float cur_score[MAX_BEAMS];
@@ -401,6 +414,13 @@ tree_verify_strict_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int draft_len, in
     }
     __syncthreads();
     round_tail(t, g, trie, P, m, npk, draft_len, fin_parent, fin_tok, fin_edge, fin_score);
+}
+
+__global__ void __launch_bounds__(64)
+tree_verify_strict_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int draft_len, int root_rows,
+                          const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                          const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int P) {
+    tree_verify_strict_body(t, g, trie, draft_len, root_rows, cand_tok, cand_edge, cand_logp, cand_cnt, P);
 }
 
 int tree_verify_strict(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int draft_len, int root_rows,
@@ -504,10 +524,10 @@ __device__ int block_top_keys(const unsigned long long* keys, int n, int want, i
 // sampling select: level + 1 = `width` samples without replacement from q = softmax(flat) where
 // flat[j * V + tok] = logp(row j, tok) / T + score(j) over the rows' warped candidates
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SAMPLE_THREADS)
-tree_select_sample_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int level, int row0, const int* __restrict__ cand_tok,
-                          const int* __restrict__ cand_edge, const float* __restrict__ cand_logp,
-                          const int* __restrict__ cand_cnt, int width, int P, SampleCfg sc, unsigned site) {
+__device__ void tree_select_sample_body(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int level, int row0,
+                                        const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                                        const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int width,
+                                        int P, const SampleCfg& sc, unsigned site) {
     __shared__ unsigned long long keys[SAMPLE_MAX_CAND];
     __shared__ int sel[MAX_BEAMS];
     const int tid = threadIdx.x, B = sc.B, V = g.V;
@@ -558,6 +578,13 @@ tree_select_sample_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int level, int ro
     if (tid == 0) { t.cnt[nl] = n; t.scal[SC_RESULT] = nl; t.lse_q[level] = lse; }
 }
 
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+tree_select_sample_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int level, int row0, const int* __restrict__ cand_tok,
+                          const int* __restrict__ cand_edge, const float* __restrict__ cand_logp,
+                          const int* __restrict__ cand_cnt, int width, int P, SampleCfg sc, unsigned site) {
+    tree_select_sample_body(t, g, trie, level, row0, cand_tok, cand_edge, cand_logp, cand_cnt, width, P, sc, site);
+}
+
 int tree_select_sample(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int level, int row0, const int* cand_tok,
                        const int* cand_edge, const float* cand_logp, const int* cand_cnt, int width, int P,
                        const SampleCfg& sc, unsigned site, cudaStream_t st) {
@@ -581,10 +608,10 @@ int tree_select_sample(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie,
 // Where the reference is undefined (empty residual: multinomial over zeros raises for i > 0 and returns
 // disallowed tokens for i = 0) the extra beams are drawn from p itself and SC_FALLBACK is incremented.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SAMPLE_THREADS)
-tree_verify_relaxed_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int draft_len, int root_rows,
-                           const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
-                           const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int P, SampleCfg sc) {
+__device__ void tree_verify_relaxed_body(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int draft_len, int root_rows,
+                                         const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                                         const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int P,
+                                         const SampleCfg& sc) {
     __shared__ unsigned long long keys[MAX_K * MAX_BEAMS];
     __shared__ float tflat[MAX_K * MAX_BEAMS];        // target flat score of candidate (k, h)
     __shared__ int sel[MAX_K];
@@ -785,6 +812,13 @@ tree_verify_relaxed_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int draft_len, i
     round_tail(t, g, trie, P, m, npk, draft_len, fin_parent, fin_tok, fin_edge, fin_score);
 }
 
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+tree_verify_relaxed_kernel(TreeDev t, TreeGeom g, TrieCSR trie, int draft_len, int root_rows,
+                           const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                           const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int P, SampleCfg sc) {
+    tree_verify_relaxed_body(t, g, trie, draft_len, root_rows, cand_tok, cand_edge, cand_logp, cand_cnt, P, sc);
+}
+
 int tree_verify_relaxed(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int draft_len, int root_rows,
                         const int* cand_tok, const int* cand_edge, const float* cand_logp, const int* cand_cnt, int P,
                         const SampleCfg& sc, cudaStream_t st) {
@@ -799,7 +833,7 @@ int tree_verify_relaxed(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie
 // ---------------------------------------------------------------------------------------------
 // final ordering in sampling mode: beams sorted by score, descending (beamSD.py:529-531)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) tree_sort_level_kernel(TreeDev t, int level) {
+__device__ void tree_sort_level_body(const TreeDev& t, int level) {
     __shared__ int s_tok[MAX_BEAMS], s_parent[MAX_BEAMS], s_node[MAX_BEAMS], s_slot[MAX_BEAMS], s_gen[MAX_BEAMS][MAX_NEW];
     __shared__ float s_score[MAX_BEAMS];
     __shared__ uint32_t s_vis[MAX_BEAMS][VIS_WORDS];
@@ -823,6 +857,8 @@ __global__ void __launch_bounds__(64) tree_sort_level_kernel(TreeDev t, int leve
     }
 }
 
+__global__ void __launch_bounds__(64) tree_sort_level_kernel(TreeDev t, int level) { tree_sort_level_body(t, level); }
+
 int tree_sort_level(const TreeDev& t, int level, cudaStream_t st) {
     ATS_CHECK_ARG(level >= 0 && level < MAX_LEVELS, "sort: level=%d", level);
     tree_sort_level_kernel<<<1, 64, 0, st>>>(t, level);
@@ -841,6 +877,180 @@ __global__ void noise_fill_kernel(unsigned long long seed, unsigned long long st
 int noise_fill(unsigned long long seed, unsigned long long stream, int kind, int n, void* out, cudaStream_t st) {
     ATS_CHECK_ARG(n >= 1 && kind >= 0 && kind <= 2 && out, "noise_fill: n=%d kind=%d", n, kind);
     noise_fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(seed, stream, kind, n, out);
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
+}
+
+}  // namespace atspeed
+
+// =============================================================================================
+// Cohort kernels: one launch advances every user of a cohort (grid = users).  Each block runs the
+// single-user body above on its user's tree with the user's token / row offsets, so a user's results do
+// not depend on who shares the launch with it.
+// =============================================================================================
+namespace atspeed {
+
+__global__ void cohort_begin_kernel(Cohort c, const TreeDev* __restrict__ trees) {
+    const UserCtx& u = c.u[blockIdx.x];
+    const TreeDev t = trees[u.tree];
+    const int tid = threadIdx.x;
+    if (tid < SC_COUNT) t.scal[tid] = 0;
+    if (tid < MAX_LEVELS) t.cnt[tid] = tid == 0 ? 1 : 0;
+    __syncthreads();
+    if (tid == 0) {
+        t.scal[SC_P] = u.P;
+        t.scal[SC_FIRST] = 1;
+        t.tok[0] = -1; t.parent[0] = -1; t.node[0] = 0; t.slot[0] = -1; t.score[0] = 0.f;
+    }
+    if (tid < MAX_NEW) t.gen[tid] = 0;
+    if (tid < VIS_WORDS) t.vis[tid] = 0u;
+}
+
+int cohort_begin(const Cohort& c, const TreeDev* trees, cudaStream_t st) {
+    ATS_CHECK_ARG(c.n >= 1 && c.n <= MAX_USERS, "cohort of %d users", c.n);
+    cohort_begin_kernel<<<c.n, 64, 0, st>>>(c, trees);
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
+}
+
+__global__ void cohort_build_batch_kernel(Cohort c, const TreeDev* __restrict__ trees, BatchDev b, TreeGeom g,
+                                          const int* __restrict__ prompts, int prompt_stride) {
+    const UserCtx& u = c.u[blockIdx.x];
+    tree_build_batch_body(trees[u.tree], b, g, u.plan, prompts + static_cast<long long>(u.tree) * prompt_stride, u.P, u.T, u.R,
+                          u.tok0, u.row0, static_cast<int>(blockIdx.x));
+}
+
+int cohort_build_batch(const Cohort& c, const TreeDev* trees, const BatchDev& b, const TreeGeom& g, const int* prompts,
+                       int prompt_stride, cudaStream_t st) {
+    ATS_CHECK_ARG(c.n >= 1 && c.n <= MAX_USERS, "cohort of %d users", c.n);
+    cohort_build_batch_kernel<<<c.n, 256, 0, st>>>(c, trees, b, g, prompts, prompt_stride);
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
+}
+
+__global__ void __launch_bounds__(64)
+cohort_select_kernel(Cohort c, const TreeDev* __restrict__ trees, TreeGeom g, TrieCSR trie, int B,
+                     const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                     const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt) {
+    const UserCtx& u = c.u[blockIdx.x];
+    if (u.mode != 1) return;
+    tree_select_body(trees[u.tree], g, trie, u.level, u.row0, B, cand_tok, cand_edge, cand_logp, cand_cnt, u.width, u.P);
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+cohort_select_sample_kernel(Cohort c, const TreeDev* __restrict__ trees, TreeGeom g, TrieCSR trie,
+                            const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                            const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, SampleCfg sc) {
+    const UserCtx& u = c.u[blockIdx.x];
+    if (u.mode != 1) return;
+    const TreeDev t = trees[u.tree];
+    sc.stream_base = u.stream_base;
+    if (u.is_draft) {
+        // keep the draft's warped candidates of this step: the relaxed verify needs q on them (single-user sessions let
+        // kernel (a) write there directly; here kernel (a) served the whole cohort into shared rows)
+        const int n_rows = t.cnt[u.level];
+        const long long lb = static_cast<long long>(u.level) * MAX_BEAMS * MAX_BEAMS;
+        for (int i = threadIdx.x; i < n_rows * sc.B; i += blockDim.x) {
+            const long long src = static_cast<long long>(u.row0) * sc.B + i;
+            t.dcand_tok[lb + i] = cand_tok[src];
+            t.dcand_logp[lb + i] = cand_logp[src];
+            t.dcand_edge[lb + i] = cand_edge[src];
+        }
+        for (int i = threadIdx.x; i < n_rows; i += blockDim.x) t.dcand_cnt[u.level * MAX_BEAMS + i] = cand_cnt[u.row0 + i];
+    }
+    tree_select_sample_body(t, g, trie, u.level, u.row0, cand_tok, cand_edge, cand_logp, cand_cnt, u.width, u.P, sc,
+                            u.is_draft ? SITE_DRAFT : SITE_STEP);
+}
+
+int cohort_select(const Cohort& c, const TreeDev* trees, const TreeGeom& g, const TrieCSR& trie, int B, const int* cand_tok,
+                  const int* cand_edge, const float* cand_logp, const int* cand_cnt, bool sampling, const SampleCfg& sc,
+                  cudaStream_t st) {
+    ATS_CHECK_ARG(c.n >= 1 && c.n <= MAX_USERS, "cohort of %d users", c.n);
+    if (sampling) {
+        ATS_CHECK_ARG(sc.B == B, "cohort select: candidate stride %d != sample width %d", B, sc.B);
+        cohort_select_sample_kernel<<<c.n, SAMPLE_THREADS, 0, st>>>(c, trees, g, trie, cand_tok, cand_edge, cand_logp, cand_cnt, sc);
+    } else {
+        cohort_select_kernel<<<c.n, 64, 0, st>>>(c, trees, g, trie, B, cand_tok, cand_edge, cand_logp, cand_cnt);
+    }
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
+}
+
+__global__ void __launch_bounds__(64)
+cohort_verify_strict_kernel(Cohort c, const TreeDev* __restrict__ trees, TreeGeom g, TrieCSR trie, int B,
+                            const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                            const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt) {
+    const UserCtx& u = c.u[blockIdx.x];
+    if (u.mode != 2) return;
+    const long long o = static_cast<long long>(u.row0) * B;
+    tree_verify_strict_body(trees[u.tree], g, trie, u.draft_len, u.root_rows, cand_tok + o, cand_edge + o, cand_logp + o,
+                            cand_cnt + u.row0, u.P);
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+cohort_verify_relaxed_kernel(Cohort c, const TreeDev* __restrict__ trees, TreeGeom g, TrieCSR trie,
+                             const int* __restrict__ cand_tok, const int* __restrict__ cand_edge,
+                             const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, SampleCfg sc) {
+    const UserCtx& u = c.u[blockIdx.x];
+    if (u.mode != 2) return;
+    sc.stream_base = u.stream_base;
+    const long long o = static_cast<long long>(u.row0) * sc.B;
+    tree_verify_relaxed_body(trees[u.tree], g, trie, u.draft_len, u.root_rows, cand_tok + o, cand_edge + o, cand_logp + o,
+                             cand_cnt + u.row0, u.P, sc);
+}
+
+int cohort_verify(const Cohort& c, const TreeDev* trees, const TreeGeom& g, const TrieCSR& trie, int B, const int* cand_tok,
+                  const int* cand_edge, const float* cand_logp, const int* cand_cnt, bool sampling, const SampleCfg& sc,
+                  cudaStream_t st) {
+    ATS_CHECK_ARG(c.n >= 1 && c.n <= MAX_USERS, "cohort of %d users", c.n);
+    if (sampling)
+        cohort_verify_relaxed_kernel<<<c.n, SAMPLE_THREADS, 0, st>>>(c, trees, g, trie, cand_tok, cand_edge, cand_logp, cand_cnt, sc);
+    else
+        cohort_verify_strict_kernel<<<c.n, 64, 0, st>>>(c, trees, g, trie, B, cand_tok, cand_edge, cand_logp, cand_cnt);
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
+}
+
+__global__ void cohort_collect_kernel(Cohort c, const TreeDev* __restrict__ trees, int* __restrict__ out4) {
+    const int i = threadIdx.x;
+    if (i >= c.n) return;
+    const TreeDev& t = trees[c.u[i].tree];
+    out4[4 * i + 0] = t.scal[SC_NMATCH];
+    out4[4 * i + 1] = t.scal[SC_MISS];
+    out4[4 * i + 2] = t.cnt[0];
+    out4[4 * i + 3] = t.scal[SC_FALLBACK];
+}
+
+int cohort_collect(const Cohort& c, const TreeDev* trees, int* out4, cudaStream_t st) {
+    cohort_collect_kernel<<<1, 32, 0, st>>>(c, trees, out4);
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
+}
+
+// u.level = the level that holds the user's final beams, u.row0 = the record index the user's result is written to
+__global__ void __launch_bounds__(64)
+cohort_results_kernel(Cohort c, const TreeDev* __restrict__ trees, int K, int sort, int* __restrict__ tokens,
+                      float* __restrict__ scores, int* __restrict__ counts) {
+    const UserCtx& u = c.u[blockIdx.x];
+    const TreeDev t = trees[u.tree];
+    const long long o = u.row0;
+    if (sort) {
+        tree_sort_level_body(t, u.level);
+        __syncthreads();
+    }
+    const int n = t.cnt[u.level] < K ? t.cnt[u.level] : K;
+    for (int i = threadIdx.x; i < K * MAX_NEW; i += blockDim.x) {
+        const int b = i / MAX_NEW, k = i - b * MAX_NEW;
+        tokens[(o * K + b) * MAX_NEW + k] = b < n ? t.gen[L_IDX(u.level, b) * MAX_NEW + k] : 0;
+    }
+    for (int b = threadIdx.x; b < K; b += blockDim.x) scores[o * K + b] = b < n ? t.score[L_IDX(u.level, b)] : -INFINITY;
+    if (threadIdx.x == 0 && counts) counts[o] = n;
+}
+
+int cohort_results(const Cohort& c, const TreeDev* trees, int K, bool sort, int* tokens, float* scores, int* counts,
+                   cudaStream_t st) {
+    ATS_CHECK_ARG(c.n >= 1 && c.n <= MAX_USERS, "cohort of %d users", c.n);
+    cohort_results_kernel<<<c.n, 64, 0, st>>>(c, trees, K, sort ? 1 : 0, tokens, scores, counts);
     ATS_LAUNCH_CHECK();
     return ATS_OK;
 }

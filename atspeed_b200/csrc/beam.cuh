@@ -60,6 +60,7 @@ enum { SC_P = 0, SC_GEN0 = 1, SC_FIRST = 2, SC_ACC = 3, SC_NMATCH = 4, SC_MISS =
 // Forward batch (one per model invocation) + logits-row selection, device arrays.
 struct BatchDev {
     int* tok; int* pos; int* slot; int* prefix_len; uint32_t* vis;   // [T_max] ([T_max][VIS_WORDS])
+    int* tok_user;    // [T_max] cohort forwards: which user of the cohort each token belongs to
     int* rows_idx;    // [R_max] batch index of each logits row
     int* row_node;    // [R_max] trie node of each logits row (-1 = padding row)
 };
@@ -94,6 +95,41 @@ int tree_select(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int le
 int tree_verify_strict(const TreeDev& t, const TreeGeom& g, const TrieCSR& trie, int draft_len, int root_rows,
                        const int* cand_tok, const int* cand_edge, const float* cand_logp, const int* cand_cnt, int P,
                        cudaStream_t st);
+
+// ---- cohort: several users' searches advanced by the same launches (cohort.cu) --------------------------------------
+// What one launch does for one user; passed by value inside `Cohort` (kernel parameter, no H2D copy per launch).
+struct UserCtx {
+    int tree;              // index of the user's TreeDev in the session's device array
+    int P;                 // prompt length
+    int tok0, T;           // the user's token range in the forward batch
+    int row0, R;           // the user's logits-row range
+    int level, width;      // select: expand `level` into level + 1 keeping `width` beams
+    int draft_len, root_rows;   // verify
+    int mode;              // post-forward action: 1 = select (one_step_beam_search), 2 = verify, 0 = none
+    int is_draft;          // sampling: the step belongs to the draft model (candidates are recorded, SITE_DRAFT noise)
+    BatchPlan plan;
+    unsigned long long stream_base;   // noise stream of (user, round)
+};
+struct Cohort {
+    int n;
+    UserCtx u[MAX_USERS];
+};
+int cohort_begin(const Cohort& c, const TreeDev* trees, cudaStream_t st);
+int cohort_build_batch(const Cohort& c, const TreeDev* trees, const BatchDev& b, const TreeGeom& g, const int* prompts,
+                       int prompt_stride, cudaStream_t st);
+// select / verify for every user of the cohort whose mode asks for it; candidates are read from cand_* rows
+// [row0, row0 + R) of each user with row stride B
+int cohort_select(const Cohort& c, const TreeDev* trees, const TreeGeom& g, const TrieCSR& trie, int B, const int* cand_tok,
+                  const int* cand_edge, const float* cand_logp, const int* cand_cnt, bool sampling, const SampleCfg& sc,
+                  cudaStream_t st);
+int cohort_verify(const Cohort& c, const TreeDev* trees, const TreeGeom& g, const TrieCSR& trie, int B, const int* cand_tok,
+                  const int* cand_edge, const float* cand_logp, const int* cand_cnt, bool sampling, const SampleCfg& sc,
+                  cudaStream_t st);
+// pack what the host needs after a verify: out[i] = {n_matches, miss_n, beams, fallbacks} of user i
+int cohort_collect(const Cohort& c, const TreeDev* trees, int* out4, cudaStream_t st);
+// final beams of every user (sorted by score first when `sort`): tokens [n][K][MAX_NEW], scores [n][K], counts [n]
+int cohort_results(const Cohort& c, const TreeDev* trees, int K, bool sort, int* tokens, float* scores, int* counts,
+                   cudaStream_t st);
 
 // ---- AtSpeed-R ----
 // sampling form of tree_select: N samples without replacement from softmax(logp / T + parent score) over the rows'

@@ -200,14 +200,14 @@ __global__ void qkv_rope_append_kernel(const float* __restrict__ part, SplitMap 
                                        int head_dim, const float* __restrict__ rope_cos,
                                        const float* __restrict__ rope_sin, int max_pos,
                                        __nv_bfloat16* __restrict__ qbuf, __nv_bfloat16* __restrict__ kcache,
-                                       __nv_bfloat16* __restrict__ vcache) {
+                                       __nv_bfloat16* __restrict__ vcache, const int* __restrict__ tok_user, CohortKV ckv) {
     pdl_launch_dependents();
     pdl_wait();
     const int t = blockIdx.x;
     const int HD = n_heads * head_dim, half = head_dim >> 1;
     int p = pos[t];
     p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
-    const long long srow = static_cast<long long>(slot[t]) * HD;
+    const long long srow = static_cast<long long>(slot[t]) * HD + (tok_user ? ckv.kv_off[tok_user[t]] : 0);
     const float* prow = part + static_cast<long long>(t) * ldp;
     const float* ct = rope_cos + static_cast<long long>(p) * half;
     const float* sn = rope_sin + static_cast<long long>(p) * half;
@@ -244,7 +244,7 @@ qkv_rope_append_vec_kernel(const float* __restrict__ part, SplitMap sm, long lon
                            const int* __restrict__ pos, const int* __restrict__ slot, int n_heads, int head_dim,
                            const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int max_pos,
                            __nv_bfloat16* __restrict__ qbuf, __nv_bfloat16* __restrict__ kcache,
-                           __nv_bfloat16* __restrict__ vcache) {
+                           __nv_bfloat16* __restrict__ vcache, const int* __restrict__ tok_user, CohortKV ckv) {
     pdl_launch_dependents();
     pdl_wait();
     const int t = blockIdx.x;
@@ -254,7 +254,7 @@ qkv_rope_append_vec_kernel(const float* __restrict__ part, SplitMap sm, long lon
     const int hd = e / q4, i = (e - hd * q4) * 4;
     int p = pos[t];
     p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
-    const long long srow = static_cast<long long>(slot[t]) * HD;
+    const long long srow = static_cast<long long>(slot[t]) * HD + (tok_user ? ckv.kv_off[tok_user[t]] : 0);
     const float* prow = part + static_cast<long long>(t) * ldp;
     const int c0 = hd * head_dim + i, c1 = c0 + half;
     float4 a[6];
@@ -304,11 +304,11 @@ int qkv_rope_append(const float* part, const SplitMap& sm, long long split_strid
         const int work = n_heads * (head_dim >> 3);
         dim3 grid(T, (work + 255) / 256);
         ATS_CUDA(launch_pdl(qkv_rope_append_vec_kernel, grid, dim3(256), 0, st, part, sm, split_stride, ldp, b.pos, b.slot,
-                            n_heads, head_dim, rope_cos, rope_sin, max_pos, qbuf, kcache, vcache));
+                            n_heads, head_dim, rope_cos, rope_sin, max_pos, qbuf, kcache, vcache, b.tok_user, b.ckv));
         return ATS_OK;
     }
     ATS_CUDA(launch_pdl(qkv_rope_append_kernel, dim3(T), dim3(256), 0, st, part, sm, split_stride, ldp, b.pos, b.slot,
-                        n_heads, head_dim, rope_cos, rope_sin, max_pos, qbuf, kcache, vcache));
+                        n_heads, head_dim, rope_cos, rope_sin, max_pos, qbuf, kcache, vcache, b.tok_user, b.ckv));
     return ATS_OK;
 }
 

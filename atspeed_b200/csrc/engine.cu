@@ -22,98 +22,13 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
-struct LayerRT {
-    GemmWeights qkv, o, gu, down;
-    const __nv_bfloat16 *ln1, *ln2;
-};
-
-struct ModelRT {
-    atspeed_model_desc d;
-    std::vector<LayerRT> layers;
-    GemmWeights lm;
-    int HD;
-    // activations (device, carved from the workspace)
-    __nv_bfloat16 *h, *x, *q, *a, *m, *xsel, *kv;
-    float *part, *logits;
-    // fp32 exact-parity mode (d.weights_f32): fp32 activations and KV cache instead of the bf16 ones above
-    bool f32;
-    float *fh, *fx, *fq, *fa, *fm, *fxsel, *fqkv, *fgu, *fkv;
-    int elem_bytes;       // bytes per KV / activation element (2 or 4)
-    long long kv_plane;   // elements per K (or V) plane of one layer
-    int ldl;              // logits row stride
-    int last_rows;
-    int forwards;
-};
-
-// host-side flags kept next to the pinned scalar mirror: is the root still the prompt, does the draft owe KV for
-// accepted tokens, which tree level holds the current beams
-enum { H_FIRST = 32, H_MISS = 33, H_LEVEL = 34 };
-
-struct Carver {
-    uint8_t* base;
-    size_t off;
-    template <typename T> T* take(size_t n) {
-        off = (off + 1023) & ~size_t(1023);
-        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-        off += n * sizeof(T);
-        return p;
-    }
-};
-
 }  // namespace atspeed
+
+#include "session.h"
 
 using namespace atspeed;
 
-struct atspeed_session {
-    atspeed_config cfg;
-    TreeGeom geom;
-    TrieCSR trie;
-    ModelRT tgt, dft;
-    bool has_draft;
-    TreeDev tree;
-    BatchDev batch;
-    int *cand_tok, *cand_edge, *cand_cnt;
-    float *cand_logp, *lse;
-    int* prompt_dev;
-    int T_max, R_max, S_max;
-    int P;
-    int num_sms;
-    int* pinned;          // pinned host scratch
-    long long launches;
-    // sampling mode (AtSpeed-R): noise key, user sequence number of the current search, round within it
-    unsigned long long seed, user_seq, next_user_seq;
-    int round;
-    int sample_B;
-    // optional per-launch CUDA-event timing (bench.py roofline / share-of-step); off by default
-    bool prof_on;
-    std::vector<cudaEvent_t> prof_ev;
-    std::vector<int> prof_cat;
-    int prof_n;
-    double prof_bytes[6];
-};
-
 namespace atspeed {
-
-enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ELEM = 2, CAT_TOPK = 3, CAT_BEAM = 4, CAT_GATHER = 5, CAT_COUNT = 6 };
-static constexpr int PROF_PAIRS = 16384;
-
-static inline void prof_begin(atspeed_session* s, int cat, double bytes, cudaStream_t st) {
-    if (!s->prof_on || s->prof_n >= PROF_PAIRS) return;
-    s->prof_cat[s->prof_n] = cat;
-    s->prof_bytes[cat] += bytes;
-    cudaEventRecord(s->prof_ev[2 * s->prof_n], st);
-}
-static inline void prof_end(atspeed_session* s, cudaStream_t st) {
-    if (!s->prof_on || s->prof_n >= PROF_PAIRS) return;
-    cudaEventRecord(s->prof_ev[2 * s->prof_n + 1], st);
-    s->prof_n++;
-}
-#define PROF(s, cat, bytes, call)              \
-    do {                                       \
-        prof_begin(s, cat, bytes, st);         \
-        ATS_TRY(call);                         \
-        prof_end(s, st);                       \
-    } while (0)
 
 static double gemm_bytes(const GemmWeights& g, int T) {
     double rows = 0;
@@ -146,7 +61,8 @@ static size_t part_elems(const atspeed_model_desc& d, int T_max, int num_sms) {
     return e;
 }
 
-static void carve_model(Carver& c, ModelRT& m, const atspeed_model_desc& d, int T_max, int R_max, int S_max, int num_sms) {
+static void carve_model(Carver& c, ModelRT& m, const atspeed_model_desc& d, int T_max, int R_max, int S_max, int num_sms,
+                        int n_users) {
     m.d = d;
     m.HD = d.n_heads * d.head_dim;
     m.ldl = (d.vocab + 7) & ~7;
@@ -165,7 +81,7 @@ static void carve_model(Carver& c, ModelRT& m, const atspeed_model_desc& d, int 
         m.fqkv = c.take<float>(static_cast<size_t>(T_max) * 3 * m.HD);
         m.fgu = c.take<float>(static_cast<size_t>(T_max) * 2 * d.mlp);
         m.logits = c.take<float>(static_cast<size_t>(R_max) * m.ldl);
-        m.fkv = c.take<float>(static_cast<size_t>(d.n_layers) * 2 * m.kv_plane);
+        m.fkv = c.take<float>(static_cast<size_t>(n_users) * d.n_layers * 2 * m.kv_plane);
         return;
     }
     m.h = c.take<__nv_bfloat16>(static_cast<size_t>(T_max) * d.hidden);
@@ -176,13 +92,10 @@ static void carve_model(Carver& c, ModelRT& m, const atspeed_model_desc& d, int 
     m.xsel = c.take<__nv_bfloat16>(static_cast<size_t>(R_max) * d.hidden);
     m.part = c.take<float>(part_elems(d, T_max, num_sms));
     m.logits = c.take<float>(static_cast<size_t>(R_max) * m.ldl);
-    m.kv = c.take<__nv_bfloat16>(static_cast<size_t>(d.n_layers) * 2 * m.kv_plane);
+    m.kv = c.take<__nv_bfloat16>(static_cast<size_t>(n_users) * d.n_layers * 2 * m.kv_plane);
 }
 
-static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_desc* target, const atspeed_model_desc* draft) {
-    carve_model(c, s->tgt, *target, s->T_max, s->R_max, s->S_max, s->num_sms);
-    if (draft) carve_model(c, s->dft, *draft, s->T_max, s->R_max, s->S_max, s->num_sms);
-    TreeDev& t = s->tree;
+static void carve_tree(Carver& c, TreeDev& t) {
     t.cnt = c.take<int>(MAX_LEVELS);
     t.tok = c.take<int>(MAX_LEVELS * MAX_BEAMS);
     t.parent = c.take<int>(MAX_LEVELS * MAX_BEAMS);
@@ -209,12 +122,25 @@ static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_des
     t.dcand_cnt = c.take<int>(MAX_LEVELS * MAX_BEAMS);
     t.lse_q = c.take<float>(MAX_LEVELS);
     t.tr_acc = c.take<int>(MAX_LEVELS * MAX_BEAMS);
+}
+
+static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_desc* target, const atspeed_model_desc* draft) {
+    const int U = s->max_users;
+    carve_model(c, s->tgt, *target, s->T_max, s->R_max, s->S_max, s->num_sms, U);
+    if (draft) carve_model(c, s->dft, *draft, s->T_max, s->R_max, s->S_max, s->num_sms, U);
+    s->kv_user_elems_tgt = static_cast<long long>(target->n_layers) * 2 * s->tgt.kv_plane;
+    s->kv_user_elems_dft = draft ? static_cast<long long>(draft->n_layers) * 2 * s->dft.kv_plane : 0;
+    s->trees_host.resize(U);
+    for (int u = 0; u < U; ++u) carve_tree(c, s->trees_host[u]);
+    s->tree = s->trees_host[0];                     // the single-user stages drive user slot 0
+    s->trees_dev = c.take<TreeDev>(U);
     BatchDev& b = s->batch;
     b.tok = c.take<int>(s->T_max);
     b.pos = c.take<int>(s->T_max);
     b.slot = c.take<int>(s->T_max);
     b.prefix_len = c.take<int>(s->T_max);
     b.vis = c.take<uint32_t>(static_cast<size_t>(s->T_max) * VIS_WORDS);
+    b.tok_user = c.take<int>(s->T_max);
     b.rows_idx = c.take<int>(s->R_max);
     b.row_node = c.take<int>(s->R_max);
     s->cand_tok = c.take<int>(static_cast<size_t>(s->R_max) * MAX_BEAMS);
@@ -222,7 +148,12 @@ static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_des
     s->cand_logp = c.take<float>(static_cast<size_t>(s->R_max) * MAX_BEAMS);
     s->cand_cnt = c.take<int>(s->R_max);
     s->lse = c.take<float>(s->R_max);
-    s->prompt_dev = c.take<int>(s->cfg.max_prompt);
+    s->prompts_dev = c.take<int>(static_cast<size_t>(U) * s->cfg.max_prompt);
+    s->prompt_dev = s->prompts_dev;
+    s->collect_dev = c.take<int>(U * 4);
+    s->res_tok_dev = c.take<int>(static_cast<size_t>(U) * MAX_K * MAX_NEW);
+    s->res_score_dev = c.take<float>(static_cast<size_t>(U) * MAX_K);
+    s->res_cnt_dev = c.take<int>(U);
 }
 
 static int check_cfg(const atspeed_model_desc* target, const atspeed_model_desc* draft, const atspeed_config* cfg) {
@@ -232,6 +163,9 @@ static int check_cfg(const atspeed_model_desc* target, const atspeed_model_desc*
     ATS_CHECK_ARG(cfg->max_new_tokens >= 1 && cfg->max_new_tokens <= MAX_NEW && cfg->max_new_tokens < MAX_LEVELS + 1,
                   "max_new_tokens=%d outside [1,%d]", cfg->max_new_tokens, MAX_LEVELS);
     ATS_CHECK_ARG(cfg->max_prompt >= 1, "max_prompt=%d", cfg->max_prompt);
+    ATS_CHECK_ARG(cfg->max_users >= 0 && cfg->max_users <= MAX_USERS, "max_users=%d outside [0,%d]", cfg->max_users, MAX_USERS);
+    if (cfg->max_users > 1)
+        ATS_CHECK_ARG(!target->weights_f32 && !(draft && draft->weights_f32), "cohort mode (max_users > 1) needs bf16 models");
     if (cfg->do_sample) {
         ATS_CHECK_ARG(cfg->top_k >= 1 && cfg->top_k <= MAX_BEAMS,
                       "do_sample needs generation_config.top_k in [1,%d] (transformers 4.41 default 50), got %d", MAX_BEAMS,
@@ -264,6 +198,8 @@ static void session_dims(atspeed_session* s) {
     s->T_max = T;
     s->geom.K = c.K; s->geom.N = c.N; s->geom.A_cap = c.max_new_tokens * c.K; s->geom.V = 0;
     s->R_max = c.K + (MAX_LEVELS - 1) * c.N + 1;
+    s->max_users = c.max_users > 1 ? c.max_users : 1;
+    if (s->max_users > 1) { s->T_max = 512; s->R_max = 512; }     // a cohort forward packs users up to the GEMM's token limit
     s->S_max = c.max_prompt + s->geom.A_cap + s->geom.lvl_off(MAX_LEVELS) + c.K;
 }
 
@@ -334,8 +270,8 @@ static int forward_f32(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T
 }
 
 // One forward of `m` over the batch in `b` (T tokens; attention scans KV slots [0, S)), logits for R rows.
-static int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, const int* rows_idx, int R,
-                   cudaStream_t st) {
+int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, const int* rows_idx, int R,
+            cudaStream_t st) {
     const atspeed_model_desc& d = m.d;
     ATS_CHECK_ARG(T >= 1 && T <= s->T_max, "forward: T=%d exceeds T_max=%d", T, s->T_max);
     ATS_CHECK_ARG(R >= 1 && R <= s->R_max, "forward: R=%d exceeds R_max=%d", R, s->R_max);
@@ -398,19 +334,19 @@ static int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, in
 
 static BatchDesc batch_desc(const atspeed_session* s) {
     BatchDesc b;
+    memset(&b, 0, sizeof(b));
     b.tok = s->batch.tok; b.pos = s->batch.pos; b.slot = s->batch.slot; b.prefix_len = s->batch.prefix_len;
     b.vis = s->batch.vis; b.vis_base = s->P; b.n_valid = nullptr;
     return b;
 }
 
-struct CandOut { int* tok; int* edge; float* logp; int* cnt; };
-static CandOut shared_cand(atspeed_session* s) { return CandOut{s->cand_tok, s->cand_edge, s->cand_logp, s->cand_cnt}; }
+CandOut shared_cand(atspeed_session* s) { return CandOut{s->cand_tok, s->cand_edge, s->cand_logp, s->cand_cnt}; }
 // the draft's step-`level` candidates are kept per level in sampling mode: verify needs q on them
 static CandOut draft_level_cand(atspeed_session* s, int level) {
     const size_t o = static_cast<size_t>(level) * MAX_BEAMS * MAX_BEAMS;
     return CandOut{s->tree.dcand_tok + o, s->tree.dcand_edge + o, s->tree.dcand_logp + o, s->tree.dcand_cnt + level * MAX_BEAMS};
 }
-static SampleCfg sample_cfg(const atspeed_session* s) {
+SampleCfg sample_cfg(const atspeed_session* s) {
     SampleCfg sc;
     sc.B = s->sample_B;
     sc.inv_temp = 1.0f / s->cfg.temperature;
@@ -419,7 +355,7 @@ static SampleCfg sample_cfg(const atspeed_session* s) {
     return sc;
 }
 
-static int run_topk(atspeed_session* s, ModelRT& m, int R, int B, const CandOut& o, cudaStream_t st) {
+int run_topk(atspeed_session* s, ModelRT& m, int R, int B, const CandOut& o, cudaStream_t st) {
     PROF(s, CAT_TOPK, static_cast<double>(R) * m.d.vocab * 4.0,
          mask_logsoftmax_topk(m.logits, 0, R, m.d.vocab, m.ldl, s->batch.row_node, nullptr, s->trie, B, o.tok, o.edge,
                               o.logp, o.cnt, s->lse, st));
@@ -518,12 +454,26 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
     int r = build_model(s->tgt, sms);
     if (r == ATS_OK && draft) r = build_model(s->dft, sms);
     if (r != ATS_OK) { delete s; return r; }
+    if (cudaMemcpy(s->trees_dev, s->trees_host.data(), sizeof(TreeDev) * s->max_users, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("uploading the per-user tree table failed");
+        delete s;
+        return ATS_ERR_CUDA;
+    }
     if (cudaMallocHost(&s->pinned, 64 * sizeof(int)) != cudaSuccess) {
         set_error("cudaMallocHost failed");
         delete s;
         return ATS_ERR_CUDA;
     }
     memset(s->pinned, 0, 64 * sizeof(int));
+    s->cohort_pinned = nullptr;
+    if (s->max_users > 1 &&
+        cudaMallocHost(&s->cohort_pinned, sizeof(int) * (MAX_USERS * 4 + MAX_USERS * MAX_K * MAX_NEW + MAX_USERS) +
+                                              sizeof(float) * MAX_USERS * MAX_K) != cudaSuccess) {
+        set_error("cudaMallocHost failed");
+        cudaFreeHost(s->pinned);
+        delete s;
+        return ATS_ERR_CUDA;
+    }
     s->P = 0;
     s->seed = cfg->seed; s->user_seq = 0; s->next_user_seq = 0; s->round = 0;
     {
@@ -542,6 +492,7 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
 int atspeed_session_destroy(atspeed_session* s) {
     if (!s) return ATS_OK;
     if (s->pinned) cudaFreeHost(s->pinned);
+    if (s->cohort_pinned) cudaFreeHost(s->cohort_pinned);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     delete s;
     return ATS_OK;
@@ -875,6 +826,7 @@ int atspeed_session_forward_raw(atspeed_session* s, int32_t model, const int32_t
     ATS_CHECK_ARG(s && tok && pos && slot && prefix_len && vis && rows_idx, "null argument");
     ATS_CHECK_ARG(model == 0 || (model == 1 && s->has_draft), "model=%d", model);
     BatchDesc b;
+    memset(&b, 0, sizeof(b));
     b.tok = tok; b.pos = pos; b.slot = slot; b.prefix_len = prefix_len; b.vis = vis; b.vis_base = vis_base; b.n_valid = nullptr;
     return forward(s, model == 0 ? s->tgt : s->dft, b, T, S, rows_idx, R, static_cast<cudaStream_t>(stream));
 }

@@ -46,6 +46,17 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, float* o
 bool pdl_enabled();   // ATSPEED_PDL=0 disables programmatic dependent launch (debugging)
 
 // ---- elementwise.cu -----------------------------------------------------------------------------
+// Several users' trees in ONE forward ("cohort", cohort.cu): every user keeps its own KV cache, prompt length and
+// attention extent; tokens of user i occupy batch positions [tok0[i], tok0[i] + T[i]).  n == 0: single-user forward.
+constexpr int MAX_USERS = 16;
+struct CohortKV {
+    int n;
+    long long kv_off[MAX_USERS];   // element offset of the user's cache inside the model's KV allocation
+    int S[MAX_USERS];              // KV slots the user's tokens may attend
+    int vis_base[MAX_USERS];       // = the user's prompt length
+    int tok0[MAX_USERS], T[MAX_USERS];
+};
+
 // Forward-batch descriptor, all device arrays of length >= T (built by beam.cu kernels).
 struct BatchDesc {
     const int* tok;          // token ids
@@ -55,6 +66,8 @@ struct BatchDesc {
     const uint32_t* vis;     // [T][VIS_WORDS] bit j: token attends slot vis_base + j
     int vis_base;            // first slot covered by the bit masks (= prompt length)
     const int* n_valid;      // device scalar: tokens >= *n_valid are padding (may be nullptr = all valid)
+    const int* tok_user;     // cohort forward: user index (into ckv) of each token; nullptr otherwise
+    CohortKV ckv;
 };
 int embed_rows(const __nv_bfloat16* table, const int* tok, int T, int hidden, int vocab, __nv_bfloat16* h,
                cudaStream_t st);
@@ -114,5 +127,15 @@ int kv_gather_rows(void* base, long long plane_stride, int n_planes, int row_byt
 int kv_gather_rows_oop(const void* src_base, void* dst_base, long long src_plane_stride, long long dst_plane_stride,
                        int n_planes, int row_bytes, const int* src, const int* dst, const int* n_rows_dev,
                        int max_rows, cudaStream_t st);
+// the same for several users in one launch: user i moves rows inside base + byte_off[i] using its own lists
+struct GatherCohort {
+    int n;
+    long long byte_off[MAX_USERS];
+    const int* src[MAX_USERS];
+    const int* dst[MAX_USERS];
+    const int* n_rows[MAX_USERS];
+};
+int kv_gather_rows_cohort(void* base, long long plane_stride, int n_planes, int row_bytes, const GatherCohort& gc,
+                          int max_rows, cudaStream_t st);
 
 }  // namespace atspeed

@@ -76,6 +76,56 @@ int kv_gather_rows_oop(const void* src_base, void* dst_base, long long src_plane
     return ATS_OK;
 }
 
+__global__ void __launch_bounds__(32)
+kv_gather_cohort_kernel(uint8_t* __restrict__ base, long long plane_stride, int row_bytes, GatherCohort gc) {
+    extern __shared__ __align__(128) uint8_t buf[];
+    __shared__ __align__(8) uint64_t bar;
+    const int i = blockIdx.x, plane = blockIdx.y, u = blockIdx.z;
+    if (i >= *gc.n_rows[u]) return;
+    if (threadIdx.x != 0) return;
+    uint8_t* ub = base + gc.byte_off[u] + plane * plane_stride;
+    const uint8_t* src = ub + static_cast<long long>(gc.src[u][i]) * row_bytes;
+    uint8_t* dst = ub + static_cast<long long>(gc.dst[u][i]) * row_bytes;
+    const uint32_t bar_a = smem_u32(&bar), buf_a = smem_u32(buf);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t phase = 0;
+    for (int off = 0; off < row_bytes; off += GATHER_CHUNK) {
+        const uint32_t n = static_cast<uint32_t>(row_bytes - off < GATHER_CHUNK ? row_bytes - off : GATHER_CHUNK);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_a),
+                     "l"(src + off), "r"(n), "r"(bar_a)
+                     : "memory");
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "W_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra D_%=;\n\t"
+            "bra W_%=;\n\t"
+            "D_%=:\n\t"
+            "}" ::"r"(bar_a),
+            "r"(phase)
+            : "memory");
+        phase ^= 1;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(buf_a), "r"(n)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+int kv_gather_rows_cohort(void* base, long long plane_stride, int n_planes, int row_bytes, const GatherCohort& gc,
+                          int max_rows, cudaStream_t st) {
+    ATS_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0, "kv_gather: row_bytes=%d must be a multiple of 16", row_bytes);
+    ATS_CHECK_ARG(gc.n >= 1 && gc.n <= MAX_USERS && max_rows >= 1 && n_planes >= 1, "kv_gather: users=%d rows=%d", gc.n, max_rows);
+    const int smem = row_bytes < GATHER_CHUNK ? row_bytes : GATHER_CHUNK;
+    dim3 grid(max_rows, n_planes, gc.n);
+    kv_gather_cohort_kernel<<<grid, 32, smem, st>>>(static_cast<uint8_t*>(base), plane_stride, row_bytes, gc);
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
+}
+
 int kv_gather_rows(void* base, long long plane_stride, int n_planes, int row_bytes, const int* src, const int* dst,
                    const int* n_rows_dev, int max_rows, cudaStream_t st) {
     return kv_gather_rows_oop(base, base, plane_stride, plane_stride, n_planes, row_bytes, src, dst, n_rows_dev,

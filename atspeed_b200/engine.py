@@ -143,7 +143,7 @@ class Session:
 
     def __init__(self, target: DeviceModel, draft: Optional[DeviceModel], trie: DeviceTrie, K: int, N: int,
                  max_new_tokens: int = 4, max_prompt: Optional[int] = None, do_sample: bool = False,
-                 top_k: Optional[int] = None, temperature: float = 1.0, seed: int = 0):
+                 top_k: Optional[int] = None, temperature: float = 1.0, seed: int = 0, max_users: int = 1):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.AtSpeedError("atspeed_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -156,7 +156,9 @@ class Session:
         self.do_sample = bool(do_sample)
         cfg = _lib.Config(K, N, max_new_tokens, max_prompt,
                           torch.cuda.get_device_properties(self.device).multi_processor_count,
-                          1 if do_sample else 0, int(top_k or 0), float(temperature or 1.0), int(seed) & (2 ** 64 - 1))
+                          1 if do_sample else 0, int(top_k or 0), float(temperature or 1.0), int(seed) & (2 ** 64 - 1),
+                          int(max_users))
+        self.max_users = int(max_users)
         self.cfg = cfg
         nbytes = C.c_size_t(0)
         dptr = C.byref(draft.desc) if draft is not None else None
@@ -206,6 +208,45 @@ class Session:
             _lib.check(self.lib.atspeed_bssd(self.handle, ptr, P, gamma, self._tok, self._sc, C.byref(self._cnt),
                                              C.byref(st), self._stream()))
         return self._collect(st)
+
+    def bssd_batch(self, prompts: Sequence[Sequence[int]], gamma: int) -> List[Dict]:
+        """Cohort mode (Session(max_users > 1)): speculative beam search for all `prompts`, up to max_users of them in
+        flight at a time with their trees packed into shared forwards.  Returns one dict per prompt, in order."""
+        n = len(prompts)
+        lens = np.asarray([len(p) for p in prompts], dtype=np.int32)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32) for p in prompts]))
+        toks = np.zeros((n, self.K, self.L), dtype=np.int32)
+        scores = np.zeros((n, self.K), dtype=np.float32)
+        cnt = np.zeros(n, dtype=np.int32)
+        stats = (_lib.Stats * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.atspeed_bssd_batch(self.handle, n, flat.ctypes.data_as(_lib.c_i32p),
+                                                   lens.ctypes.data_as(_lib.c_i32p), gamma, toks.ctypes.data_as(_lib.c_i32p),
+                                                   scores.ctypes.data_as(_lib.c_f32p), cnt.ctypes.data_as(_lib.c_i32p),
+                                                   C.cast(stats, C.c_void_p), self._stream()))
+        out = []
+        for i in range(n):
+            st = stats[i]
+            out.append({"tokens": toks[i, : cnt[i]].copy(), "scores": scores[i, : cnt[i]].copy(), "n_run": st.n_run,
+                        "total_accept_steps": st.total_accept_steps,
+                        "accept_steps": [st.accept_steps[r] for r in range(min(st.n_run, 8))],
+                        "target_forwards": st.target_forwards, "draft_forwards": st.draft_forwards,
+                        "kernel_launches": st.kernel_launches})
+        return out
+
+    def bssd_batch_device(self, prompts_dev: torch.Tensor, lens: Sequence[int], gamma: int, tokens_dev: torch.Tensor,
+                          scores_dev: torch.Tensor) -> List[Dict]:
+        """Cohort mode with the concatenated prompts (int32 CUDA tensor) and the results (int32 [n,K,6], fp32 [n,K] CUDA
+        tensors) resident in HBM."""
+        n = len(lens)
+        la = np.asarray(lens, dtype=np.int32)
+        stats = (_lib.Stats * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.atspeed_bssd_batch_device(self.handle, n, prompts_dev.data_ptr(), la.ctypes.data_as(_lib.c_i32p),
+                                                          gamma, tokens_dev.data_ptr(), scores_dev.data_ptr(),
+                                                          C.cast(stats, C.c_void_p), self._stream()))
+        return [{"n_run": st.n_run, "total_accept_steps": st.total_accept_steps, "target_forwards": st.target_forwards,
+                 "draft_forwards": st.draft_forwards, "kernel_launches": st.kernel_launches} for st in stats]
 
     def bssd_device(self, prompt_dev: torch.Tensor, gamma: int, tokens_dev: torch.Tensor, scores_dev: torch.Tensor) -> Dict:
         """Prompt (int32 CUDA tensor) and results (int32 [K,6], fp32 [K] CUDA tensors) stay in HBM."""

@@ -47,7 +47,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="atspeed", choices=["atspeed", "reference"])
-    ap.add_argument("--users-per-step", type=int, default=8)
+    ap.add_argument("--users-per-step", type=int, default=32)
+    ap.add_argument("--cohort", type=int, default=8,
+                    help="users whose trees share each forward (atspeed_bssd_batch; <= 512 tokens per forward); 1 = one "
+                         "search per forward as the reference")
     ap.add_argument("--dataset", default="beauty")
     ap.add_argument("--K", type=int, default=10)
     ap.add_argument("--N", type=int, default=40)
@@ -56,7 +59,7 @@ def parse():
     ap.add_argument("--draft", default="68m")
     ap.add_argument("--constraint", default="strict", choices=["strict", "positional"])
     ap.add_argument("--profile-users", type=int, default=4)
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=4,
                     help="independent searches in flight per GPU (each its own session + CUDA stream + host thread): one "
                          "user's latency-bound draft / verify phases overlap another's weight-streaming target forward")
     ap.add_argument("--do-sample", action="store_true", help="AtSpeed-R relaxed acceptance (configs[2]) instead of AtSpeed-S")
@@ -70,7 +73,9 @@ def workload_name(a):
     mode = "AtSpeed-R relaxed acceptance (do_sample, top_k=50, T=1)" if a.do_sample else "AtSpeed-S strict top-K verify"
     return (f"LLaMA-{a.target}-shape target + LLaMA-{a.draft}-shape draft, {mode}, "
             f"{a.dataset} test users, {a.constraint} constraint, K={a.K} N={a.N} gamma={a.gamma} max_new_tokens=4, "
-            f"{a.users_per_step} users/step/GPU, batch 1 per search (as the reference), {a.lanes} searches in flight per GPU")
+            f"{a.users_per_step} users/step/GPU, " +
+            (f"cohorts of up to {a.cohort} users per forward (<=512 tokens), {a.lanes} cohorts in flight per GPU"
+             if a.cohort > 1 else f"batch 1 per search (as the reference), {a.lanes} searches in flight per GPU"))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -237,6 +242,8 @@ def atspeed_arm(a, rank, world, local_rank):
     dtrie = DeviceTrie(csr, dev)
     skw = dict(do_sample=True, top_k=50, temperature=1.0, seed=2025) if a.do_sample else {}
     n_lanes = max(1, a.lanes)
+    if a.cohort > 1:
+        skw["max_users"] = a.cohort
     lanes = [Session(tdm, ddm, dtrie, a.K, a.N, 4, **skw) for _ in range(n_lanes)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
     sess = lanes[0]
@@ -259,17 +266,16 @@ def atspeed_arm(a, rank, world, local_rank):
 
     def on_lanes(fn, s):
         """Users of step s dealt round-robin to the lanes; every lane runs on its own stream from its own thread (the C
-        calls release the GIL); the default stream is fenced before and after with events."""
+        calls release the GIL); the default stream is fenced before and after with events.  fn(session, lane, indices)
+        handles the lane's users (indices into the step's user list) and returns a list."""
         start = torch.cuda.Event()
         start.record()
 
         def work(l):
             torch.cuda.set_device(dev)
-            out = []
             with torch.cuda.stream(streams[l]):
                 streams[l].wait_event(start)
-                for i in range(l, len(step_users[s]), n_lanes):
-                    out.append(fn(lanes[l], i, step_users[s][i]))
+                out = fn(lanes[l], l, list(range(l, len(step_users[s]), n_lanes)))
                 done = torch.cuda.Event()
                 done.record()
             return out, done
@@ -279,20 +285,48 @@ def atspeed_arm(a, rank, world, local_rank):
             torch.cuda.current_stream(dev).wait_event(done)
         return [x for out, _ in res for x in out]
 
+    # cohort mode: each lane's users of a step as ONE concatenated device tensor (inputs resident in HBM)
+    cat_dev = {}
+    if a.cohort > 1:
+        for s_ in range(n_steps_total):
+            for l in range(n_lanes):
+                us = [step_users[s_][i] for i in range(l, U, n_lanes)]
+                cat_dev[(s_, l)] = (torch.cat([prompts_dev[u] for u in us]), [len(prompts_host[u]) for u in us])
+    lane_tok = [torch.zeros((U + n_lanes - 1) // n_lanes, a.K, _lib.MAX_NEW, dtype=torch.int32, device=dev) for _ in range(n_lanes)]
+    lane_sc = [torch.zeros((U + n_lanes - 1) // n_lanes, a.K, dtype=torch.float32, device=dev) for _ in range(n_lanes)]
+
     def step_device(s):
-        sts = on_lanes(lambda ss, i, u: ss.bssd_device(prompts_dev[u], a.gamma, tok_dev[i], sc_dev[i]), s)
+        if a.cohort > 1:
+            def fn(ss, l, idx):
+                cat, lens = cat_dev[(s, l)]
+                sts = ss.bssd_batch_device(cat, lens, a.gamma, lane_tok[l], lane_sc[l])
+                tok_dev[idx] = lane_tok[l][: len(idx)]
+                return sts
+        else:
+            def fn(ss, l, idx):
+                return [ss.bssd_device(prompts_dev[step_users[s][i]], a.gamma, tok_dev[i], sc_dev[i]) for i in idx]
+        sts = on_lanes(fn, s)
         if world > 1:   # the one collective of the path: ranked lists of every rank, over NVLink
             dist.all_gather(gathered, tok_dev)
         return (sum(st["kernel_launches"] for st in sts), sum(st["total_accept_steps"] for st in sts),
                 sum(st["n_run"] for st in sts))
 
     def step_host(s):
-        def one(ss, i, u):
-            t0 = time.perf_counter()
-            out = ss.bssd(prompts_host[u], a.gamma)
-            return time.perf_counter() - t0, out["tokens"]
-
-        res = on_lanes(one, s)
+        if a.cohort > 1:
+            def fn(ss, l, idx):
+                t0 = time.perf_counter()
+                outs = ss.bssd_batch([prompts_host[step_users[s][i]] for i in idx], a.gamma)
+                dt = time.perf_counter() - t0
+                return [(dt, o["tokens"]) for o in outs]          # every user of the call waits for the whole cohort
+        else:
+            def fn(ss, l, idx):
+                out = []
+                for i in idx:
+                    t0 = time.perf_counter()
+                    o = ss.bssd(prompts_host[step_users[s][i]], a.gamma)
+                    out.append((time.perf_counter() - t0, o["tokens"]))
+                return out
+        res = on_lanes(fn, s)
         if world > 1:
             t = torch.from_numpy(np.stack([x[1] for x in res])).to(dev)
             dist.all_gather([torch.empty_like(t) for _ in range(world)], t)
@@ -331,7 +365,10 @@ def atspeed_arm(a, rank, world, local_rank):
     lat1 = []
     for u in step_users[a.warmup][: min(U, 8)]:
         t0 = time.perf_counter()
-        sess.bssd(prompts_host[u], a.gamma)
+        if a.cohort > 1:
+            sess.bssd_batch([prompts_host[u]], a.gamma)
+        else:
+            sess.bssd(prompts_host[u], a.gamma)
         lat1.append(time.perf_counter() - t0)
     h2d = int(np.mean([sum(len(prompts_host[u]) * 4 for u in step_users[s]) for s in range(a.warmup, n_steps_total)]))
     d2h = U * (a.K * 4 * 4 + a.K * 4) + int(round(runs / max(a.steps, 1))) * 64
@@ -339,8 +376,12 @@ def atspeed_arm(a, rank, world, local_rank):
     roofline, groups = None, None
     if rank == 0:
         sess.profile(True)
-        for u in step_users[a.warmup][: max(1, a.profile_users)]:
-            sess.bssd_device(prompts_dev[u], a.gamma, tok_dev[0], sc_dev[0])
+        if a.cohort > 1:
+            a.profile_users = len(cat_dev[(a.warmup, 0)][1])
+            sess.bssd_batch_device(*cat_dev[(a.warmup, 0)], a.gamma, lane_tok[0], lane_sc[0])
+        else:
+            for u in step_users[a.warmup][: max(1, a.profile_users)]:
+                sess.bssd_device(prompts_dev[u], a.gamma, tok_dev[0], sc_dev[0])
         prof = sess.profile_read()
         sess.profile(False)
         tot = sum(v["ms"] for v in prof.values())

@@ -82,6 +82,11 @@ typedef struct atspeed_config {
     int32_t top_k;            /* TopKLogitsWarper k (transformers 4.41 default 50); 1..64 required when do_sample */
     float temperature;        /* TemperatureLogitsWarper; 1.0 = off */
     uint64_t seed;            /* key of the counter-based noise (see atspeed_session_set_seed) */
+    /* Cohort mode (atspeed_bssd_batch): up to max_users (1..16) independent searches advance together, their trees packed
+     * into the same forwards (<= 512 tokens each) so the weights are streamed once per step for all of them.  0 or 1 =
+     * single-user session.  Each user keeps its own KV caches and beam tree; results per user are those of a
+     * single-user session.  bf16 models only. */
+    int32_t max_users;
 } atspeed_config;
 
 typedef struct atspeed_session atspeed_session;
@@ -143,6 +148,25 @@ typedef struct atspeed_stats {
  * (the 4-byte n_matches) and once for the result. */
 int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int32_t gamma, int32_t* tokens_host,
                  float* scores_host, int32_t* count, atspeed_stats* stats, void* stream);
+
+/* BSSD for n_users prompts at once (cohort mode, cfg.max_users > 1): a host-side scheduler keeps up to max_users
+ * searches in flight, batches every draft step / target verify forward / final step of the users that are ready into one
+ * forward of at most 512 tokens, and runs kernels (a), (b), (c) for all of them in single launches.  Users finish in
+ * 1..4 rounds independently; a finished user's slot is refilled from the remaining prompts.
+ *   prompts_host : int32, all prompts concatenated;  prompt_lens int32[n_users]
+ *   tokens_host  : int32[n_users][K * max_new_tokens], scores_host float[n_users][K], counts int32[n_users]
+ *   stats        : atspeed_stats[n_users] (may be NULL)
+ * One stream synchronisation per scheduler step (the accepted lengths of the users verified in it). */
+int atspeed_bssd_batch(atspeed_session* s, int32_t n_users, const int32_t* prompts_host, const int32_t* prompt_lens,
+                       int32_t gamma, int32_t* tokens_host, float* scores_host, int32_t* counts, atspeed_stats* stats,
+                       void* stream);
+
+/* The same with the concatenated prompts resident in HBM (DEVICE int32; lengths stay on the host: they size the
+ * forwards) and the results left there: tokens_dev int32[n_users][K][6], scores_dev float[n_users][K], record i = prompt
+ * i.  This is what bench.py times as `value`. */
+int atspeed_bssd_batch_device(atspeed_session* s, int32_t n_users, const int32_t* prompts_dev,
+                              const int32_t* prompt_lens_host, int32_t gamma, int32_t* tokens_dev, float* scores_dev,
+                              atspeed_stats* stats, void* stream);
 
 /* Same loop with the prompt already resident in HBM (DEVICE int32[P]) and the result left on the device:
  * tokens_dev int32[K][6] (generated suffix per beam, row stride 6 = ATSPEED_MAX_NEW_TOKENS), scores_dev float[K].
