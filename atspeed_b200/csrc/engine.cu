@@ -293,6 +293,13 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
     ATS_TRY(gemm_make_xmap(&xm_a, m.a, T, m.HD));
     ATS_TRY(gemm_make_xmap(&xm_m, m.m, T, d.mlp));
     ATS_TRY(gemm_make_xmap(&xm_sel, m.xsel, R, d.hidden));
+    const int c_qkv = 3 * m.HD, c_gu = 2 * d.mlp;
+    OMap om_qkv, om_o, om_gu, om_down, om_lm;
+    ATS_TRY(gemm_make_omap(&om_qkv, L0.qkv, m.part, c_qkv, static_cast<long long>(T) * c_qkv, T, p_qkv.max_slices));
+    ATS_TRY(gemm_make_omap(&om_o, L0.o, m.part, d.hidden, static_cast<long long>(T) * d.hidden, T, p_o.max_slices));
+    ATS_TRY(gemm_make_omap(&om_gu, L0.gu, m.part, c_gu, static_cast<long long>(T) * c_gu, T, p_gu.max_slices));
+    ATS_TRY(gemm_make_omap(&om_down, L0.down, m.part, d.hidden, static_cast<long long>(T) * d.hidden, T, p_down.max_slices));
+    ATS_TRY(gemm_make_omap(&om_lm, m.lm, m.logits, m.ldl, 0, R, 1));
     PROF(s, CAT_ELEM, 0, embed_rows(embed, b.tok, T, d.hidden, d.vocab, m.h, st));
     PROF(s, CAT_ELEM, 0, rmsnorm_rows(m.h, m.layers[0].ln1, T, d.hidden, d.rms_eps, m.x, nullptr, st));
     s->launches += 2;
@@ -300,23 +307,21 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
         LayerRT& L = m.layers[l];
         __nv_bfloat16* kc = m.kv + static_cast<long long>(l) * 2 * m.kv_plane;
         __nv_bfloat16* vc = kc + m.kv_plane;
-        const int c_qkv = 3 * m.HD, c_gu = 2 * d.mlp;
-        PROF(s, CAT_GEMM, gemm_bytes(L.qkv, T),
-             gemm_wx(L.qkv, xm_x, p_qkv, m.part, c_qkv, static_cast<long long>(T) * c_qkv, st));
+        PROF(s, CAT_GEMM, gemm_bytes(L.qkv, T), gemm_wx(L.qkv, xm_x, p_qkv, om_qkv, st));
         PROF(s, CAT_ELEM, 0,
              qkv_rope_append(m.part, sm_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
                              d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
         PROF(s, CAT_ATTN, 0, tree_attention(m.q, kc, vc, b, T, S, d.n_heads, d.head_dim, m.a, st));
         PROF(s, CAT_GEMM, gemm_bytes(L.o, T),
-             gemm_wx(L.o, xm_a, p_o, m.part, d.hidden, static_cast<long long>(T) * d.hidden, st));
+             gemm_wx(L.o, xm_a, p_o, om_o, st));
         PROF(s, CAT_ELEM, 0,
              residual_rmsnorm(m.h, m.part, sm_o, static_cast<long long>(T) * d.hidden, d.hidden, L.ln2, T, d.hidden,
                               d.rms_eps, m.x, st));
         PROF(s, CAT_GEMM, gemm_bytes(L.gu, T),
-             gemm_wx(L.gu, xm_x, p_gu, m.part, c_gu, static_cast<long long>(T) * c_gu, st));
+             gemm_wx(L.gu, xm_x, p_gu, om_gu, st));
         PROF(s, CAT_ELEM, 0, silu_mul(m.part, sm_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
         PROF(s, CAT_GEMM, gemm_bytes(L.down, T),
-             gemm_wx(L.down, xm_m, p_down, m.part, d.hidden, static_cast<long long>(T) * d.hidden, st));
+             gemm_wx(L.down, xm_m, p_down, om_down, st));
         const __nv_bfloat16* next_ln = l + 1 < d.n_layers ? m.layers[l + 1].ln1 : nullptr;
         PROF(s, CAT_ELEM, 0,
              residual_rmsnorm(m.h, m.part, sm_down, static_cast<long long>(T) * d.hidden, d.hidden, next_ln, T,
@@ -325,7 +330,7 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
     }
     PROF(s, CAT_ELEM, 0,
          rmsnorm_rows(m.h, static_cast<const __nv_bfloat16*>(d.final_norm), R, d.hidden, d.rms_eps, m.xsel, rows_idx, st));
-    PROF(s, CAT_GEMM, gemm_bytes(m.lm, R), gemm_wx(m.lm, xm_sel, p_lm, m.logits, m.ldl, 0, st));
+    PROF(s, CAT_GEMM, gemm_bytes(m.lm, R), gemm_wx(m.lm, xm_sel, p_lm, om_lm, st));
     s->launches += 2;
     m.last_rows = R;
     m.forwards++;
@@ -915,7 +920,9 @@ int atspeed_gemm_bf16(const void* x, int32_t T, int32_t K, const void* w0, int32
     const int cols = g.colbase[g.n - 1] + g.rows[g.n - 1];
     ATS_CHECK_ARG(!out || ldo >= cols, "ldo=%d < total columns %d", ldo, cols);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ATS_TRY(gemm_wx(g, xm, pl, scratch, cols, static_cast<long long>(T) * cols, st));
+    OMap om;
+    ATS_TRY(gemm_make_omap(&om, g, scratch, cols, static_cast<long long>(T) * cols, T, pl.max_slices));
+    ATS_TRY(gemm_wx(g, xm, pl, om, st));
     if (out) ATS_TRY(reduce_slices(scratch, gemm_split_map(g, pl), static_cast<long long>(T) * cols, cols, T, cols, out, ldo, st));
     return ATS_OK;
 }

@@ -30,6 +30,7 @@ static constexpr int UMMA_K = 16;
 static constexpr int GEMM_THREADS = 192;
 static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 static constexpr int MAX_STAGES = 12;
+static constexpr int OUT_STAGE_BYTES = 2 * 16 * 128 * 4;   // epilogue staging: two [16 tokens][128 features] fp32 tiles
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -59,6 +60,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// smem [1][16][128] fp32 box -> global (coordinates: feature, token, slice); bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -119,6 +127,8 @@ struct GemmParams {
     int tmem_cols, acc_stride;
     int n_bufs, buf_stride;   // accumulator double buffering in TMEM: segment s uses buffer s % n_bufs
     int b_box_bytes;          // bytes the activation TMA box(es) deliver per stage (== T_pad * 128 except in timing experiments)
+    int dbg;                  // TIMING EXPERIMENTS (ATSPEED_GEMM_DBG): bit 0 = no epilogue stores, bit 1 = no MMA instructions
+    int tma_store;            // epilogue writes through shared memory + cp.async.bulk.tensor stores (tmO*) instead of STG
 };
 
 // Work decomposition ("stream-K with consumer-side fix-up").  The (tile, k-block) units of the whole GEMM are
@@ -130,7 +140,8 @@ struct GemmParams {
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
-                const __grid_constant__ CUtensorMap tmX1, const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmO0,
+                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -241,6 +252,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 const uint32_t b_addr = a_addr + a_bytes;
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    if (p.dbg & 2) break;
                     const uint32_t acc = (!seg_start || k > 0) ? 1u : 0u;
                     const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
                     const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
@@ -264,6 +276,8 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         // ===== epilogue: TMEM -> registers -> global fp32 partial-sum slice =====
         asm volatile("griddepcontrol.wait;" ::: "memory");    // `out` may still be read by the previous consumer
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);   // 2 x 8 KB
+        int st_chunk = 0;
         int seg = 0;
         for (int u = u_begin; u < u_end; ++seg) {
             const int tile = u / KB;
@@ -274,6 +288,34 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
             mbar_wait(&accum_full[buf], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (p.tma_store) {
+                // TMEM -> registers -> [16 tokens][128 features] fp32 staging tile -> ONE bulk tensor store per 8 KB: the
+                // scalar-store epilogue below is LSU-issue bound (40 % of the kernel at T = 512, tools/gemm_sweep.py bigT)
+                const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
+                const bool elected = threadIdx.x == 64;                       // first epilogue thread
+                const int f = q * 32 + lane;                                  // feature within the 128-row half
+                for (int half = 0; half < (p.BM >> 7); ++half) {
+                    const uint32_t tbase = tmem_base + buf * p.buf_stride + half * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+                    for (int c = 0; c < p.T_pad; c += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(tbase + static_cast<uint32_t>(c), r);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float* stg = stage_out + (st_chunk & 1) * (16 * 128);
+                        // the store issued two chunks ago has finished reading this staging buffer
+                        if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (elected && !(p.dbg & 1)) {
+                            tma_store_3d(tmO, stg, m0 + half * BLOCK_M, c, slice);   // clipped to [rows_i, T, slices]
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        ++st_chunk;
+                    }
+                }
+            } else
             for (int half = 0; half < (p.BM >> 7); ++half) {
                 const int row = m0 + half * BLOCK_M + q * 32 + lane;           // output feature
                 const bool row_ok = row < p.n_rows[wid];
@@ -283,7 +325,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     uint32_t r[16];
                     tmem_ld16(tbase + static_cast<uint32_t>(c), r);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (row_ok) {
+                    if (row_ok && !(p.dbg & 1)) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
@@ -294,6 +336,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
             u = seg_end;
         }
+        if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -393,7 +436,7 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
         if (n > pl->max_slices) pl->max_slices = n;
     }
     const int stage_bytes = pl->BM * BLOCK_K * 2 + pl->T_pad * BLOCK_K * 2;
-    int stages = (220 * 1024) / stage_bytes;
+    int stages = (220 * 1024 - OUT_STAGE_BYTES) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (const char* e = getenv("ATSPEED_GEMM_STAGES")) { if (atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
     if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
@@ -443,9 +486,40 @@ int gemm_make_xmap(XMap* xm, const void* x, int T, int K) {
     return ATS_OK;
 }
 
+// Output tensor maps of one launch: per weight a 3-D view (feature, token, slice) of the fp32 partial-sum buffer, so the
+// epilogue's bulk stores are clipped to the weight's own columns, to T tokens and to the slice.  ok = 0 when the buffer
+// does not meet TMA's 16-byte rules (odd ldo in unit tests): the kernel then falls back to its scalar-store epilogue.
+int gemm_make_omap(OMap* om, const GemmWeights& w, float* out, int ldo, long long slice_stride, int T, int max_slices) {
+    memset(om, 0, sizeof(*om));
+    om->out = out; om->ldo = ldo; om->slice_stride = slice_stride; om->T = T;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return ATS_OK;
+    const char* e = getenv("ATSPEED_GEMM_TMASTORE");
+    if (e && atoi(e) == 0) return ATS_OK;
+    const long long sstride = max_slices > 1 ? slice_stride : static_cast<long long>(T) * ldo;
+    if ((ldo & 3) || (sstride & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return ATS_OK;
+    for (int i = 0; i < w.n; ++i) {
+        if (w.colbase[i] & 3) return ATS_OK;
+        cuuint64_t dims[3] = {static_cast<cuuint64_t>(w.rows[i]), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(max_slices)};
+        cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldo) * 4, static_cast<cuuint64_t>(sstride) * 4};
+        cuuint32_t box[3] = {128, 16, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&om->tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out + w.colbase[i], dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return ATS_OK;
+    }
+    for (int i = w.n; i < 3; ++i) om->tm[i] = om->tm[0];
+    om->ok = 1;
+    return ATS_OK;
+}
+
 // out[slice][t][...]. X: [T, K] bf16 row-major (through xm). W_i: [n_rows_i, K] bf16 row-major.
-int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, float* out, int ldo, long long slice_stride,
-            cudaStream_t stream) {
+int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap& om, cudaStream_t stream) {
+    float* out = om.out;
+    const int ldo = om.ldo;
+    const long long slice_stride = om.slice_stride;
+    ATS_CHECK_ARG(om.T == pl.T, "gemm: output map built for T=%d, plan for T=%d", om.T, pl.T);
     ATS_CHECK_ARG(xm.T == pl.T && xm.K == w.K, "gemm: activation map (%d x %d) does not match the plan (%d x %d)", xm.T,
                   xm.K, pl.T, w.K);
     GemmParams p;
@@ -462,7 +536,7 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, float* out
     p.n_bufs = pl.n_bufs; p.buf_stride = pl.buf_stride;
     p.b_box_bytes = (pl.T_pad > 256 ? pl.T_pad : xm.box0) * BLOCK_K * 2;
     const int stage_bytes = pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
-    const size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + 1024;
+    const size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + OUT_STAGE_BYTES + 1024;
     static int max_dyn = 0;
     if (!max_dyn) {
         cudaFuncAttributes fa;
@@ -483,8 +557,11 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, float* out
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // previous kernel; see griddepcontrol.wait
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    if (const char* e = getenv("ATSPEED_GEMM_DBG")) p.dbg = atoi(e);
     const CUtensorMap* tw = pl.BM == 256 ? w.tmap256 : w.tmap;
-    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1, p));
+    p.tma_store = om.ok;
+    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1,
+                                om.tm[0], om.tm[1], om.tm[2], p));
     return ATS_OK;
 }
 

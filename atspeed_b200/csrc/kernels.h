@@ -41,8 +41,9 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
 int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms);
 SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& plan);
 int gemm_make_xmap(XMap* xm, const void* x, int T, int K);
-int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, float* out, int ldo, long long slice_stride,
-            cudaStream_t stream);
+struct OMap { CUtensorMap tm[3]; float* out; int ldo; long long slice_stride; int T; int ok; };   // fp32 partial-sum output
+int gemm_make_omap(OMap* om, const GemmWeights& w, float* out, int ldo, long long slice_stride, int T, int max_slices);
+int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, const OMap& om, cudaStream_t stream);
 bool pdl_enabled();   // ATSPEED_PDL=0 disables programmatic dependent launch (debugging)
 
 // ---- elementwise.cu -----------------------------------------------------------------------------

@@ -56,7 +56,11 @@ TS = (10, 50, 130, 220)
 CONFIGS = [("default", {}), ("1 tmem buf", {"ATSPEED_GEMM_BUFS": "1"}), ("bm128", {"ATSPEED_GEMM_BM": "128"}),
            ("bm256", {"ATSPEED_GEMM_BM": "256"}), ("bm128 x132", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_CTAS": "132"}),
            ("bm128 2/SM", {"ATSPEED_GEMM_BM": "128", "ATSPEED_GEMM_STAGES": "2", "ATSPEED_GEMM_CTAS": "296"})]
-if len(sys.argv) > 1 and sys.argv[1] == "chains":
+if len(sys.argv) > 1 and sys.argv[1] == "bigT":
+    CONFIGS = [("default", {}), ("no epi stores", {"ATSPEED_GEMM_DBG": "1"}), ("no mma", {"ATSPEED_GEMM_DBG": "2"}),
+               ("neither", {"ATSPEED_GEMM_DBG": "3"})]
+    TS = (256, 300, 400, 512)
+elif len(sys.argv) > 1 and sys.argv[1] == "chains":
     CONFIGS = [("default", {}), ("c1 b2", {"ATSPEED_GEMM_CHAINS": "1", "ATSPEED_GEMM_BUFS": "2"}),
                ("c2 b1", {"ATSPEED_GEMM_CHAINS": "2", "ATSPEED_GEMM_BUFS": "1"}),
                ("c2 b2", {"ATSPEED_GEMM_CHAINS": "2", "ATSPEED_GEMM_BUFS": "2"}),
