@@ -28,7 +28,7 @@ class TrieDesc(C.Structure):
 class Config(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("max_new_tokens", C.c_int32), ("max_prompt", C.c_int32),
                 ("num_sms", C.c_int32), ("do_sample", C.c_int32), ("top_k", C.c_int32), ("temperature", C.c_float),
-                ("seed", C.c_uint64), ("max_users", C.c_int32)]
+                ("seed", C.c_uint64), ("max_users", C.c_int32), ("cohort_tokens", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -69,7 +69,7 @@ SYMBOLS = {
     "atspeed_session_result_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "atspeed_session_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "atspeed_session_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
-                                               C.POINTER(C.c_double), C.c_void_p]),
+                                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),
     "atspeed_target_generate": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, c_i32p, c_f32p, c_i32p,
                                           C.POINTER(Stats), C.c_void_p]),
     "atspeed_session_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),

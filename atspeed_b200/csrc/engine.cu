@@ -37,6 +37,12 @@ static double gemm_bytes(const GemmWeights& g, int T) {
     return 2.0 * (rows * g.K + static_cast<double>(T) * g.K + static_cast<double>(T) * rows);
 }
 
+static double gemm_flops(const GemmWeights& g, int T) {
+    double rows = 0;
+    for (int i = 0; i < g.n; ++i) rows += g.rows[i];
+    return 2.0 * rows * g.K * T;
+}
+
 static GemmWeights shape_only(int K, std::initializer_list<int> rows) {
     GemmWeights g;
     memset(&g, 0, sizeof(g));
@@ -164,6 +170,8 @@ static int check_cfg(const atspeed_model_desc* target, const atspeed_model_desc*
                   "max_new_tokens=%d outside [1,%d]", cfg->max_new_tokens, MAX_LEVELS);
     ATS_CHECK_ARG(cfg->max_prompt >= 1, "max_prompt=%d", cfg->max_prompt);
     ATS_CHECK_ARG(cfg->max_users >= 0 && cfg->max_users <= MAX_USERS, "max_users=%d outside [0,%d]", cfg->max_users, MAX_USERS);
+    ATS_CHECK_ARG(cfg->cohort_tokens == 0 || (cfg->cohort_tokens >= 256 && cfg->cohort_tokens <= 512),
+                  "cohort_tokens=%d outside [256,512]", cfg->cohort_tokens);
     if (cfg->max_users > 1)
         ATS_CHECK_ARG(!target->weights_f32 && !(draft && draft->weights_f32), "cohort mode (max_users > 1) needs bf16 models");
     if (cfg->do_sample) {
@@ -199,7 +207,7 @@ static void session_dims(atspeed_session* s) {
     s->geom.K = c.K; s->geom.N = c.N; s->geom.A_cap = c.max_new_tokens * c.K; s->geom.V = 0;
     s->R_max = c.K + (MAX_LEVELS - 1) * c.N + 1;
     s->max_users = c.max_users > 1 ? c.max_users : 1;
-    if (s->max_users > 1) { s->T_max = 512; s->R_max = 512; }     // a cohort forward packs users up to the GEMM's token limit
+    if (s->max_users > 1) { s->T_max = c.cohort_tokens > 0 ? c.cohort_tokens : 512; s->R_max = s->T_max; }   // tokens packed per forward
     s->S_max = c.max_prompt + s->geom.A_cap + s->geom.lvl_off(MAX_LEVELS) + c.K;
 }
 
@@ -307,21 +315,18 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
         LayerRT& L = m.layers[l];
         __nv_bfloat16* kc = m.kv + static_cast<long long>(l) * 2 * m.kv_plane;
         __nv_bfloat16* vc = kc + m.kv_plane;
-        PROF(s, CAT_GEMM, gemm_bytes(L.qkv, T), gemm_wx(L.qkv, xm_x, p_qkv, om_qkv, st));
+        PROF_GEMM(s, L.qkv, T, gemm_wx(L.qkv, xm_x, p_qkv, om_qkv, st));
         PROF(s, CAT_ELEM, 0,
              qkv_rope_append(m.part, sm_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
                              d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
         PROF(s, CAT_ATTN, 0, tree_attention(m.q, kc, vc, b, T, S, d.n_heads, d.head_dim, m.a, st));
-        PROF(s, CAT_GEMM, gemm_bytes(L.o, T),
-             gemm_wx(L.o, xm_a, p_o, om_o, st));
+        PROF_GEMM(s, L.o, T, gemm_wx(L.o, xm_a, p_o, om_o, st));
         PROF(s, CAT_ELEM, 0,
              residual_rmsnorm(m.h, m.part, sm_o, static_cast<long long>(T) * d.hidden, d.hidden, L.ln2, T, d.hidden,
                               d.rms_eps, m.x, st));
-        PROF(s, CAT_GEMM, gemm_bytes(L.gu, T),
-             gemm_wx(L.gu, xm_x, p_gu, om_gu, st));
+        PROF_GEMM(s, L.gu, T, gemm_wx(L.gu, xm_x, p_gu, om_gu, st));
         PROF(s, CAT_ELEM, 0, silu_mul(m.part, sm_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
-        PROF(s, CAT_GEMM, gemm_bytes(L.down, T),
-             gemm_wx(L.down, xm_m, p_down, om_down, st));
+        PROF_GEMM(s, L.down, T, gemm_wx(L.down, xm_m, p_down, om_down, st));
         const __nv_bfloat16* next_ln = l + 1 < d.n_layers ? m.layers[l + 1].ln1 : nullptr;
         PROF(s, CAT_ELEM, 0,
              residual_rmsnorm(m.h, m.part, sm_down, static_cast<long long>(T) * d.hidden, d.hidden, next_ln, T,
@@ -330,7 +335,7 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
     }
     PROF(s, CAT_ELEM, 0,
          rmsnorm_rows(m.h, static_cast<const __nv_bfloat16*>(d.final_norm), R, d.hidden, d.rms_eps, m.xsel, rows_idx, st));
-    PROF(s, CAT_GEMM, gemm_bytes(m.lm, R), gemm_wx(m.lm, xm_sel, p_lm, om_lm, st));
+    PROF_GEMM(s, m.lm, R, gemm_wx(m.lm, xm_sel, p_lm, om_lm, st));
     s->launches += 2;
     m.last_rows = R;
     m.forwards++;
@@ -490,6 +495,7 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
     s->prof_on = false;
     s->prof_n = 0;
     for (double& b : s->prof_bytes) b = 0;
+    for (double& b : s->prof_flops) b = 0;
     *out = s;
     return ATS_OK;
 }
@@ -563,13 +569,18 @@ int atspeed_session_profile(atspeed_session* s, int32_t enable) {
     s->prof_on = enable != 0;
     s->prof_n = 0;
     for (double& b : s->prof_bytes) b = 0;
+    for (double& b : s->prof_flops) b = 0;
     return ATS_OK;
 }
 
-int atspeed_session_profile_read(atspeed_session* s, double* ms6, int64_t* count6, double* bytes6, void* stream) {
+int atspeed_session_profile_read(atspeed_session* s, double* ms6, int64_t* count6, double* bytes6, double* flops6,
+                                 void* stream) {
     ATS_CHECK_ARG(s && ms6 && count6 && bytes6, "null argument");
     ATS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-    for (int c = 0; c < CAT_COUNT; ++c) { ms6[c] = 0; count6[c] = 0; bytes6[c] = s->prof_bytes[c]; }
+    for (int c = 0; c < CAT_COUNT; ++c) {
+        ms6[c] = 0; count6[c] = 0; bytes6[c] = s->prof_bytes[c];
+        if (flops6) flops6[c] = s->prof_flops[c];
+    }
     for (int i = 0; i < s->prof_n; ++i) {
         float ms = 0.f;
         ATS_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[2 * i], s->prof_ev[2 * i + 1]));
@@ -578,6 +589,7 @@ int atspeed_session_profile_read(atspeed_session* s, double* ms6, int64_t* count
     }
     s->prof_n = 0;
     for (double& b : s->prof_bytes) b = 0;
+    for (double& b : s->prof_flops) b = 0;
     return ATS_OK;
 }
 

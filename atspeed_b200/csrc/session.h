@@ -85,6 +85,7 @@ struct atspeed_session {
     std::vector<int> prof_cat;
     int prof_n;
     double prof_bytes[6];
+    double prof_flops[6];
 };
 
 namespace atspeed {
@@ -92,10 +93,11 @@ namespace atspeed {
 enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ELEM = 2, CAT_TOPK = 3, CAT_BEAM = 4, CAT_GATHER = 5, CAT_COUNT = 6 };
 static constexpr int PROF_PAIRS = 16384;
 
-static inline void prof_begin(atspeed_session* s, int cat, double bytes, cudaStream_t st) {
+static inline void prof_begin(atspeed_session* s, int cat, double bytes, cudaStream_t st, double flops = 0.0) {
     if (!s->prof_on || s->prof_n >= PROF_PAIRS) return;
     s->prof_cat[s->prof_n] = cat;
     s->prof_bytes[cat] += bytes;
+    s->prof_flops[cat] += flops;
     cudaEventRecord(s->prof_ev[2 * s->prof_n], st);
 }
 static inline void prof_end(atspeed_session* s, cudaStream_t st) {
@@ -108,6 +110,12 @@ static inline void prof_end(atspeed_session* s, cudaStream_t st) {
         prof_begin(s, cat, bytes, st);         \
         ATS_TRY(call);                         \
         prof_end(s, st);                       \
+    } while (0)
+#define PROF_GEMM(s, w, T, call)                                          \
+    do {                                                                  \
+        prof_begin(s, CAT_GEMM, gemm_bytes(w, T), st, gemm_flops(w, T));  \
+        ATS_TRY(call);                                                    \
+        prof_end(s, st);                                                  \
     } while (0)
 
 

@@ -143,7 +143,8 @@ class Session:
 
     def __init__(self, target: DeviceModel, draft: Optional[DeviceModel], trie: DeviceTrie, K: int, N: int,
                  max_new_tokens: int = 4, max_prompt: Optional[int] = None, do_sample: bool = False,
-                 top_k: Optional[int] = None, temperature: float = 1.0, seed: int = 0, max_users: int = 1):
+                 top_k: Optional[int] = None, temperature: float = 1.0, seed: int = 0, max_users: int = 1,
+                 cohort_tokens: int = 0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.AtSpeedError("atspeed_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -157,7 +158,7 @@ class Session:
         cfg = _lib.Config(K, N, max_new_tokens, max_prompt,
                           torch.cuda.get_device_properties(self.device).multi_processor_count,
                           1 if do_sample else 0, int(top_k or 0), float(temperature or 1.0), int(seed) & (2 ** 64 - 1),
-                          int(max_users))
+                          int(max_users), int(cohort_tokens))
         self.max_users = int(max_users)
         self.cfg = cfg
         nbytes = C.c_size_t(0)
@@ -280,10 +281,10 @@ class Session:
         _lib.check(self.lib.atspeed_session_profile(self.handle, 1 if enable else 0))
 
     def profile_read(self) -> Dict[str, Dict[str, float]]:
-        ms, cnt, by = (C.c_double * 6)(), (C.c_int64 * 6)(), (C.c_double * 6)()
-        _lib.check(self.lib.atspeed_session_profile_read(self.handle, ms, cnt, by, self._stream()))
+        ms, cnt, by, fl = (C.c_double * 6)(), (C.c_int64 * 6)(), (C.c_double * 6)(), (C.c_double * 6)()
+        _lib.check(self.lib.atspeed_session_profile_read(self.handle, ms, cnt, by, fl, self._stream()))
         names = ("gemm", "attention", "rowwise", "topk", "beam", "kvgather")
-        return {n: {"ms": ms[i], "launches": int(cnt[i]), "bytes": by[i]} for i, n in enumerate(names)}
+        return {n: {"ms": ms[i], "launches": int(cnt[i]), "bytes": by[i], "flops": fl[i]} for i, n in enumerate(names)}
 
     def target_generate(self, prompt_ids: Sequence[int]) -> Dict:
         arr, ptr, P = self._prompt(prompt_ids)

@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="atspeed", choices=["atspeed", "reference"])
-    ap.add_argument("--users-per-step", type=int, default=32)
+    ap.add_argument("--users-per-step", type=int, default=48)
     ap.add_argument("--cohort", type=int, default=8,
                     help="users whose trees share each forward (atspeed_bssd_batch; <= 512 tokens per forward); 1 = one "
                          "search per forward as the reference")
@@ -59,9 +59,10 @@ def parse():
     ap.add_argument("--draft", default="68m")
     ap.add_argument("--constraint", default="strict", choices=["strict", "positional"])
     ap.add_argument("--profile-users", type=int, default=4)
-    ap.add_argument("--lanes", type=int, default=4,
+    ap.add_argument("--lanes", type=int, default=3,
                     help="independent searches in flight per GPU (each its own session + CUDA stream + host thread): one "
                          "user's latency-bound draft / verify phases overlap another's weight-streaming target forward")
+    ap.add_argument("--cohort-tokens", type=int, default=512, help="most tokens one cohort forward packs (256..512)")
     ap.add_argument("--do-sample", action="store_true", help="AtSpeed-R relaxed acceptance (configs[2]) instead of AtSpeed-S")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hf-baseline-users", type=int, default=3,
@@ -74,7 +75,7 @@ def workload_name(a):
     return (f"LLaMA-{a.target}-shape target + LLaMA-{a.draft}-shape draft, {mode}, "
             f"{a.dataset} test users, {a.constraint} constraint, K={a.K} N={a.N} gamma={a.gamma} max_new_tokens=4, "
             f"{a.users_per_step} users/step/GPU, " +
-            (f"cohorts of up to {a.cohort} users per forward (<=512 tokens), {a.lanes} cohorts in flight per GPU"
+            (f"cohorts of up to {a.cohort} users per forward (<={a.cohort_tokens} tokens), {a.lanes} cohorts in flight per GPU"
              if a.cohort > 1 else f"batch 1 per search (as the reference), {a.lanes} searches in flight per GPU"))
 
 
@@ -151,11 +152,12 @@ def ncu_traffic(kernel):
 
 
 def peaks():
+    """(HBM GB/s, sustained bf16 TFLOP/s, source): the GEMM is timed inside a long step, so the sustained figure applies."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return j["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return j["hbm_gbs"], j.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md 6.65 TB/s, ~1.4 PFLOP/s sustained)"
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -244,6 +246,7 @@ def atspeed_arm(a, rank, world, local_rank):
     n_lanes = max(1, a.lanes)
     if a.cohort > 1:
         skw["max_users"] = a.cohort
+        skw["cohort_tokens"] = a.cohort_tokens
     lanes = [Session(tdm, ddm, dtrie, a.K, a.N, 4, **skw) for _ in range(n_lanes)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
     sess = lanes[0]
@@ -388,13 +391,25 @@ def atspeed_arm(a, rank, world, local_rank):
         groups = {k: {"ms_per_user": v["ms"] / max(1, a.profile_users), "launches_per_user": v["launches"] / max(1, a.profile_users),
                       "share": v["ms"] / tot if tot else 0.0} for k, v in prof.items()}
         g = prof["gemm"]
-        peak, how = peaks()
-        ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] else 0.0
+        peak, peak_tf, how = peaks()
+        sec = g["ms"] * 1e-3
+        ach = g["bytes"] / sec / 1e9 if sec else 0.0
+        ach_tf = g["flops"] / sec / 1e12 if sec else 0.0
+        # which resource bounds the launches in aggregate: time the algorithmic bytes need at the measured copy peak vs
+        # time the FLOPs need at the measured sustained cuBLAS peak (cohort forwards are large enough to be tensor-bound)
+        t_hbm, t_tensor = g["bytes"] / (peak * 1e9), g["flops"] / (peak_tf * 1e12)
         traffic, tinfo = ncu_traffic("gemm_wx_tcgen05")
-        roofline = {"kernel": "gemm_wx_tcgen05", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic, "traffic_source": tinfo, "peak_source": how,
-                    "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]), "launches": g["launches"],
-                    "algorithmic_bytes_per_launch": g["bytes"] / max(1, g["launches"])}
+        if t_tensor > t_hbm:
+            roofline = {"kernel": "gemm_wx_tcgen05", "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": ach_tf / peak_tf, "hbm_achieved_gbs": ach, "hbm_frac": ach / peak}
+        else:
+            roofline = {"kernel": "gemm_wx_tcgen05", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "tensor_achieved_tflops": ach_tf, "tensor_frac": ach_tf / peak_tf}
+        roofline.update({"traffic": traffic, "traffic_source": tinfo, "peak_source": how,
+                         "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]), "launches": g["launches"],
+                         "algorithmic_bytes_per_launch": g["bytes"] / max(1, g["launches"]),
+                         "flops_per_launch": g["flops"] / max(1, g["launches"]),
+                         "roofline_time_frac": max(t_hbm, t_tensor) / sec if sec else 0.0})
     users_total = world * U * a.steps
     out = {"metric": "topk_recs_per_sec", "value": users_total / (ms_total * 1e-3), "unit": "users/s", "n_gpus": world,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,

@@ -87,6 +87,7 @@ typedef struct atspeed_config {
      * single-user session.  Each user keeps its own KV caches and beam tree; results per user are those of a
      * single-user session.  bf16 models only. */
     int32_t max_users;
+    int32_t cohort_tokens;    /* most tokens a cohort forward may pack (256..512 = the GEMM's limit; 0 = 512) */
 } atspeed_config;
 
 typedef struct atspeed_session atspeed_session;
@@ -151,7 +152,7 @@ int atspeed_bssd(atspeed_session* s, const int32_t* prompt_host, int32_t P, int3
 
 /* BSSD for n_users prompts at once (cohort mode, cfg.max_users > 1): a host-side scheduler keeps up to max_users
  * searches in flight, batches every draft step / target verify forward / final step of the users that are ready into one
- * forward of at most 512 tokens, and runs kernels (a), (b), (c) for all of them in single launches.  Users finish in
+ * forward of at most cfg.cohort_tokens tokens, and runs kernels (a), (b), (c) for all of them in single launches.  Users finish in
  * 1..4 rounds independently; a finished user's slot is refilled from the remaining prompts.
  *   prompts_host : int32, all prompts concatenated;  prompt_lens int32[n_users]
  *   tokens_host  : int32[n_users][K * max_new_tokens], scores_host float[n_users][K], counts int32[n_users]
@@ -229,9 +230,11 @@ int atspeed_session_sample_width(atspeed_session* s);
 /* Per-launch CUDA-event timing (the reference's `Timer` blocks, code/beamSD.py:12-37,51,60,220,276, without the
  * forced device syncs): when enabled every kernel launch is bracketed by two events on the caller's stream.
  * profile_read synchronises and returns, per category {0 gemm, 1 attention, 2 row-wise, 3 kernel (a), 4 beam/verify
- * kernel (b), 5 kernel (c)}: total milliseconds, launch count and algorithmic bytes, then resets the counters. */
+ * kernel (b), 5 kernel (c)}: total milliseconds, launch count, algorithmic bytes and (GEMM only; may be NULL) floating-point
+ * operations, then resets the counters. */
 int atspeed_session_profile(atspeed_session* s, int32_t enable);
-int atspeed_session_profile_read(atspeed_session* s, double* ms6, int64_t* count6, double* bytes6, void* stream);
+int atspeed_session_profile_read(atspeed_session* s, double* ms6, int64_t* count6, double* bytes6, double* flops6,
+                                 void* stream);
 
 /* Run one forward of model `model` (0 target, 1 draft) on an explicit batch (all DEVICE arrays): used by the
  * forward parity tests.  tok/pos/slot/prefix_len int32[T], vis uint32[T][16] relative to slot `vis_base`,

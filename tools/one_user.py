@@ -22,6 +22,7 @@ ap.add_argument("--N", type=int, default=40)
 ap.add_argument("--gamma", type=int, default=3)
 ap.add_argument("--dataset", default="beauty")
 ap.add_argument("--constraint", default="strict")
+ap.add_argument("--cohort", type=int, default=1, help="> 1: run --users users through atspeed_bssd_batch")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 ds = load_dataset(a.dataset)
@@ -33,8 +34,14 @@ for name in (a.target, a.draft):
 tdm = DeviceModel(specs[0], bench.gpu_weights(specs[0], 1, dev), dev)
 ddm = DeviceModel(specs[1], bench.gpu_weights(specs[1], 2, dev), dev)
 csr = compile_constraint(fn, ds.prompt_ids(0), 4, other_prompt=ds.prompt_ids(1))
-sess = Session(tdm, ddm, DeviceTrie(csr, dev), a.K, a.N, 4)
-for u in range(a.users + 1):
-    out = sess.bssd(ds.prompt_ids(u), a.gamma)
+if a.cohort > 1:
+    sess = Session(tdm, ddm, DeviceTrie(csr, dev), a.K, a.N, 4, max_users=a.cohort)
+    for rep in range(2):       # first pass = warm-up
+        outs = sess.bssd_batch([ds.prompt_ids(u) for u in range(a.users)], a.gamma)
+    out = outs[-1]
+else:
+    sess = Session(tdm, ddm, DeviceTrie(csr, dev), a.K, a.N, 4)
+    for u in range(a.users + 1):
+        out = sess.bssd(ds.prompt_ids(u), a.gamma)
 torch.cuda.synchronize()
 print("ok", out["n_run"], out["accept_steps"], out["kernel_launches"])
