@@ -193,9 +193,20 @@ def make_fn(ds, kind):
     return positional_prefix_allowed_tokens_fn(ds.positional_allowed(), RESPONSE_SEP)
 
 
+def host_threads():
+    """All the host cores this process may use (torchrun pins OMP_NUM_THREADS=1: undo that for the CPU arm)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def reference_arm(a, rank):
     if rank != 0:
         return
+    host_threads()
     from atspeed_b200.prompts import load_dataset
     ds = load_dataset(a.dataset)
     fn = make_fn(ds, a.constraint)
@@ -427,6 +438,7 @@ def atspeed_arm(a, rank, world, local_rank):
            "kernel_groups": groups, "roofline": roofline}
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
+            host_threads()
             models = cpu_models(a, V)
             dt, _ = cpu_one_user(a, models, ds, fn, step_users[a.warmup][0])
             out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
