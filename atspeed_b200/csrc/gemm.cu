@@ -61,6 +61,51 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// ---- cta_group::2 (CTA pair) forms ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by both CTAs of the pair; the transaction bytes are credited to the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once the issuing thread's MMAs retire) on the barrier at the same shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+// arrive on the barrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_m(uint32_t m, uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 // smem [1][16][128] fp32 box -> global (coordinates: feature, token, slice); bulk-group completion
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
@@ -129,6 +174,7 @@ struct GemmParams {
     int b_box_bytes;          // bytes the activation TMA box(es) deliver per stage (== T_pad * 128 except in timing experiments)
     int dbg;                  // TIMING EXPERIMENTS (ATSPEED_GEMM_DBG): bit 0 = no epilogue stores, bit 1 = no MMA instructions
     int tma_store;            // epilogue writes through shared memory + cp.async.bulk.tensor stores (tmO*) instead of STG
+    int n_mma, N_mma;         // 2-CTA kernel: the token axis (padded to 64) is covered by n_mma MMAs of N_mma columns each
 };
 
 // Work decomposition ("stream-K with consumer-side fix-up").  The (tile, k-block) units of the whole GEMM are
@@ -346,6 +392,207 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for large token counts (cohort forwards, T > 256).
+//
+// Two CTAs on the SMs of one TPC own one 256-row weight tile: each streams ITS 128 rows (A) and HALF of the activation
+// tile (B: the tokens are split across the pair), and the leader's single MMA thread issues M = 256 MMAs that read both
+// CTAs' shared memory and write both CTAs' TMEM.  Per CTA a k-block stage is 16 KB + T/2 x 128 B instead of
+// 16 KB + T x 128 B, so the ring is twice as deep at T = 512 (4 stages instead of 2) and the L2->SM traffic of the
+// activations is halved.  Work decomposition, slices and epilogue are those of gemm_wx_tcgen05 with "CTA" read as
+// "pair" and BM = 256.
+// Barriers (same offsets in both CTAs): full[s] lives in the leader (its producer posts the expected bytes of BOTH CTAs,
+// every TMA of the pair completes on it); empty[s] and accum_full[b] are signalled in both CTAs by the leader's
+// multicast commit; accum_empty[b] lives in the leader and collects the 8 epilogue warps of the pair.
+// ---------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+                     const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t accum_full[2], accum_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int T64 = p.n_mma * p.N_mma;                       // tokens padded to a multiple of 64
+    const int b_half_rows = p.N_mma >> 1;                    // tokens of one MMA held by this CTA
+    const int b_mma_bytes = b_half_rows * BLOCK_K * 2;
+    const int a_bytes = A_TILE_BYTES;
+    const int stage_bytes = a_bytes + p.n_mma * b_mma_bytes;
+    const int KB = p.n_kblocks;
+    const int u_begin = pair * p.U;
+    const int u_end = min(u_begin + p.U, p.total_units);
+    const int n_units = u_end - u_begin;
+
+    auto tile_of = [&](int tile, int& wid, int& m0) {
+        wid = 0;
+        if (tile >= p.tiles[0]) { tile -= p.tiles[0]; wid = 1; }
+        if (wid == 1 && tile >= p.tiles[1]) { tile -= p.tiles[1]; wid = 2; }
+        m0 = tile * 256 + static_cast<int>(rank) * BLOCK_M;   // this CTA's 128 rows of the pair's 256-row tile
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&accum_full[b], 1);
+            mbar_init(&accum_empty[b], 8);        // 4 epilogue warps of each CTA of the pair
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmW0); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmX);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(static_cast<uint32_t>(p.tmem_cols)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                      // barriers of BOTH CTAs initialised, TMEM allocated
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer (one thread in each CTA) =====
+        if (lane == 0) {
+            int tile = u_begin / KB, kb = u_begin - tile * KB, wid, m0;
+            tile_of(tile, wid, m0);
+            auto advance = [&]() {
+                if (++kb == KB) { kb = 0; ++tile; tile_of(tile, wid, m0); }
+            };
+            auto load_a = [&](int s) {
+                const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
+                if (leader) mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+                tma_load_2d_2sm(tmW, &full_bar[s], smem + static_cast<size_t>(s) * stage_bytes, kb * BLOCK_K, m0);
+            };
+            auto load_b = [&](int s, int kbb) {
+                uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
+                for (int i = 0; i < p.n_mma; ++i)            // tokens [i*N_mma + rank*N_mma/2, +N_mma/2): rows past T are zeros
+                    tma_load_2d_2sm(&tmX, &full_bar[s], b_dst + i * b_mma_bytes, kbb * BLOCK_K,
+                                    i * p.N_mma + static_cast<int>(rank) * b_half_rows);
+            };
+            const int npre = n_units < p.stages ? n_units : p.stages;
+            const int kb_first = kb;
+            for (int i = 0; i < npre; ++i) { load_a(i); advance(); }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            for (int i = 0, kbb = kb_first; i < npre; ++i) { load_b(i, kbb); if (++kbb == KB) kbb = 0; }
+            int s = npre == p.stages ? 0 : npre;
+            uint32_t ph = npre == p.stages ? 1 : 0;
+            for (int u = u_begin + npre; u < u_end; ++u) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                load_a(s);
+                load_b(s, kb);
+                advance();
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the LEADER CTA =====
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc_m(256, static_cast<uint32_t>(p.N_mma));
+            int s = 0; uint32_t ph = 0;
+            int kb = u_begin % KB;
+            int buf = 0;
+            uint32_t use[2] = {0, 0};
+            for (int u = u_begin; u < u_end; ++u) {
+                const bool seg_start = (u == u_begin) || kb == 0;
+                if (seg_start && use[buf] > 0) {
+                    mbar_wait(&accum_empty[buf], (use[buf] - 1) & 1);     // both CTAs' epilogues drained this buffer
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t tacc = tmem_base + buf * p.buf_stride;
+                mbar_wait(&full_bar[s], ph);                              // both CTAs' tiles of this stage have landed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    const uint32_t acc = (!seg_start || k > 0) ? 1u : 0u;
+                    const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
+                    umma_bf16_2sm(tacc, da, make_smem_desc(b_addr + k * UMMA_K * 2), idesc, acc);
+                    if (p.n_mma == 2)
+                        umma_bf16_2sm(tacc + p.N_mma, da, make_smem_desc(b_addr + b_mma_bytes + k * UMMA_K * 2), idesc, acc);
+                }
+                umma_commit_2sm(&empty_bar[s]);                           // frees the slot in both CTAs
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+                if (++kb == KB) kb = 0;
+                if (u + 1 == u_end || kb == 0) {
+                    umma_commit_2sm(&accum_full[buf]);                    // accumulators complete in both CTAs
+                    ++use[buf];
+                    if (p.n_bufs == 2) buf ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): this CTA's 128 rows of the pair's tile =====
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int q = warp & 3;
+        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+        int st_chunk = 0;
+        int seg = 0;
+        const bool elected = threadIdx.x == 64;
+        const int f = q * 32 + lane;
+        for (int u = u_begin; u < u_end; ++seg) {
+            const int tile = u / KB;
+            const int seg_end = min((tile + 1) * KB, u_end);
+            int wid, m0;
+            tile_of(tile, wid, m0);
+            const int slice = pair - (tile * KB) / p.U;
+            const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
+            mbar_wait(&accum_full[buf], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
+            const uint32_t tbase = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
+            const int row = m0 + f;
+            const bool row_ok = row < p.n_rows[wid];
+            float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
+            for (int c = 0; c < T64 && c < p.T; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(tbase + static_cast<uint32_t>(c), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p.tma_store) {
+                    float* stg = stage_out + (st_chunk & 1) * (16 * 128);
+                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (elected && !(p.dbg & 1)) {
+                        tma_store_3d(tmO, stg, m0, c, slice);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++st_chunk;
+                } else if (row_ok && !(p.dbg & 1)) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], 0);     // the leader's MMA thread waits for all 8 warps
+            u = seg_end;
+        }
+        if (p.tma_store && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                      // nobody frees TMEM / exits while the peer may still touch it
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(static_cast<uint32_t>(p.tmem_cols)));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -383,6 +630,13 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, lon
     return ATS_OK;
 }
 
+// Large token counts (cohort forwards) run the CTA-pair kernel; ATSPEED_GEMM_2CTA=0 keeps the single-CTA kernel.
+bool gemm_use_2cta(int T) {
+    const char* e = getenv("ATSPEED_GEMM_2CTA");
+    const int T_pad = (T + 15) & ~15;
+    return !(e && atoi(e) == 0) && T_pad > 256;
+}
+
 // Choose the tile height, the persistent grid and the unit range of every CTA for one GEMM shape.
 //   allow_cut : tiles may be cut along K across CTAs (partial-sum slices; consumers reduce via SplitMap).  When false
 //               (lm_head: its consumer, kernel (a), reads plain fp32 logits) whole tiles are dealt out instead.
@@ -394,6 +648,51 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     pl->T = T;
     pl->T_pad = (T + 15) & ~15;
     pl->KB = (w.K + BLOCK_K - 1) / BLOCK_K;
+    if (gemm_use_2cta(T) && num_sms >= 2) {
+        // CTA-pair kernel (gemm_wx_tcgen05_2cta): 256-row tiles owned by SM pairs, tokens padded to 64 and covered by one
+        // or two M=256 MMAs of N_mma columns (each CTA holds N_mma/2 tokens of each)
+        pl->two_cta = 1;
+        const int T64 = (T + 63) & ~63;
+        pl->n_mma = T64 > 256 ? 2 : 1;
+        pl->N_mma = T64 / pl->n_mma;
+        pl->BM = 256;
+        pl->total_tiles = 0;
+        for (int i = 0; i < 3; ++i) {
+            pl->tiles[i] = i < w.n ? (w.rows[i] + 255) / 256 : 0;
+            pl->tilebase[i] = pl->total_tiles;
+            pl->total_tiles += pl->tiles[i];
+        }
+        const int pairs = num_sms / 2;
+        const int units = pl->total_tiles * pl->KB;
+        if (allow_cut) {
+            const int grid = units < pairs ? units : pairs;
+            pl->U = (units + grid - 1) / grid;
+            const int min_u = pl->KB < 8 ? pl->KB : 8;
+            if (pl->U < min_u) pl->U = min_u;
+            const int s = pairs / pl->total_tiles;      // narrow outputs: whole k-splits per tile (one segment per pair)
+            if (s >= 2 && s <= pl->KB && pl->total_tiles * s * 10 >= pairs * 8) pl->U = (pl->KB + s - 1) / s;
+        } else {
+            pl->U = ((pl->total_tiles + pairs - 1) / pairs) * pl->KB;
+        }
+        pl->grid = 2 * ((units + pl->U - 1) / pl->U);
+        pl->max_slices = 1;
+        for (int t = 0; t < pl->total_tiles; ++t) {
+            const int n = (t * pl->KB + pl->KB - 1) / pl->U - (t * pl->KB) / pl->U + 1;
+            if (n > pl->max_slices) pl->max_slices = n;
+        }
+        const int stage_bytes = A_TILE_BYTES + (T64 / 2) * BLOCK_K * 2;
+        int stages = (220 * 1024 - OUT_STAGE_BYTES) / stage_bytes;
+        if (stages > MAX_STAGES) stages = MAX_STAGES;
+        if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
+        pl->stages = stages;
+        int acc = 32;
+        while (acc < T64) acc <<= 1;
+        pl->acc_stride = acc;
+        pl->n_bufs = 2 * acc <= 512 ? 2 : 1;
+        pl->buf_stride = acc;
+        pl->tmem_cols = pl->n_bufs * acc;
+        return ATS_OK;
+    }
     int tiles128 = 0;
     for (int i = 0; i < w.n; ++i) tiles128 += (w.rows[i] + 127) / 128;
     // Two stacked 128-row MMAs per activation tile halve the L2->SM re-reads of the activations (the limiter at
@@ -474,6 +773,15 @@ SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& pl) {
 }
 
 int gemm_make_xmap(XMap* xm, const void* x, int T, int K) {
+    if (gemm_use_2cta(T)) {
+        // CTA-pair kernel: one box = the N_mma/2 tokens of one MMA that one CTA of the pair holds
+        const int T64 = (T + 63) & ~63;
+        const int n_mma = T64 > 256 ? 2 : 1;
+        ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, T64 / n_mma / 2));
+        xm->tm1 = xm->tm0;
+        xm->T = T; xm->K = K; xm->box0 = T64 / n_mma / 2;
+        return ATS_OK;
+    }
     const int T_pad = (T + 15) & ~15;
     // activations: tokens 0..255 through tm0 (box = min(T_pad,256) rows), tokens 256..T_pad-1 through tm1
     // (box = T_pad-256 rows); rows past T are zero-filled by TMA, and each box always delivers its full byte count.
@@ -535,7 +843,9 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.acc_stride = pl.acc_stride;
     p.n_bufs = pl.n_bufs; p.buf_stride = pl.buf_stride;
     p.b_box_bytes = (pl.T_pad > 256 ? pl.T_pad : xm.box0) * BLOCK_K * 2;
-    const int stage_bytes = pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
+    p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
+    const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
+                                       : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
     const size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + OUT_STAGE_BYTES + 1024;
     static int max_dyn = 0;
     if (!max_dyn) {
@@ -560,6 +870,21 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     if (const char* e = getenv("ATSPEED_GEMM_DBG")) p.dbg = atoi(e);
     const CUtensorMap* tw = pl.BM == 256 ? w.tmap256 : w.tmap;
     p.tma_store = om.ok;
+    if (pl.two_cta) {
+        static int max_dyn2 = 0;
+        if (!max_dyn2) {
+            cudaFuncAttributes fa;
+            ATS_CUDA(cudaFuncGetAttributes(&fa, gemm_wx_tcgen05_2cta));
+            const int want = 227 * 1024 - static_cast<int>(fa.sharedSizeBytes);
+            ATS_CUDA(cudaFuncSetAttribute(gemm_wx_tcgen05_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            max_dyn2 = want;
+        }
+        ATS_CHECK_ARG(static_cast<int>(smem_bytes) <= max_dyn2 && (pl.grid & 1) == 0, "gemm (2-CTA): smem %zu grid %d", smem_bytes, pl.grid);
+        tw = w.tmap;      // each CTA of the pair loads its own 128-row box
+        ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, om.tm[0],
+                                    om.tm[1], om.tm[2], p));
+        return ATS_OK;
+    }
     ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1,
                                 om.tm[0], om.tm[1], om.tm[2], p));
     return ATS_OK;

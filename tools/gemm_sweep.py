@@ -17,7 +17,7 @@ NBUF = 6
 
 
 def bench(name, T, env):
-    for k in ("ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL", "ATSPEED_GEMM_BUFS", "ATSPEED_GEMM_BBOX", "ATSPEED_GEMM_PACKED", "ATSPEED_GEMM_DBG", "ATSPEED_GEMM_CHAINS"):
+    for k in ("ATSPEED_GEMM_2CTA", "ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL", "ATSPEED_GEMM_BUFS", "ATSPEED_GEMM_BBOX", "ATSPEED_GEMM_PACKED", "ATSPEED_GEMM_DBG", "ATSPEED_GEMM_CHAINS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     K, rows = SHAPES[name]
@@ -60,6 +60,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "bigT":
     CONFIGS = [("default", {}), ("no epi stores", {"ATSPEED_GEMM_DBG": "1"}), ("no mma", {"ATSPEED_GEMM_DBG": "2"}),
                ("neither", {"ATSPEED_GEMM_DBG": "3"})]
     TS = (256, 300, 400, 512)
+elif len(sys.argv) > 1 and sys.argv[1] == "2cta":
+    CONFIGS = [("2cta", {}), ("1cta", {"ATSPEED_GEMM_2CTA": "0"})]
+    TS = (220, 300, 400, 512)
 elif len(sys.argv) > 1 and sys.argv[1] == "chains":
     CONFIGS = [("default", {}), ("c1 b2", {"ATSPEED_GEMM_CHAINS": "1", "ATSPEED_GEMM_BUFS": "2"}),
                ("c2 b1", {"ATSPEED_GEMM_CHAINS": "2", "ATSPEED_GEMM_BUFS": "1"}),
