@@ -28,6 +28,7 @@ static constexpr int BLOCK_M = 128;    // output features per CTA (UMMA M)
 static constexpr int BLOCK_K = 64;     // 64 bf16 = 128 B = one SWIZZLE_128B row
 static constexpr int UMMA_K = 16;
 static constexpr int GEMM_THREADS = 192;
+static constexpr size_t EXCLUSIVE_SMEM_BYTES = 120 * 1024;   // > 227 KiB / 2: at most one GEMM CTA per SM
 static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 static constexpr int MAX_STAGES = 12;
 static constexpr int OUT_STAGE_BYTES = 2 * 16 * 128 * 4;   // epilogue staging: two [16 tokens][128 features] fp32 tiles
@@ -633,8 +634,9 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, lon
 // Large token counts (cohort forwards) run the CTA-pair kernel; ATSPEED_GEMM_2CTA=0 keeps the single-CTA kernel.
 bool gemm_use_2cta(int T) {
     const char* e = getenv("ATSPEED_GEMM_2CTA");
+    const char* m = getenv("ATSPEED_GEMM_2CTA_MIN");       // experiments: smallest padded token count that uses the pair kernel
     const int T_pad = (T + 15) & ~15;
-    return !(e && atoi(e) == 0) && T_pad > 256;
+    return !(e && atoi(e) == 0) && T_pad > (m ? atoi(m) : 256);
 }
 
 // Choose the tile height, the persistent grid and the unit range of every CTA for one GEMM shape.
@@ -846,7 +848,12 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
     const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
                                        : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
-    const size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + OUT_STAGE_BYTES + 1024;
+    size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + OUT_STAGE_BYTES + 1024;
+    // One GEMM CTA per SM, always: a CTA holds its TMEM columns from prologue to exit and, with PDL and several streams,
+    // CTAs of different launches overlap in time.  Two CTA PAIRS sharing a TPC can each win tcgen05.alloc on one SM and
+    // wait forever for the other (observed as a hang with small-K draft-model GEMMs whose rings need < half an SM's
+    // shared memory); asking for more than half of the SM's shared memory makes co-residency impossible.
+    if (smem_bytes < EXCLUSIVE_SMEM_BYTES) smem_bytes = EXCLUSIVE_SMEM_BYTES;
     static int max_dyn = 0;
     if (!max_dyn) {
         cudaFuncAttributes fa;

@@ -17,7 +17,7 @@ NBUF = 6
 
 
 def bench(name, T, env):
-    for k in ("ATSPEED_GEMM_2CTA", "ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL", "ATSPEED_GEMM_BUFS", "ATSPEED_GEMM_BBOX", "ATSPEED_GEMM_PACKED", "ATSPEED_GEMM_DBG", "ATSPEED_GEMM_CHAINS"):
+    for k in ("ATSPEED_GEMM_2CTA", "ATSPEED_GEMM_2CTA_MIN", "ATSPEED_GEMM_BM", "ATSPEED_GEMM_STAGES", "ATSPEED_GEMM_CTAS", "ATSPEED_PDL", "ATSPEED_GEMM_BUFS", "ATSPEED_GEMM_BBOX", "ATSPEED_GEMM_PACKED", "ATSPEED_GEMM_DBG", "ATSPEED_GEMM_CHAINS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     K, rows = SHAPES[name]
@@ -61,8 +61,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "bigT":
                ("neither", {"ATSPEED_GEMM_DBG": "3"})]
     TS = (256, 300, 400, 512)
 elif len(sys.argv) > 1 and sys.argv[1] == "2cta":
-    CONFIGS = [("2cta", {}), ("1cta", {"ATSPEED_GEMM_2CTA": "0"})]
-    TS = (220, 300, 400, 512)
+    CONFIGS = [("2cta>256", {}), ("2cta>128", {"ATSPEED_GEMM_2CTA_MIN": "128"}), ("2cta>64", {"ATSPEED_GEMM_2CTA_MIN": "64"}),
+               ("2cta>0", {"ATSPEED_GEMM_2CTA_MIN": "0"})]
+    TS = (10, 50, 90, 130, 220, 256)
 elif len(sys.argv) > 1 and sys.argv[1] == "chains":
     CONFIGS = [("default", {}), ("c1 b2", {"ATSPEED_GEMM_CHAINS": "1", "ATSPEED_GEMM_BUFS": "2"}),
                ("c2 b1", {"ATSPEED_GEMM_CHAINS": "2", "ATSPEED_GEMM_BUFS": "1"}),

@@ -14,7 +14,7 @@ python tools/one_user.py --cohort 8 --users 8 > gpurun_out/plain_c_$TAG.log 2>&1
 ncu --metrics gpu__time_duration.sum,launch__grid_size --clock-control none -s 2600 -c 2700 --csv --log-file gpurun_out/launches_cohort_$TAG.csv \
     python tools/one_user.py --cohort 8 --users 8 > gpurun_out/ncu_list_c_$TAG.log 2>&1; echo "ncu list cohort rc=$?"
 # full captures on the cohort path (second pass): GEMMs of 3 layers of a large forward, attention, row-wise, kernels (a)/(b)/(c)
-ncu --set full --clock-control none --import-source on -k regex:gemm_wx -s 1330 -c 12 -f -o gpurun_out/prof_gemm_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:gemm_wx -s 1330 -c 16 -f -o gpurun_out/prof_gemm_$TAG \
     python tools/one_user.py --cohort 8 --users 8 > gpurun_out/ncu_gemm_$TAG.log 2>&1; echo "ncu gemm rc=$?"
 ncu --set full --clock-control none --import-source on -k "regex:tree_attention|mask_logsoftmax|kv_gather|cohort_verify|cohort_select|residual_rmsnorm|qkv_rope|silu_mul" \
     -s 2200 -c 40 -f -o gpurun_out/prof_small_$TAG python tools/one_user.py --cohort 8 --users 8 > gpurun_out/ncu_small_$TAG.log 2>&1; echo "ncu small rc=$?"
