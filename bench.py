@@ -484,8 +484,21 @@ def hf_baseline(a, ds, fn, dev, users):
                     "(users_per_s = 1 / p50 latency)"}
 
 
+def arm_watchdog(seconds):
+    """A hung GPU must not hang the caller: abort the process (torchrun then stops the other ranks) after `seconds`."""
+    def fire():
+        sys.stderr.write("bench.py watchdog: no result after %d s, aborting\n" % seconds)
+        sys.stderr.flush()
+        os._exit(17)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     a = parse()
+    arm_watchdog(900)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

@@ -27,17 +27,26 @@ def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut):
         assert rc == 0, lib.atspeed_last_error()
         BM, KB, tiles, U, grid, max_slices, stages, tmem, bufs, T_pad = (int(info[i]) for i in range(10))
         tl = [int(info[10 + i]) for i in range(3)]
+        two_cta, n_mma, N_mma = (int(info[i]) for i in (13, 14, 15))
         assert BM in (128, 256) and KB == -(-K // 64) and T_pad == -(-T // 16) * 16
         assert tiles == sum(-(-x // BM) for x in rows) == sum(tl)
         units = tiles * KB
-        assert grid <= sms or not cut        # persistent: at most one CTA per SM when tiles may be cut
-        assert (grid - 1) * U < units <= grid * U, "every CTA owns at least one unit and the ranges cover all units"
+        assert two_cta == int(T_pad > 256), "the CTA-pair kernel serves exactly the forwards of more than 256 tokens"
+        n_workers = grid // 2 if two_cta else grid          # CTAs, or CTA pairs, that own a unit range
+        assert (n_workers - 1) * U < units <= n_workers * U, "every worker owns at least one unit and the ranges cover all units"
         assert 2 <= stages <= 12 and tmem <= 512 and tmem & (tmem - 1) == 0
-        assert stages * (BM * 128 + T_pad * 128) <= 220 * 1024
-        assert (BM // 128) * bufs * T_pad <= 512
+        if two_cta:
+            assert BM == 256 and grid % 2 == 0 and (grid <= sms or not cut)
+            assert n_mma in (1, 2) and N_mma % 32 == 0 and N_mma <= 256 and n_mma * N_mma >= T > n_mma * N_mma - 64
+            assert stages * (16384 + (n_mma * N_mma // 2) * 128) + 16384 <= 220 * 1024
+            assert bufs * n_mma * N_mma <= 512
+        else:
+            assert grid <= sms or not cut        # persistent: at most one CTA per SM when tiles may be cut
+            assert stages * (BM * 128 + T_pad * 128) + 16384 <= 220 * 1024
+            assert (BM // 128) * bufs * T_pad <= 512
         if not cut:
             assert U % KB == 0 and max_slices == 1
-        # slices per column == number of CTA ranges [c*U, (c+1)*U) that intersect the tile's units [t*KB, (t+1)*KB)
+        # slices per column == number of unit ranges [c*U, (c+1)*U) that intersect the tile's units [t*KB, (t+1)*KB)
         slices = np.frombuffer(sl, dtype=np.int32)
         col, t = 0, 0
         worst = 0
@@ -51,3 +60,26 @@ def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut):
                 t += 1
             col += w
         assert worst == max_slices
+
+
+def test_every_token_count_has_a_sane_plan():
+    """All T in 1..512 for the 7B and 68M projection shapes (cohort forwards pack arbitrary token counts): unit ranges
+    tile the work, rings fit in shared memory, accumulators fit in TMEM."""
+    from atspeed_b200 import _lib
+    lib = _lib.load()
+    shapes = {"qkv": (4096, (4096, 4096, 4096)), "o": (4096, (4096,)), "gu": (4096, (11008, 11008)), "down": (11008, (4096,)),
+              "lm": (4096, (32859,)), "dqkv": (768, (768, 768, 768)), "do": (768, (768,)), "dgu": (768, (3072, 3072)),
+              "ddown": (3072, (768,)), "dlm": (768, (33014,))}
+    info = (C.c_int32 * 16)()
+    for name, (K, rows) in shapes.items():
+        r = list(rows) + [0] * (3 - len(rows))
+        cut = 0 if name.endswith("lm") else 1
+        for T in range(1, 513):
+            assert lib.atspeed_gemm_plan(T, K, r[0], r[1], r[2], 148, cut, info, None) == 0, (name, T)
+            BM, KB, tiles, U, grid, ms, stages, tmem, bufs, T_pad, _, _, _, two, n_mma, N_mma = (int(x) for x in info)
+            units = tiles * KB
+            workers = grid // 2 if two else grid
+            assert (workers - 1) * U < units <= workers * U and grid <= 148, (name, T)
+            stage = 16384 + (n_mma * N_mma // 2) * 128 if two else BM * 128 + T_pad * 128
+            assert 2 <= stages and stages * stage + 16384 + 1024 <= 226 * 1024, (name, T)
+            assert tmem <= 512 and (bufs * n_mma * N_mma <= 512 if two else (BM // 128) * bufs * T_pad <= 512), (name, T)
