@@ -35,6 +35,16 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+T_START = time.perf_counter()
+STATE = {"rank": int(os.environ.get("RANK", 0)), "phase": "start", "t_phase": T_START, "partial": None}
+
+
+def log(phase):
+    """Progress breadcrumb on stderr (rank, seconds since start, phase): a stalled multi-GPU run shows where it stopped."""
+    STATE["phase"], STATE["t_phase"] = phase, time.perf_counter()
+    sys.stderr.write("[bench r%d +%.1fs] %s\n" % (STATE["rank"], time.perf_counter() - T_START, phase))
+    sys.stderr.flush()
+
 SHAPES = {"7b": dict(hidden=4096, n_layers=32, n_heads=32, mlp=11008),
           "68m": dict(hidden=768, n_layers=2, n_heads=12, mlp=3072),
           "small": dict(hidden=256, n_layers=2, n_heads=4, mlp=512),
@@ -106,6 +116,8 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
+        if self.index is None:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -213,9 +225,11 @@ def reference_arm(a, rank):
     models = cpu_models(a, ds.vocab_size)
     users = list(range(ds.n_users))
     for w in range(a.warmup):
+        log("reference arm (CPU oracle port): warm-up user %d" % w)
         cpu_one_user(a, models, ds, fn, users[w % len(users)])
     t0 = time.perf_counter()
     for s in range(a.steps):
+        log("reference arm (CPU oracle port): timed user %d" % s)
         cpu_one_user(a, models, ds, fn, users[(a.warmup + s) % len(users)])
     dt = time.perf_counter() - t0
     val = a.steps / dt
@@ -242,6 +256,7 @@ def atspeed_arm(a, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    log("setup: models, sessions, prompts")
     ds = load_dataset(a.dataset)
     V = ds.vocab_size
     fn = make_fn(ds, a.constraint)
@@ -309,7 +324,7 @@ def atspeed_arm(a, rank, world, local_rank):
     lane_tok = [torch.zeros((U + n_lanes - 1) // n_lanes, a.K, _lib.MAX_NEW, dtype=torch.int32, device=dev) for _ in range(n_lanes)]
     lane_sc = [torch.zeros((U + n_lanes - 1) // n_lanes, a.K, dtype=torch.float32, device=dev) for _ in range(n_lanes)]
 
-    def step_device(s):
+    def step_device(s, trace=False):
         if a.cohort > 1:
             def fn(ss, l, idx):
                 cat, lens = cat_dev[(s, l)]
@@ -320,8 +335,13 @@ def atspeed_arm(a, rank, world, local_rank):
             def fn(ss, l, idx):
                 return [ss.bssd_device(prompts_dev[step_users[s][i]], a.gamma, tok_dev[i], sc_dev[i]) for i in idx]
         sts = on_lanes(fn, s)
+        if trace:
+            log("  step %d: searches of this rank done" % s)
         if world > 1:   # the one collective of the path: ranked lists of every rank, over NVLink
             dist.all_gather(gathered, tok_dev)
+            if trace:
+                torch.cuda.synchronize(dev)
+                log("  step %d: all-gather done" % s)
         return (sum(st["kernel_launches"] for st in sts), sum(st["total_accept_steps"] for st in sts),
                 sum(st["n_run"] for st in sts))
 
@@ -348,11 +368,15 @@ def atspeed_arm(a, rank, world, local_rank):
 
     # ---- device-resident pass (value) ----
     for s in range(a.warmup):
-        step_device(s)
+        log("device pass: warm-up step %d" % s)
+        step_device(s, trace=True)
+    log("device pass: barrier before the timed region")
     barrier()
+    log("device pass: timed region (%d steps)" % a.steps)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = accept = runs = 0
-    with ClockSampler(local_rank) as clocks:
+    # clocks are reported for rank 0's GPU only: one nvidia-smi poller per box, not one per rank
+    with ClockSampler(local_rank if rank == 0 else None) as clocks:
         ev0.record()
         for s in range(a.warmup, n_steps_total):
             l, ac, rn = step_device(s)
@@ -363,10 +387,22 @@ def atspeed_arm(a, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    users_total = world * U * a.steps
+    base = {"metric": "topk_recs_per_sec", "value": users_total / (ms_total * 1e-3), "unit": "users/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (13.5 GB of weights streamed per forward)",
+                       "parallelism": f"user-sharded x{world}, one all-gather of ranked lists per step",
+                       "gemm_pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "1") != "0"},
+            "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "accepted_tokens_per_verify": accept * a.K / max(1, runs)}
+    STATE["partial"] = dict(base)          # what the watchdog prints if a later phase stalls
+    log("device pass done: %.1f users/s; host-buffer pass: warm-up" % base["value"])
     # ---- host-buffer pass (e2e) ----
     for s in range(min(a.warmup, 1)):
         step_host(s)
     barrier()
+    log("host-buffer pass: timed region")
     t0 = time.perf_counter()
     lat = []
     for s in range(a.warmup, n_steps_total):
@@ -375,6 +411,7 @@ def atspeed_arm(a, rank, world, local_rank):
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    log("host-buffer pass done; single-search latency")
     # single-search latency (nothing else in flight on the GPU): what one user waits for
     lat1 = []
     for u in step_users[a.warmup][: min(U, 8)]:
@@ -389,6 +426,7 @@ def atspeed_arm(a, rank, world, local_rank):
     # ---- profiled pass (roofline of the dominant kernel, share of step per kernel group) ----
     roofline, groups = None, None
     if rank == 0:
+        log("profiled pass (per-launch CUDA events)")
         sess.profile(True)
         if a.cohort > 1:
             a.profile_users = len(cat_dev[(a.warmup, 0)][1])
@@ -421,23 +459,17 @@ def atspeed_arm(a, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": g["bytes"] / max(1, g["launches"]),
                          "flops_per_launch": g["flops"] / max(1, g["launches"]),
                          "roofline_time_frac": max(t_hbm, t_tensor) / sec if sec else 0.0})
-    users_total = world * U * a.steps
-    out = {"metric": "topk_recs_per_sec", "value": users_total / (ms_total * 1e-3), "unit": "users/s", "n_gpus": world,
-           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (13.5 GB of weights streamed per forward)",
-                      "parallelism": f"user-sharded x{world}, one all-gather of ranked lists per step"},
-           "clocks": clocks.summary(),
-           "e2e": {"value": users_total / float(e2e_s.item()), "unit": "users/s", "h2d_bytes_per_step": h2d,
-                   "d2h_bytes_per_step": d2h},
-           "gpu_launches": int(launches),
-           "latency_ms_p50": float(np.percentile(np.asarray(lat1) * 1e3, 50)),
-           "latency_ms_p95": float(np.percentile(np.asarray(lat1) * 1e3, 95)),
-           "latency_ms_p50_loaded": float(np.percentile(np.asarray(lat) * 1e3, 50)),
-           "accepted_tokens_per_verify": accept * a.K / max(1, runs),
-           "kernel_groups": groups, "roofline": roofline}
+    out = dict(base)
+    out.update({"e2e": {"value": users_total / float(e2e_s.item()), "unit": "users/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h},
+                "latency_ms_p50": float(np.percentile(np.asarray(lat1) * 1e3, 50)),
+                "latency_ms_p95": float(np.percentile(np.asarray(lat1) * 1e3, 95)),
+                "latency_ms_p50_loaded": float(np.percentile(np.asarray(lat) * 1e3, 50)),
+                "kernel_groups": groups, "roofline": roofline})
+    STATE["partial"] = dict(out)
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
+            log("cpu_baseline: one user through the oracle port")
             host_threads()
             models = cpu_models(a, V)
             dt, _ = cpu_one_user(a, models, ds, fn, step_users[a.warmup][0])
@@ -447,12 +479,15 @@ def atspeed_arm(a, rank, world, local_rank):
         else:
             out["cpu_baseline"] = None
         if world == 1 and a.hf_baseline_users > 0:
+            log("hf_gpu_baseline: transformers generate(num_beams=K) on the same GPU")
             try:
                 out["hf_gpu_baseline"] = hf_baseline(a, ds, fn, dev, step_users[a.warmup][: a.hf_baseline_users])
                 out["hf_gpu_baseline"]["speedup_e2e"] = out["e2e"]["value"] / out["hf_gpu_baseline"]["users_per_s"]
             except Exception as e:   # informative only: never fail the bench line on the comparison arm
                 out["hf_gpu_baseline"] = {"error": repr(e)[:200]}
-        print(json.dumps(out))
+        STATE["partial"] = None
+        print(json.dumps(out), flush=True)
+    log("done")
 
 
 def hf_baseline(a, ds, fn, dev, users):
@@ -484,38 +519,96 @@ def hf_baseline(a, ds, fn, dev, users):
                     "(users_per_s = 1 / p50 latency)"}
 
 
-def arm_watchdog(seconds):
-    """A hung GPU must not hang the caller: abort the process (torchrun then stops the other ranks) after `seconds`."""
-    def fire():
-        sys.stderr.write("bench.py watchdog: no result after %d s, aborting\n" % seconds)
+def arm_watchdog(total_s, stall_s):
+    """A stalled GPU or collective must not hang the caller.  When the run exceeds `total_s`, or no phase breadcrumb has been
+    written for `stall_s`, every thread's Python stack goes to stderr (where did the host stop?), rank 0 prints what it has
+    measured so far -- marked incomplete -- and the process exits (torchrun then stops the other ranks)."""
+    def fire(why):
+        import faulthandler
+        sys.stderr.write("bench.py watchdog [r%d]: %s; last phase: %s\n" % (STATE["rank"], why, STATE["phase"]))
+        try:
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        except Exception:
+            pass
         sys.stderr.flush()
+        part = STATE.get("partial")
+        if part is not None:      # set on every rank once the device-resident pass is through
+            if STATE["rank"] == 0:
+                part["incomplete"] = "stalled in phase '%s'; keys measured after it are absent" % STATE["phase"]
+                print(json.dumps(part), flush=True)
+            os._exit(0)
         os._exit(17)
-    t = threading.Timer(seconds, fire)
-    t.daemon = True
+
+    def watch():
+        while True:
+            time.sleep(2.0)
+            now = time.perf_counter()
+            if now - T_START > total_s:
+                fire("no result after %d s" % total_s)
+            if now - STATE["t_phase"] > stall_s:
+                fire("no progress for %d s" % stall_s)
+
+    t = threading.Thread(target=watch, daemon=True)
     t.start()
     return t
 
 
+def multi_gpu_env(world):
+    """Conservative settings for N > 1 (only defaults: anything the caller exports wins).
+      * the one collective moves ~12 KB per step, so NVSwitch multicast (NVLS) buys nothing: leave its set-up out of the
+        communicator's initialisation;
+      * the CTA-pair GEMM (cta_group::2, T > 256) has only been validated in single-process runs -- the only verified
+        multi-GPU run (2 GPUs, profiles/r01_bench_n2.json) used the single-CTA kernel for every T, and the two 8-GPU
+        attempts that included the pair kernel did not finish.  Until that is understood the
+        multi-GPU bench runs the configuration that is known to work; the line says so in config.gemm_pair_kernel."""
+    if world > 1:
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("ATSPEED_GEMM_2CTA", "0")
+
+
 def main():
     a = parse()
-    arm_watchdog(900)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    gpu_multi = world > 1 and a.impl != "reference"
+    arm_watchdog(int(os.environ.get("ATSPEED_BENCH_WATCHDOG_S", 600 if gpu_multi else 900)),
+                 int(os.environ.get("ATSPEED_BENCH_STALL_S", 240 if gpu_multi else 600)))
     if a.impl == "reference":
         reference_arm(a, rank)
         return
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
+    multi_gpu_env(world)
     try:
-        atspeed_arm(a, rank, world, local_rank)
-    finally:
         if world > 1:
+            import datetime
             import torch.distributed as dist
-            dist.destroy_process_group()
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            log("init_process_group(nccl), world %d" % world)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=900))
+            torch.cuda.set_device(local_rank)
+            log("communicator up; first collective (barrier)")
+            dist.barrier()
+            torch.cuda.synchronize()
+            log("barrier done")
+        atspeed_arm(a, rank, world, local_rank)
+    except BaseException:
+        # fail fast and loudly: a rank that raises must not sit in destroy_process_group while its peers wait in a collective
+        import traceback
+        sys.stderr.write("bench.py [r%d] failed in phase '%s':\n%s" % (rank, STATE["phase"], traceback.format_exc()))
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(1)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        # every rank has passed its last collective and rank 0 has printed: tear the communicator down, but never let the
+        # teardown (which can wait on peers that are still profiling) keep the process alive
+        import torch.distributed as dist
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(30.0)
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,57 @@
+"""CPU tests of bench.py's process plumbing (no GPU work): the watchdog that turns a stalled run into stack dumps plus
+whatever was measured, the conservative multi-GPU environment defaults, and the reference arm's rank gating."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(code, env=None, timeout=120):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=e, capture_output=True, text=True, timeout=timeout)
+
+
+def test_watchdog_prints_partial_result_and_stacks():
+    r = _run("import time, bench\n"
+             "bench.STATE['partial'] = {'metric': 'topk_recs_per_sec', 'value': 1.5}\n"
+             "bench.log('host-buffer pass: timed region')\n"
+             "bench.arm_watchdog(100, 1)\n"
+             "time.sleep(30)\n")
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["value"] == 1.5 and "host-buffer pass" in line["incomplete"]
+    assert "watchdog [r0]: no progress for 1 s" in r.stderr and "File" in r.stderr      # faulthandler stack dump
+
+
+def test_watchdog_without_a_measurement_fails_the_run():
+    r = _run("import time, bench\nbench.arm_watchdog(1, 100)\ntime.sleep(30)\n")
+    assert r.returncode == 17 and r.stdout.strip() == "" and "no result after 1 s" in r.stderr
+
+
+def test_watchdog_other_ranks_stay_silent():
+    r = _run("import time, bench\nbench.STATE['partial'] = {'value': 2}\nbench.arm_watchdog(1, 100)\ntime.sleep(30)\n",
+             env={"RANK": "3"})
+    assert r.returncode == 0 and r.stdout.strip() == "" and "watchdog [r3]" in r.stderr
+
+
+def test_multi_gpu_env_defaults_do_not_override_the_caller():
+    r = _run("import os, bench\n"
+             "bench.multi_gpu_env(1)\n"
+             "assert 'ATSPEED_GEMM_2CTA' not in os.environ and 'NCCL_NVLS_ENABLE' not in os.environ\n"
+             "bench.multi_gpu_env(8)\n"
+             "assert os.environ['ATSPEED_GEMM_2CTA'] == '0' and os.environ['NCCL_NVLS_ENABLE'] == '0'\n"
+             "os.environ['ATSPEED_GEMM_2CTA'] = '1'\n"
+             "bench.multi_gpu_env(8)\n"
+             "assert os.environ['ATSPEED_GEMM_2CTA'] == '1'\n",
+             env={k: "" for k in ()})
+    assert r.returncode == 0, r.stderr
+
+
+def test_reference_arm_runs_on_rank_0_only():
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
