@@ -438,7 +438,11 @@ def atspeed_arm(a, rank, world, local_rank):
         sess.profile(False)
         tot = sum(v["ms"] for v in prof.values())
         groups = {k: {"ms_per_user": v["ms"] / max(1, a.profile_users), "launches_per_user": v["launches"] / max(1, a.profile_users),
-                      "share": v["ms"] / tot if tot else 0.0} for k, v in prof.items()}
+                      "share": v["ms"] / tot if tot else 0.0,
+                      # algorithmic bytes / CUDA-event time where the runtime knows the bytes on the host (GEMMs, kernel (a):
+                      # rows x V x 4 B of fp32 logits -- L2-resident right after lm_head, so not an HBM figure)
+                      "algorithmic_gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] > 0 and v["ms"] > 0 else None}
+                  for k, v in prof.items()}
         g = prof["gemm"]
         peak, peak_tf, how = peaks()
         sec = g["ms"] * 1e-3
