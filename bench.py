@@ -567,6 +567,7 @@ def multi_gpu_env(world):
         multi-GPU bench runs the configuration that is known to work; the line says so in config.gemm_pair_kernel."""
     if world > 1:
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        os.environ.setdefault("NCCL_MNNVL_ENABLE", "0")      # one box: no multi-node NVLink / IMEX probing either
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         os.environ.setdefault("ATSPEED_GEMM_2CTA", "0")
 
