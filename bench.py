@@ -75,6 +75,8 @@ def parse():
     ap.add_argument("--cohort-tokens", type=int, default=512, help="most tokens one cohort forward packs (256..512)")
     ap.add_argument("--do-sample", action="store_true", help="AtSpeed-R relaxed acceptance (configs[2]) instead of AtSpeed-S")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shard", default=None, metavar="R/W",
+                    help="diagnostic: on ONE GPU, process the user slice rank R of W would get (no collective), e.g. 0/8")
     ap.add_argument("--hf-baseline-users", type=int, default=5,
                     help="also time HF generate(num_beams=K) on the same GPU (N=1 only; 0 = skip)")
     return ap.parse_args()
@@ -280,6 +282,9 @@ def atspeed_arm(a, rank, world, local_rank):
     pool = ThreadPoolExecutor(n_lanes)
     U = a.users_per_step
     mine = shard_users(list(range(ds.n_users)), rank, world)
+    if a.emulate_shard and world == 1:
+        er, ew = (int(x) for x in a.emulate_shard.split("/"))
+        mine = shard_users(list(range(ds.n_users)), er, ew)
     n_steps_total = a.warmup + a.steps
     step_users = [[mine[(s * U + i) % len(mine)] for i in range(U)] for s in range(n_steps_total)]
     prompts_host = {u: ds.prompt_ids(u) for us in step_users for u in us}
