@@ -55,3 +55,39 @@ def test_reference_arm_runs_on_rank_0_only():
                        cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), capture_output=True,
                        text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+STUB = os.path.join(ROOT, "tests", "helpers", "bench_flow_stub.py")
+KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+        "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "kernel_groups", "cpu_baseline")
+
+
+def test_bench_control_flow_single_process():
+    """bench.py's own sequencing (phases, JSON keys) with the CUDA session stubbed out: catches a broken bench line on CPU."""
+    for extra in ([], ["--cohort", "1", "--lanes", "2"]):
+        r = subprocess.run([sys.executable, STUB, "--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--hf-baseline-users", "0"]
+                           + extra, cwd=ROOT, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
+        assert line["n_gpus"] == 1 and line["config"]["gemm_pair_kernel"] is True and "incomplete" not in line
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+        assert "device pass: timed region" in r.stderr and "done" in r.stderr
+
+
+def test_bench_control_flow_two_ranks_gloo():
+    """The N = 2 launch exactly as the driver does it (torchrun), NCCL replaced by gloo: every rank walks the same collectives,
+    rank 0 alone prints ONE line, the conservative multi-GPU defaults are in force, and every process exits 0."""
+    env = {k: v for k, v in os.environ.items() if k not in ("ATSPEED_GEMM_2CTA", "NCCL_NVLS_ENABLE")}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29677", STUB, "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["config"]["gemm_pair_kernel"] is False and line["cpu_baseline"] is None
+    assert line["gpu_launches"] > 0 and line["scaling"] == "weak"
+    for rank in (0, 1):
+        assert f"[bench r{rank} " in r.stderr and "all-gather done" in r.stderr
