@@ -218,6 +218,7 @@ def _probe(fn, prompt, depth: int, budget: int) -> CSRTrie:
 
 
 _CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_UNCONSTRAINED: dict = {}
 
 
 def compile_constraint(fn: Optional[Callable], prompt: Sequence[int], depth: int,
@@ -226,8 +227,17 @@ def compile_constraint(fn: Optional[Callable], prompt: Sequence[int], depth: int
     """Compile `fn` for `depth` generated tokens. `fn=None` (no constraint) needs `vocab_size` and
     yields one node per depth allowing every token."""
     if fn is None:
-        assert vocab_size is not None
-        return csr_from_positional({d: range(vocab_size) for d in range(depth)}, depth)
+        # cached per (V, depth): callers key device tries and sessions on the table's identity (beamSD.get_session), so a
+        # fresh table per call would build a fresh multi-GB session per search
+        if vocab_size is None:
+            raise ValueError("compile_constraint(None, ...) needs vocab_size")
+        key = (int(vocab_size), int(depth))
+        if not use_cache or key not in _UNCONSTRAINED:
+            csr = csr_from_positional({d: range(vocab_size) for d in range(depth)}, depth)
+            if not use_cache:
+                return csr
+            _UNCONSTRAINED[key] = csr
+        return _UNCONSTRAINED[key]
     if use_cache:
         try:
             hit = _CACHE.get(fn, {}).get(depth)

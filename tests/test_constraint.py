@@ -93,3 +93,15 @@ def test_prompt_dependent_constraint_is_rejected():
     other = next(ds.prompt_ids(u) for u in range(1, 50) if ds.prompt_ids(u)[40] % 7 != p0[40] % 7)
     with pytest.raises(ValueError):
         compile_constraint(fn, p0, 2, other_prompt=other, use_cache=False)
+
+
+def test_unconstrained_table_is_cached_per_vocab_and_depth():
+    """beamSD.get_session keys device tries and sessions on the table's identity: `prefix_allowed_tokens_fn=None` must not
+    produce a fresh table (hence a fresh multi-GB session) per search."""
+    from atspeed_b200.constraint import compile_constraint
+    a = compile_constraint(None, [1, 2, 3], 2, vocab_size=300)
+    b = compile_constraint(None, [9], 2, vocab_size=300)
+    assert a is b and a.n_edges == 600
+    assert compile_constraint(None, [9], 3, vocab_size=300) is not a
+    assert compile_constraint(None, [9], 2, vocab_size=301) is not a
+    assert compile_constraint(None, [9], 2, vocab_size=300, use_cache=False) is not a
