@@ -350,6 +350,8 @@ def atspeed_arm(a, rank, world, local_rank):
         return (sum(st["kernel_launches"] for st in sts), sum(st["total_accept_steps"] for st in sts),
                 sum(st["n_run"] for st in sts))
 
+    host_lists = {}
+
     def step_host(s):
         if a.cohort > 1:
             def fn(ss, l, idx):
@@ -366,8 +368,14 @@ def atspeed_arm(a, rank, world, local_rank):
                     out.append((time.perf_counter() - t0, o["tokens"]))
                 return out
         res = on_lanes(fn, s)
+        # ranked lists of the step as one fixed-shape block (a user with fewer than K beams is padded with zeros)
+        block = np.zeros((U, a.K, 4), dtype=np.int32)
+        order = [i for l in range(n_lanes) for i in range(l, U, n_lanes)]       # on_lanes returns lane-major
+        for i, (_, toks) in zip(order, res):
+            block[i, : toks.shape[0], : toks.shape[1]] = toks[: a.K, :4]
+        host_lists[s] = block
         if world > 1:
-            t = torch.from_numpy(np.stack([x[1] for x in res])).to(dev)
+            t = torch.from_numpy(block).to(dev)
             dist.all_gather([torch.empty_like(t) for _ in range(world)], t)
         return [x[0] for x in res]
 
@@ -388,6 +396,7 @@ def atspeed_arm(a, rank, world, local_rank):
             launches += l; accept += ac; runs += rn
         ev1.record()
         barrier()
+    dev_lists_last = tok_dev.cpu().numpy()[:, :, :4].copy()          # device-resident pass, last timed step
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -416,7 +425,17 @@ def atspeed_arm(a, rank, world, local_rank):
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    log("host-buffer pass done; single-search latency")
+    # integrity: the host-buffer pass re-runs the same users in the same cohorts, so its ranked lists must be the
+    # device-resident pass's, bit for bit (a difference would mean a race between lanes / streams)
+    try:
+        if a.do_sample:         # every search draws its own noise stream: the two passes are different samples
+            consistency = {"skipped": "sampling mode"}
+        else:
+            same = int((host_lists[n_steps_total - 1] == dev_lists_last).all(axis=(1, 2)).sum())
+            consistency = {"users_compared": U, "identical_ranked_lists": same}
+    except Exception as e:      # informative only
+        consistency = {"error": repr(e)[:200]}
+    log("host-buffer pass done (%s); single-search latency" % consistency)
     # single-search latency (nothing else in flight on the GPU): what one user waits for
     lat1 = []
     for u in step_users[a.warmup][: min(U, 8)]:
@@ -474,6 +493,7 @@ def atspeed_arm(a, rank, world, local_rank):
                 "latency_ms_p50": float(np.percentile(np.asarray(lat1) * 1e3, 50)),
                 "latency_ms_p95": float(np.percentile(np.asarray(lat1) * 1e3, 95)),
                 "latency_ms_p50_loaded": float(np.percentile(np.asarray(lat) * 1e3, 50)),
+                "pass_consistency": consistency,
                 "kernel_groups": groups, "roofline": roofline})
     STATE["partial"] = dict(out)
     if rank == 0:
