@@ -435,7 +435,11 @@ def atspeed_arm(a, rank, world, local_rank):
             consistency = {"users_compared": U, "identical_ranked_lists": same}
     except Exception as e:      # informative only
         consistency = {"error": repr(e)[:200]}
-    log("host-buffer pass done (%s); single-search latency" % consistency)
+    h2d = int(np.mean([sum(len(prompts_host[u]) * 4 for u in step_users[s]) for s in range(a.warmup, n_steps_total)]))
+    d2h = U * (a.K * 4 * 4 + a.K * 4) + int(round(runs / max(a.steps, 1))) * 64
+    e2e = {"value": users_total / float(e2e_s.item()), "unit": "users/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    STATE["partial"] = dict(base, e2e=e2e, pass_consistency=consistency)
+    log("host-buffer pass done: %.1f users/s (%s); single-search latency" % (e2e["value"], consistency))
     # single-search latency (nothing else in flight on the GPU): what one user waits for
     lat1 = []
     for u in step_users[a.warmup][: min(U, 8)]:
@@ -445,8 +449,6 @@ def atspeed_arm(a, rank, world, local_rank):
         else:
             sess.bssd(prompts_host[u], a.gamma)
         lat1.append(time.perf_counter() - t0)
-    h2d = int(np.mean([sum(len(prompts_host[u]) * 4 for u in step_users[s]) for s in range(a.warmup, n_steps_total)]))
-    d2h = U * (a.K * 4 * 4 + a.K * 4) + int(round(runs / max(a.steps, 1))) * 64
     # ---- profiled pass (roofline of the dominant kernel, share of step per kernel group) ----
     roofline, groups = None, None
     if rank == 0:
@@ -488,8 +490,7 @@ def atspeed_arm(a, rank, world, local_rank):
                          "flops_per_launch": g["flops"] / max(1, g["launches"]),
                          "roofline_time_frac": max(t_hbm, t_tensor) / sec if sec else 0.0})
     out = dict(base)
-    out.update({"e2e": {"value": users_total / float(e2e_s.item()), "unit": "users/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h},
+    out.update({"e2e": e2e,
                 "latency_ms_p50": float(np.percentile(np.asarray(lat1) * 1e3, 50)),
                 "latency_ms_p95": float(np.percentile(np.asarray(lat1) * 1e3, 95)),
                 "latency_ms_p50_loaded": float(np.percentile(np.asarray(lat) * 1e3, 50)),
@@ -520,6 +521,10 @@ def atspeed_arm(a, rank, world, local_rank):
                 out["hf_gpu_baseline"] = {"error": repr(e)[:200]}
         STATE["partial"] = None
         print(json.dumps(out), flush=True)
+    if world > 1:
+        # nobody tears its communicator down while rank 0 is still in its profiled pass
+        log("final barrier")
+        barrier()
     log("done")
 
 
