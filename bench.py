@@ -521,6 +521,7 @@ def atspeed_arm(a, rank, world, local_rank):
                 out["hf_gpu_baseline"] = {"error": repr(e)[:200]}
         STATE["partial"] = None
         print(json.dumps(out), flush=True)
+        STATE["printed"] = True
     if world > 1:
         # nobody tears its communicator down while rank 0 is still in its profiled pass
         log("final barrier")
@@ -569,6 +570,8 @@ def arm_watchdog(total_s, stall_s):
         except Exception:
             pass
         sys.stderr.flush()
+        if STATE.get("printed"):      # the result line is out; only the teardown stalled
+            os._exit(0)
         part = STATE.get("partial")
         if part is not None:      # set on every rank once the device-resident pass is through
             if STATE["rank"] == 0:
