@@ -18,7 +18,8 @@ precision = "bf16": weights are bf16-representable and activations are rounded t
     apply_rotary_pos_emb, after SiLU, after the gate*up product, after each residual add); GEMMs and
     the softmax accumulate in fp32.  Logits are returned in fp32 WITHOUT a final bf16 rounding
     unless round_logits=True (transformers 4.41 rounds them to bf16 and upcasts, SURVEY hard part 3).
-    This is the numerical contract the CUDA forward (atspeed_b200/csrc/forward.cu) is built to.
+    This is the numerical contract the CUDA forward (atspeed_b200/csrc/engine.cu `forward`: gemm.cu, elementwise.cu,
+    attention.cu) is built to.
 """
 from __future__ import annotations
 
