@@ -20,6 +20,11 @@ per second over the whole job ("users/s").
 
 Ranks shard users (rank r takes users r, r+W, ...); the only collective is one all-gather of the ranked
 lists per step.  `--impl reference` times the CPU oracle port alone (rank 0 only).
+
+Also on the line: `pass_consistency` (the host-buffer pass re-runs the device-resident pass's last step: the ranked lists
+must be identical), `kernel_groups` (share of a user's GPU time and algorithmic GB/s per kernel family), `hf_gpu_baseline`
+(transformers generate(num_beams=K) on the same GPU, N = 1).  stderr carries phase breadcrumbs; a watchdog ends a stalled
+run with every thread's stack and the partial result (`"incomplete"`), see DESIGN.md section 6.
 """
 import argparse
 import json
