@@ -896,7 +896,7 @@ int atspeed_gemm_plan(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_
     GemmPlan pl;
     ATS_TRY(gemm_make_plan(g, T, num_sms, allow_cut != 0, &pl));
     const int v[16] = {pl.BM, pl.KB, pl.total_tiles, pl.U, pl.grid, pl.max_slices, pl.stages, pl.tmem_cols, pl.n_bufs, pl.T_pad,
-                       pl.tiles[0], pl.tiles[1], pl.tiles[2], pl.two_cta, pl.n_mma, pl.N_mma};
+                       pl.tiles[0], pl.tiles[1], pl.tiles[2], pl.two_cta + pl.four_cta, pl.n_mma, pl.N_mma};   // [13]: 0 single CTA, 1 pair, 2 cluster of 4
     for (int i = 0; i < 16; ++i) info16[i] = v[i];
     if (slices_of_col) {
         const SplitMap sm = gemm_split_map(g, pl);

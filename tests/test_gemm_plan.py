@@ -83,3 +83,48 @@ def test_every_token_count_has_a_sane_plan():
             stage = 16384 + (n_mma * N_mma // 2) * 128 if two else BM * 128 + T_pad * 128
             assert 2 <= stages and stages * stage + 16384 + 1024 <= 226 * 1024, (name, T)
             assert tmem <= 512 and (bufs * n_mma * N_mma <= 512 if two else (BM // 128) * bufs * T_pad <= 512), (name, T)
+
+
+def test_experimental_4cta_plans(monkeypatch):
+    """ATSPEED_GEMM_4CTA=1 (off by default): clusters of four CTAs own 512-row tile groups.  Same invariants as
+    the other kernels -- cluster unit ranges tile the work, slice counts per column agree with the SplitMap arithmetic the
+    consumers use, rings and accumulators fit -- plus the quarter-box constraints of the multicast activation loads."""
+    from atspeed_b200 import _lib
+    lib = _lib.load()
+    info = (C.c_int32 * 16)()
+    shapes = [(4096, (4096, 4096, 4096)), (4096, (4096,)), (4096, (11008, 11008)), (11008, (4096,)), (4096, (32859,)),
+              (768, (768, 768, 768)), (3072, (768,)), (768, (33014,)), (192, (200, 72))]
+    monkeypatch.delenv("ATSPEED_GEMM_4CTA", raising=False)
+    assert lib.atspeed_gemm_plan(300, 4096, 4096, 0, 0, 148, 1, info, None) == 0 and info[13] == 1      # default: the pair kernel
+    monkeypatch.setenv("ATSPEED_GEMM_4CTA", "1")
+    for K, rows in shapes:
+        r = list(rows) + [0] * (3 - len(rows))
+        cols = sum(rows)
+        sl = (C.c_int32 * cols)()
+        for cut in (1, 0):
+            for T in (10, 256, 257, 289, 320, 390, 448, 512):
+                assert lib.atspeed_gemm_plan(T, K, r[0], r[1], r[2], 148, cut, info, sl) == 0, lib.atspeed_last_error()
+                BM, KB, tiles, U, grid, max_slices, stages, tmem, bufs, T_pad, t0, t1, t2, kind, n_mma, N_mma = (int(x) for x in info)
+                if T_pad <= 256:
+                    assert kind == 0 and BM in (128, 256)           # small forwards are untouched by the switch
+                    continue
+                assert kind == 2 and BM == 512 and grid % 4 == 0 and grid <= 148
+                assert tiles == sum(-(-x // 512) for x in rows) == t0 + t1 + t2
+                units, clusters = tiles * KB, grid // 4
+                assert (clusters - 1) * U < units <= clusters * U
+                assert n_mma in (1, 2) and N_mma % 32 == 0 and N_mma <= 256 and n_mma * N_mma >= T > n_mma * N_mma - 64
+                assert (N_mma // 4) * 128 % 1024 == 0               # a quarter box keeps the 128-byte swizzle phase
+                assert 2 <= stages and stages * (16384 + (n_mma * N_mma // 2) * 128) + 16384 + 1024 <= 226 * 1024
+                assert tmem <= 512 and bufs * n_mma * N_mma <= 512
+                if not cut:
+                    assert U % KB == 0 and max_slices == 1
+                slices = np.frombuffer(sl, dtype=np.int32)
+                col, t, worst = 0, 0, 0
+                for w in rows:
+                    for i in range(-(-w // 512)):
+                        n = ((t + 1) * KB - 1) // U - (t * KB) // U + 1
+                        worst = max(worst, n)
+                        assert (slices[col + i * 512: col + min(w, (i + 1) * 512)] == n).all()
+                        t += 1
+                    col += w
+                assert worst == max_slices
