@@ -13,12 +13,14 @@
 // < 2 GFLOP per layer, far below what would amortise a TMEM round trip; the kernel is latency-bound.
 // P is split into hi+lo bf16 parts so the PV product is accurate to ~2^-16, which keeps this kernel
 // within fp32-softmax tolerance of oracle/llama_ref.py.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace atspeed {
 
-static constexpr int ATT_BQ = 64;   // queries per CTA
+static constexpr int ATT_BQ = 64;   // queries per CTA (default); ATSPEED_ATT_BQ=32 selects the experimental 2-warp CTAs
 static constexpr int ATT_BK = 64;   // keys per tile
 static constexpr int ATT_THREADS = 128;
 
@@ -69,8 +71,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
 }
 
-template <int D>
-__global__ void __launch_bounds__(ATT_THREADS)
+// BQ = queries per CTA = 16 per warp.  BQ = 64 is the measured default; BQ = 32 (EXPERIMENTAL, ATSPEED_ATT_BQ=32, written
+// without a GPU to run it on) doubles the number of CTAs: at T ~ 300 the BQ = 64 grid is ~1 four-warp CTA per SM and the
+// kernel is latency-bound (6.8 % of peak warps active, profiles/r01_ncu_full_v3.txt); two smaller CTAs per SM interleave.
+template <int D, int BQ>
+__global__ void __launch_bounds__(BQ * 2)
 tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                       const __nv_bfloat16* __restrict__ vcache, const int* __restrict__ prefix_len,
                       const uint32_t* __restrict__ vis, int vis_base, int T, int S, int n_heads, float scale,
@@ -78,9 +83,9 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     constexpr int LDS = D + 8;                     // padded row (bf16 elements): conflict-free ldmatrix, rows 16-byte aligned
     extern __shared__ __align__(16) uint8_t att_smem[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
-    __nv_bfloat16* sKV = sQ + ATT_BQ * LDS;        // [2 buffers][K | V][ATT_BK][LDS]
-    __shared__ uint32_t sVis[ATT_BQ * VIS_WORDS];
-    __shared__ int sPl[ATT_BQ];
+    __nv_bfloat16* sKV = sQ + BQ * LDS;        // [2 buffers][K | V][ATT_BK][LDS]
+    __shared__ uint32_t sVis[BQ * VIS_WORDS];
+    __shared__ int sPl[BQ];
     __shared__ int sMaxPl;
     __shared__ uint32_t sAny[VIS_WORDS];
     __shared__ int sTiles[64];                     // key tiles some query of this CTA can see
@@ -89,18 +94,18 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     pdl_launch_dependents();
     pdl_wait();
     const int head = blockIdx.y;
-    int q0 = blockIdx.x * ATT_BQ;
+    int q0 = blockIdx.x * BQ;
     if (ckv.n > 0) {
         // cohort forward: a CTA's 64 queries belong to ONE user (own KV cache, prompt length and extent); blockIdx.x
         // enumerates the users' 64-query blocks in order
         int b = blockIdx.x, u = 0;
         for (; u < ckv.n; ++u) {
-            const int nb = (ckv.T[u] + ATT_BQ - 1) / ATT_BQ;
+            const int nb = (ckv.T[u] + BQ - 1) / BQ;
             if (b < nb) break;
             b -= nb;
         }
         if (u >= ckv.n) return;
-        q0 = ckv.tok0[u] + b * ATT_BQ;
+        q0 = ckv.tok0[u] + b * BQ;
         T = ckv.tok0[u] + ckv.T[u];            // rows >= T are padding of this user's last block
         S = ckv.S[u];
         vis_base = ckv.vis_base[u];
@@ -114,18 +119,18 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     if (threadIdx.x < VIS_WORDS) sAny[threadIdx.x] = 0;
     __syncthreads();
     // stage the Q tile with cp.async (group 0), prefix lengths and visibility words directly
-    for (int i = threadIdx.x; i < ATT_BQ * (D / 8); i += ATT_THREADS) {
+    for (int i = threadIdx.x; i < BQ * (D / 8); i += (BQ * 2)) {
         const int r = i / (D / 8), c = (i % (D / 8)) * 8;
         const bool ok = q0 + r < T;
         cp_async16(&sQ[r * LDS + c], q + static_cast<long long>(ok ? q0 + r : 0) * HD + head * D + c, ok);
     }
     cp_async_commit();
-    for (int i = threadIdx.x; i < ATT_BQ; i += ATT_THREADS) {
+    for (int i = threadIdx.x; i < BQ; i += (BQ * 2)) {
         const int pl = (q0 + i < T) ? prefix_len[q0 + i] : 0;
         sPl[i] = pl;
         atomicMax(&sMaxPl, pl);
     }
-    for (int i = threadIdx.x; i < ATT_BQ * VIS_WORDS; i += ATT_THREADS) {
+    for (int i = threadIdx.x; i < BQ * VIS_WORDS; i += (BQ * 2)) {
         const int r = i / VIS_WORDS, w = i % VIS_WORDS;
         const uint32_t v = (q0 + r < T) ? vis[static_cast<long long>(q0 + r) * VIS_WORDS + w] : 0u;
         sVis[i] = v;
@@ -152,7 +157,7 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     auto load_tile = [&](int buf, int key0) {
         __nv_bfloat16* sK = sKV + static_cast<size_t>(buf) * 2 * ATT_BK * LDS;
         __nv_bfloat16* sV = sK + ATT_BK * LDS;
-        for (int i = threadIdx.x; i < ATT_BK * (D / 8); i += ATT_THREADS) {
+        for (int i = threadIdx.x; i < ATT_BK * (D / 8); i += (BQ * 2)) {
             const int r = i / (D / 8), c = (i % (D / 8)) * 8;
             const bool ok = key0 + r < S;
             const long long off = static_cast<long long>(ok ? key0 + r : 0) * HD + head * D + c;
@@ -291,34 +296,43 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                    const BatchDesc& b, int T, int S, int n_heads, int head_dim, __nv_bfloat16* out, cudaStream_t st) {
     ATS_CHECK_ARG(T >= 1 && S >= 1, "attention: T=%d S=%d", T, S);
-    int q_blocks = (T + ATT_BQ - 1) / ATT_BQ;
+    static int bq_env = -1;       // queries per CTA: 64 unless ATSPEED_ATT_BQ=32 (experimental)
+    if (bq_env < 0) { const char* e = getenv("ATSPEED_ATT_BQ"); bq_env = (e && atoi(e) == 32) ? 32 : ATT_BQ; }
+    const int BQ = bq_env;
+    int q_blocks = (T + BQ - 1) / BQ;
     if (b.ckv.n > 0) {
         q_blocks = 0;
-        for (int u = 0; u < b.ckv.n; ++u) q_blocks += (b.ckv.T[u] + ATT_BQ - 1) / ATT_BQ;
+        for (int u = 0; u < b.ckv.n; ++u) q_blocks += (b.ckv.T[u] + BQ - 1) / BQ;
     }
     dim3 grid(q_blocks, n_heads);
     const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
-    const size_t smem = static_cast<size_t>(ATT_BQ + 4 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
-#define ATS_ATT(DD)                                                                                              \
-    do {                                                                                                         \
-        static bool attr_set = false;                                                                            \
-        if (!attr_set) {                                                                                         \
-            ATS_CUDA(cudaFuncSetAttribute(tree_attention_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          96 * 1024));                                                           \
-            attr_set = true;                                                                                     \
-        }                                                                                                        \
-        ATS_CUDA(launch_pdl(tree_attention_kernel<DD>, grid, dim3(ATT_THREADS), smem, st, q, kcache, vcache,      \
-                            b.prefix_len, b.vis, b.vis_base, T, S, n_heads, scale, out, b.ckv));                \
+    const size_t smem = static_cast<size_t>(BQ + 4 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
+#define ATS_ATT(DD, QQ)                                                                                              \
+    do {                                                                                                             \
+        static bool attr_set = false;                                                                                \
+        if (!attr_set) {                                                                                             \
+            ATS_CUDA(cudaFuncSetAttribute(tree_attention_kernel<DD, QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          96 * 1024));                                                               \
+            attr_set = true;                                                                                         \
+        }                                                                                                            \
+        ATS_CUDA(launch_pdl(tree_attention_kernel<DD, QQ>, grid, dim3(QQ * 2), smem, st, q, kcache, vcache,           \
+                            b.prefix_len, b.vis, b.vis_base, T, S, n_heads, scale, out, b.ckv));                    \
+    } while (0)
+#define ATS_ATT_BQ(DD)                 \
+    do {                               \
+        if (BQ == 32) ATS_ATT(DD, 32); \
+        else ATS_ATT(DD, 64);          \
     } while (0)
     switch (head_dim) {
-        case 16: ATS_ATT(16); break;
-        case 32: ATS_ATT(32); break;
-        case 64: ATS_ATT(64); break;
-        case 128: ATS_ATT(128); break;
+        case 16: ATS_ATT_BQ(16); break;
+        case 32: ATS_ATT_BQ(32); break;
+        case 64: ATS_ATT_BQ(64); break;
+        case 128: ATS_ATT_BQ(128); break;
         default:
             set_error("attention: head_dim=%d not in {16,32,64,128}", head_dim);
             return ATS_ERR_ARG;
     }
+#undef ATS_ATT_BQ
 #undef ATS_ATT
     return ATS_OK;
 }
