@@ -74,7 +74,10 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 // BQ = queries per CTA = 16 per warp.  BQ = 64 is the measured default; BQ = 32 (EXPERIMENTAL, ATSPEED_ATT_BQ=32, written
 // without a GPU to run it on) doubles the number of CTAs: at T ~ 300 the BQ = 64 grid is ~1 four-warp CTA per SM and the
 // kernel is latency-bound (6.8 % of peak warps active, profiles/r01_ncu_full_v3.txt); two smaller CTAs per SM interleave.
-template <int D, int BQ>
+// PLO = true (default, the tested configuration): P = hi + lo bf16 parts, the PV product is accurate to ~2^-16 as the oracle's
+// contract asks.  PLO = false (EXPERIMENTAL, ATSPEED_ATT_PLO=0, never executed): P is rounded to bf16 once -- what an HF bf16
+// module does (softmax in fp32, `.to(bf16)`, then P @ V) -- and a third of the kernel's MMAs disappear.
+template <int D, int BQ, bool PLO>
 __global__ void __launch_bounds__(BQ * 2)
 tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                       const __nv_bfloat16* __restrict__ vcache, const int* __restrict__ prefix_len,
@@ -270,9 +273,9 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
                 uint32_t b[4];
                 ldmatrix_x4_trans(b, &sV[(kk * 16 + v_row) * LDS + nb * 8 + v_col]);
                 mma_bf16_16816(o[nb], ah0, ah1, ah2, ah3, b[0], b[1]);
-                mma_bf16_16816(o[nb], al0, al1, al2, al3, b[0], b[1]);
+                if (PLO) mma_bf16_16816(o[nb], al0, al1, al2, al3, b[0], b[1]);
                 mma_bf16_16816(o[nb + 1], ah0, ah1, ah2, ah3, b[2], b[3]);
-                mma_bf16_16816(o[nb + 1], al0, al1, al2, al3, b[2], b[3]);
+                if (PLO) mma_bf16_16816(o[nb + 1], al0, al1, al2, al3, b[2], b[3]);
             }
         }
         __syncthreads();   // this buffer is refilled by the next iteration's prefetch
@@ -296,9 +299,11 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                    const BatchDesc& b, int T, int S, int n_heads, int head_dim, __nv_bfloat16* out, cudaStream_t st) {
     ATS_CHECK_ARG(T >= 1 && S >= 1, "attention: T=%d S=%d", T, S);
-    static int bq_env = -1;       // queries per CTA: 64 unless ATSPEED_ATT_BQ=32 (experimental)
+    static int bq_env = -1, plo_env = -1;   // queries per CTA: 64 unless ATSPEED_ATT_BQ=32; hi+lo P unless ATSPEED_ATT_PLO=0
     if (bq_env < 0) { const char* e = getenv("ATSPEED_ATT_BQ"); bq_env = (e && atoi(e) == 32) ? 32 : ATT_BQ; }
+    if (plo_env < 0) { const char* e = getenv("ATSPEED_ATT_PLO"); plo_env = (e && atoi(e) == 0) ? 0 : 1; }
     const int BQ = bq_env;
+    const bool plo = plo_env != 0;
     int q_blocks = (T + BQ - 1) / BQ;
     if (b.ckv.n > 0) {
         q_blocks = 0;
@@ -307,21 +312,23 @@ int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __
     dim3 grid(q_blocks, n_heads);
     const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
     const size_t smem = static_cast<size_t>(BQ + 4 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
-#define ATS_ATT(DD, QQ)                                                                                              \
-    do {                                                                                                             \
-        static bool attr_set = false;                                                                                \
-        if (!attr_set) {                                                                                             \
-            ATS_CUDA(cudaFuncSetAttribute(tree_attention_kernel<DD, QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          96 * 1024));                                                               \
-            attr_set = true;                                                                                         \
-        }                                                                                                            \
-        ATS_CUDA(launch_pdl(tree_attention_kernel<DD, QQ>, grid, dim3(QQ * 2), smem, st, q, kcache, vcache,           \
-                            b.prefix_len, b.vis, b.vis_base, T, S, n_heads, scale, out, b.ckv));                    \
+#define ATS_ATT(DD, QQ, LL)                                                                                              \
+    do {                                                                                                                 \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            ATS_CUDA(cudaFuncSetAttribute(tree_attention_kernel<DD, QQ, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          96 * 1024));                                                                   \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        ATS_CUDA(launch_pdl(tree_attention_kernel<DD, QQ, LL>, grid, dim3(QQ * 2), smem, st, q, kcache, vcache,           \
+                            b.prefix_len, b.vis, b.vis_base, T, S, n_heads, scale, out, b.ckv));                        \
     } while (0)
-#define ATS_ATT_BQ(DD)                 \
-    do {                               \
-        if (BQ == 32) ATS_ATT(DD, 32); \
-        else ATS_ATT(DD, 64);          \
+#define ATS_ATT_BQ(DD)                               \
+    do {                                             \
+        if (BQ == 32 && plo) ATS_ATT(DD, 32, true);  \
+        else if (BQ == 32) ATS_ATT(DD, 32, false);   \
+        else if (plo) ATS_ATT(DD, 64, true);         \
+        else ATS_ATT(DD, 64, false);                 \
     } while (0)
     switch (head_dim) {
         case 16: ATS_ATT_BQ(16); break;
