@@ -14,6 +14,8 @@
 // HBM-bound: algorithmic bytes = rows * V * sizeof(logit).  One CTA per row, 128-bit streaming loads
 // (ld.global.nc.L1::no_allocate) for the online max/sum-exp pass; the row's CSR children (<= 256 for
 // the item tries) are then gathered from L2 and ranked in shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -54,7 +56,10 @@ __device__ __forceinline__ MaxSum ms_merge(MaxSum a, MaxSum b) {
     return r;
 }
 
-template <typename T>
+// UNR = 128-bit loads in flight per thread in the streaming pass.  2 is the tested default; 8 (EXPERIMENTAL,
+// ATSPEED_TOPK_UNROLL=8, never executed) is for launches with fewer rows than SMs, where one 256-thread CTA per SM with
+// 8 KB in flight cannot cover the HBM latency (the sum-exp is then accumulated in chunks of 8 vectors: last-bit differences).
+template <typename T, int UNR>
 __global__ void __launch_bounds__(TOPK_THREADS)
 mask_logsoftmax_topk_kernel(const T* __restrict__ logits, int V, long long ld, const int* __restrict__ row_node,
                             const int* __restrict__ n_rows_dev, const int* __restrict__ child_off,
@@ -88,6 +93,21 @@ mask_logsoftmax_topk_kernel(const T* __restrict__ logits, int V, long long ld, c
     if (threadIdx.x < V - tail0) { float x = to_f32<T>(row[tail0 + threadIdx.x]); ms_add_chunk(acc, &x, 1); }
     const uint4* vrow = reinterpret_cast<const uint4*>(row + head);
     int i = threadIdx.x;
+    if (UNR > 2) {
+        for (; i + (UNR - 1) * TOPK_THREADS < nvec; i += UNR * TOPK_THREADS) {
+            uint4 u[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) u[j] = ld_stream_v4(vrow + i + j * TOPK_THREADS);
+            float x[UNR * EPV];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const T* e = reinterpret_cast<const T*>(&u[j]);
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) x[j * EPV + k] = to_f32<T>(e[k]);
+            }
+            ms_add_chunk(acc, x, UNR * EPV);
+        }
+    }
     for (; i + TOPK_THREADS < nvec; i += 2 * TOPK_THREADS) {     // two loads in flight per thread
         const uint4 u0 = ld_stream_v4(vrow + i), u1 = ld_stream_v4(vrow + i + TOPK_THREADS);
         float x[2 * EPV];
@@ -194,14 +214,19 @@ int mask_logsoftmax_topk(const void* logits, int logits_bf16, int rows, int V, l
                          float* cand_logp, int* cand_cnt, float* lse, cudaStream_t st) {
     ATS_CHECK_ARG(rows >= 1 && V >= 1 && B >= 1 && B <= MAX_BEAMS, "topk: rows=%d V=%d B=%d", rows, V, B);
     ATS_CHECK_ARG(ld >= V, "topk: row stride %lld < V %d", ld, V);
-    if (logits_bf16)
-        mask_logsoftmax_topk_kernel<__nv_bfloat16><<<rows, TOPK_THREADS, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(logits), V, ld, row_node, n_rows_dev, trie.child_off, trie.child_tok,
-            trie.n_nodes, B, cand_tok, cand_edge, cand_logp, cand_cnt, lse);
-    else
-        mask_logsoftmax_topk_kernel<float><<<rows, TOPK_THREADS, 0, st>>>(
-            static_cast<const float*>(logits), V, ld, row_node, n_rows_dev, trie.child_off, trie.child_tok,
-            trie.n_nodes, B, cand_tok, cand_edge, cand_logp, cand_cnt, lse);
+    static int unr_env = -1;
+    if (unr_env < 0) { const char* e = getenv("ATSPEED_TOPK_UNROLL"); unr_env = (e && atoi(e) == 8) ? 8 : 2; }
+#define ATS_TOPK(TT, UU)                                                                                                  \
+    mask_logsoftmax_topk_kernel<TT, UU><<<rows, TOPK_THREADS, 0, st>>>(static_cast<const TT*>(logits), V, ld, row_node,    \
+                                                                       n_rows_dev, trie.child_off, trie.child_tok,        \
+                                                                       trie.n_nodes, B, cand_tok, cand_edge, cand_logp,   \
+                                                                       cand_cnt, lse)
+    if (logits_bf16) {
+        if (unr_env == 8) ATS_TOPK(__nv_bfloat16, 8); else ATS_TOPK(__nv_bfloat16, 2);
+    } else {
+        if (unr_env == 8) ATS_TOPK(float, 8); else ATS_TOPK(float, 2);
+    }
+#undef ATS_TOPK
     ATS_LAUNCH_CHECK();
     return ATS_OK;
 }

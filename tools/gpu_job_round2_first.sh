@@ -20,3 +20,5 @@ timeout 600 python tools/kernel_abc_bench.py --json gpurun_out/abc_bench_$TAG.js
 ATSPEED_ATT_BQ=32 timeout 300 python -m pytest tests/test_gpu_kernels.py -q -k attention > gpurun_out/att_bq32_$TAG.log 2>&1; echo "attention BQ=32 rc=$?"; tail -3 gpurun_out/att_bq32_$TAG.log
 ATSPEED_GEMM_4CTA=1 timeout 600 python tools/gemm_T_sweep_check.py --lo 257 --hi 512 --shapes 7b --limit-s 15 > gpurun_out/gemm_4cta_check_$TAG.txt 2>&1; echo "4-CTA GEMM check rc=$?"; tail -8 gpurun_out/gemm_4cta_check_$TAG.txt
 ATSPEED_ATT_PLO=0 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_e2e.py -q -k "attention or forward_matches" > gpurun_out/att_plo0_$TAG.log 2>&1; echo "attention PLO=0 rc=$?"; tail -3 gpurun_out/att_plo0_$TAG.log
+ATSPEED_TOPK_UNROLL=8 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -k topk > gpurun_out/topk_unr8_$TAG.log 2>&1; echo "kernel (a) unroll 8 rc=$?"; tail -2 gpurun_out/topk_unr8_$TAG.log
+ATSPEED_TOPK_UNROLL=8 timeout 600 python tools/kernel_abc_bench.py --quick > gpurun_out/abc_bench_unr8_$TAG.txt 2>&1; cat gpurun_out/abc_bench_unr8_$TAG.txt
