@@ -611,6 +611,7 @@ def multi_gpu_env(world):
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         os.environ.setdefault("NCCL_MNNVL_ENABLE", "0")      # one box: no multi-node NVLink / IMEX probing either
         os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         os.environ.setdefault("ATSPEED_GEMM_2CTA", "0")
 
 
