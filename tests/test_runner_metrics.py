@@ -99,3 +99,24 @@ def test_userrecords_roundtrip():
     q = UserRecords.unpack(r.pack(), 5, 4)
     for k in ("users", "items", "scores", "meta"):
         np.testing.assert_array_equal(getattr(q, k), getattr(r, k))
+
+
+@pytest.mark.parametrize("name", ["beauty", "games"])
+def test_recall_ndcg_equal_the_reference_on_64_ranked_lists(name):
+    """Recall@K / NDCG@K must be IDENTICAL to the reference's (north star).  tools/make_golden_users.py ran the reference's
+    computeTopNAccuracy on 64 recorded ranked lists per dataset with the user's first ground-truth item planted at rank
+    (i mod 10) for two users out of three; the mirror, fed the same lists through the same decode path, must return the same
+    four rounded vectors."""
+    g = golden("bssd_strict_users.json")
+    ds = dataset(name)
+    gts, preds = [], []
+    for i, c in enumerate([c for c in g["cases"] if c["dataset"] == name]):
+        gt = ds.ground_truth_strings(c["user"])
+        names = ds.decode_items(c["bssd"]["items"])
+        if i % 3 != 2:
+            names[i % 10] = gt[0]
+        gts.append(gt)
+        preds.append(names)
+    got = computeTopNAccuracy(gts, preds, g["metrics"]["topN"])
+    assert [list(x) for x in got] == g["metrics"]["values"][name]
+    assert got[1][-1] > 0.3        # the planted hits are seen: Recall@10 is far from zero

@@ -50,7 +50,26 @@ def main(n_users=64):
                           "total_accept_steps": out["total_accept_steps"],
                           "accept_steps": [r["n_matches"] for r in rounds]})
         print(name, len(cases), f"{time.time() - t0:.0f}s", flush=True)
-    json.dump({"cases": cases}, open(os.path.join(MG.OUT, "bssd_strict_users.json"), "w"))
+    # Recall / NDCG of ranked lists, by the reference's own computeTopNAccuracy (code/utils.py:215-271).  Random-init models
+    # never hit the ground truth, so the lists are the recorded ones with the user's first ground-truth item planted at
+    # rank (i mod 10) for two users out of three -- the recipe tests/test_runner_metrics.py repeats.
+    from utils import computeTopNAccuracy
+    metrics = {}
+    for name in ("beauty", "games"):
+        ds = load_dataset(name)
+        rds = MG.reference_dataset(name)
+        gts, preds = [], []
+        for i, c in enumerate([c for c in cases if c["dataset"] == name]):
+            gt = list(rds[c["user"]]["labels"])
+            names = ds.decode_items(c["bssd"]["items"])
+            if i % 3 != 2:
+                names[i % 10] = gt[0]
+            gts.append(gt)
+            preds.append(names)
+        metrics[name] = [list(x) for x in computeTopNAccuracy(gts, preds, [1, 5, 10])]
+    json.dump({"cases": cases, "metrics": {"topN": [1, 5, 10], "values": metrics}},
+              open(os.path.join(MG.OUT, "bssd_strict_users.json"), "w"))
+    print("reference metrics", metrics)
     print("cases", len(cases), "accept histogram", np.bincount([c["total_accept_steps"] for c in cases]).tolist())
 
 
