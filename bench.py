@@ -621,8 +621,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     gpu_multi = world > 1 and a.impl != "reference"
+    gpu_single = world == 1 and a.impl != "reference"
     arm_watchdog(int(os.environ.get("ATSPEED_BENCH_WATCHDOG_S", 600 if gpu_multi else 900)),
-                 int(os.environ.get("ATSPEED_BENCH_STALL_S", 240 if gpu_multi else 600)))
+                 int(os.environ.get("ATSPEED_BENCH_STALL_S", 240 if gpu_multi else (300 if gpu_single else 600))))
     if a.impl == "reference":
         reference_arm(a, rank)
         return
