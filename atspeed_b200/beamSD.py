@@ -267,7 +267,9 @@ def BSSD(target_model, draft_model, inputs: Dict, gamma: int, max_new_tokens: in
             e[3].record()
             marks.append(e)
             if trace:
-                rounds.append({"draft": d_out, "target": t_out, "verify": sess.verify_trace(), "n_matches": n_matches})
+                # "beams": the K beams the next round starts from (generated tokens so far, root order, and their scores)
+                rounds.append({"draft": d_out, "target": t_out, "verify": sess.verify_trace(), "n_matches": n_matches,
+                               "beams": sess.result()})
             done += n_matches + 1
             accept_steps.append(n_matches)
         sess.sort_result()                                                       # beamSD.py:529-531 (sampling only)

@@ -262,7 +262,7 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
                         ++gc.n;
                     }
                     PROF(s, CAT_GATHER, 0,
-                         kv_gather_rows_cohort(m->kv, m->kv_plane * m->elem_bytes, m->d.n_layers * 2, m->HD * m->elem_bytes, gc,
+                         kv_gather_rows_cohort(m->f32 ? static_cast<void*>(m->fkv) : static_cast<void*>(m->kv), m->kv_plane * m->elem_bytes, m->d.n_layers * 2, m->HD * m->elem_bytes, gc,
                                                (max_dl + 1) * K, st));
                     s->launches += 1;
                 }

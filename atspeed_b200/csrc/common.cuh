@@ -66,9 +66,88 @@ constexpr int MAX_TREE_SLOTS = VIS_WORDS * 32;
 bool pdl_enabled();   // gemm.cu; ATSPEED_PDL=0 turns programmatic dependent launch off
 
 // ---------------------------------------------------------------------------------------------
+// Bounded mbarrier waits.  Every mbarrier wait of the library (GEMM pipelines, KV gather) gives up after
+// spin_limit_ns() (ATSPEED_SPIN_LIMIT_MS, default 4000; 0 = wait forever): the first thread whose wait expires
+// writes WHO was waiting for WHAT into a HangDiag record in mapped pinned host memory (readable after the
+// context is gone) and traps, so a protocol bug or a lost arrival ends the launch with a CUDA error and a
+// message instead of a GPU that spins until somebody kills the process.  engine.cu appends the decoded record
+// to atspeed_last_error() whenever a CUDA call fails.
+// ---------------------------------------------------------------------------------------------
+struct HangDiag {
+    unsigned int flag;        // 0 clear, 1 being written, 2 valid
+    unsigned int kernel;      // HANG_K_*
+    unsigned int block, thread;
+    unsigned int role;        // HANG_R_*
+    unsigned int barrier;     // HANG_B_*
+    unsigned int index;       // pipeline stage / accumulator buffer
+    unsigned int parity;
+    unsigned int unit, u_begin, u_end;   // GEMM: work unit being waited for and the CTA's unit range
+    unsigned int T;
+    unsigned long long waited_ns;
+};
+enum : unsigned { HANG_K_GEMM = 1, HANG_K_GEMM_PAIR = 2, HANG_K_KVGATHER = 3 };
+enum : unsigned { HANG_R_PRODUCER = 1, HANG_R_MMA = 2, HANG_R_EPILOGUE = 3, HANG_R_COPY = 4 };
+enum : unsigned { HANG_B_EMPTY = 1, HANG_B_FULL = 2, HANG_B_ACCUM_FULL = 3, HANG_B_ACCUM_EMPTY = 4, HANG_B_ROW = 5 };
+struct SpinGuard {            // passed by value to the kernels that wait on mbarriers
+    HangDiag* diag;           // device-visible address of the mapped record (nullptr: trap without a record)
+    unsigned long long limit_ns;
+};
+SpinGuard spin_guard();                       // engine.cu: mapped record (allocated once per process) + the limit
+void hang_diag_describe(char* buf, size_t n); // engine.cu: "" when no record has been written
+
+// ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+static __device__ unsigned int g_hang_elect = 0;    // per translation unit: the first reporter of a launch writes the record
+static __device__ __noinline__ void hang_report(const SpinGuard g, unsigned kernel, unsigned role, unsigned barrier, unsigned index,
+                                         unsigned parity, unsigned unit, unsigned u_begin, unsigned u_end, unsigned T,
+                                         unsigned long long waited_ns) {
+    volatile HangDiag* d = g.diag;
+    if (d != nullptr && atomicCAS(&g_hang_elect, 0u, 1u) == 0u) {     // plain stores only: the record is host memory
+        d->flag = 1u;
+        d->kernel = kernel; d->block = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); d->thread = threadIdx.x;
+        d->role = role; d->barrier = barrier; d->index = index; d->parity = parity;
+        d->unit = unit; d->u_begin = u_begin; d->u_end = u_end; d->T = T; d->waited_ns = waited_ns;
+        __threadfence_system();
+        d->flag = 2u;
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait for the phase with parity `parity` of the mbarrier at shared address bar_addr, at most g.limit_ns
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar_addr, uint32_t parity, const SpinGuard& g, unsigned kernel,
+                                                  unsigned role, unsigned barrier, unsigned index, unsigned unit,
+                                                  unsigned u_begin, unsigned u_end, unsigned T) {
+    if (mbar_try_wait_u32(bar_addr, parity)) return;
+    const unsigned long long t0 = global_timer_ns();
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try_wait_u32(bar_addr, parity)) return;
+        if ((spins & 63u) == 0u && g.limit_ns != 0ull) {
+            const unsigned long long dt = global_timer_ns() - t0;
+            if (dt > g.limit_ns) hang_report(g, kernel, role, barrier, index, parity, unit, u_begin, u_end, T, dt);
+        }
+    }
+}
+
 // Programmatic dependent launch (PDL): every kernel of the forward is launched with the
 // programmatic-stream-serialization attribute, lets its successor start early (launch_dependents) and waits for its
 // predecessor's memory (wait) before touching anything the predecessor wrote or still reads.  Launch latency and

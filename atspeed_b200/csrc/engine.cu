@@ -4,7 +4,9 @@
 // `target_generate`): it only sequences kernel launches on the caller's stream.  All search state lives
 // on the device (beam.cuh); the single device->host read per round is the accepted length.
 #include <stdarg.h>
+#include <stdlib.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/atspeed.h"
@@ -13,12 +15,55 @@
 
 namespace atspeed {
 
-static thread_local char g_err[512] = "";
+static thread_local char g_err[768] = "";
+
+// ---- bounded mbarrier waits: the mapped diagnostic record (common.cuh) ----
+static HangDiag* g_diag_host = nullptr;
+static HangDiag* g_diag_dev = nullptr;
+static unsigned long long g_spin_limit_ns = 0;
+
+SpinGuard spin_guard() {
+    static std::once_flag once;
+    std::call_once(once, []() {
+        const char* e = getenv("ATSPEED_SPIN_LIMIT_MS");
+        long long ms = e ? atoll(e) : 4000;
+        if (ms < 0) ms = 0;
+        g_spin_limit_ns = static_cast<unsigned long long>(ms) * 1000000ull;
+        void* h = nullptr;
+        void* d = nullptr;
+        if (cudaHostAlloc(&h, sizeof(HangDiag), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+            cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+            memset(h, 0, sizeof(HangDiag));
+            g_diag_host = static_cast<HangDiag*>(h);
+            g_diag_dev = static_cast<HangDiag*>(d);
+        } else {
+            cudaGetLastError();      // no record: an expired wait still traps
+        }
+    });
+    return SpinGuard{g_diag_dev, g_spin_limit_ns};
+}
+
+void hang_diag_describe(char* buf, size_t n) {
+    if (n) buf[0] = 0;
+    const volatile HangDiag* d = g_diag_host;
+    if (!d || d->flag == 0) return;
+    static const char* const kern[] = {"?", "gemm_wx_tcgen05", "gemm_wx_tcgen05_2cta", "kv_gather"};
+    static const char* const role[] = {"?", "TMA producer", "MMA issuer", "epilogue", "copy thread"};
+    static const char* const bar[] = {"?", "empty", "full", "accum_full", "accum_empty", "row"};
+    const unsigned k = d->kernel < 4 ? d->kernel : 0, r = d->role < 5 ? d->role : 0, b = d->barrier < 6 ? d->barrier : 0;
+    snprintf(buf, n,
+             " [device stall: %s block %u thread %u (%s) waited %.0f ms for %s[%u] parity %u, unit %u of [%u,%u), T=%u%s]",
+             kern[k], d->block, d->thread, role[r], d->waited_ns * 1e-6, bar[b], d->index, d->parity, d->unit, d->u_begin,
+             d->u_end, d->T, d->flag == 2 ? "" : ", record incomplete");
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+    const size_t len = strlen(g_err);
+    if (len + 1 < sizeof(g_err)) hang_diag_describe(g_err + len, sizeof(g_err) - len);
 }
 const char* last_error() { return g_err; }
 
@@ -172,8 +217,6 @@ static int check_cfg(const atspeed_model_desc* target, const atspeed_model_desc*
     ATS_CHECK_ARG(cfg->max_users >= 0 && cfg->max_users <= MAX_USERS, "max_users=%d outside [0,%d]", cfg->max_users, MAX_USERS);
     ATS_CHECK_ARG(cfg->cohort_tokens == 0 || (cfg->cohort_tokens >= 256 && cfg->cohort_tokens <= 512),
                   "cohort_tokens=%d outside [256,512]", cfg->cohort_tokens);
-    if (cfg->max_users > 1)
-        ATS_CHECK_ARG(!target->weights_f32 && !(draft && draft->weights_f32), "cohort mode (max_users > 1) needs bf16 models");
     if (cfg->do_sample) {
         ATS_CHECK_ARG(cfg->top_k >= 1 && cfg->top_k <= MAX_BEAMS,
                       "do_sample needs generation_config.top_k in [1,%d] (transformers 4.41 default 50), got %d", MAX_BEAMS,
@@ -896,7 +939,7 @@ int atspeed_gemm_plan(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_
     GemmPlan pl;
     ATS_TRY(gemm_make_plan(g, T, num_sms, allow_cut != 0, &pl));
     const int v[16] = {pl.BM, pl.KB, pl.total_tiles, pl.U, pl.grid, pl.max_slices, pl.stages, pl.tmem_cols, pl.n_bufs, pl.T_pad,
-                       pl.tiles[0], pl.tiles[1], pl.tiles[2], pl.two_cta + pl.four_cta, pl.n_mma, pl.N_mma};   // [13]: 0 single CTA, 1 pair, 2 cluster of 4
+                       pl.tiles[0], pl.tiles[1], pl.tiles[2], pl.two_cta, pl.n_mma, pl.N_mma};   // [13]: 0 single CTA, 1 CTA pair
     for (int i = 0; i < 16; ++i) info16[i] = v[i];
     if (slices_of_col) {
         const SplitMap sm = gemm_split_map(g, pl);

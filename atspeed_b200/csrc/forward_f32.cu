@@ -77,12 +77,13 @@ __global__ void __launch_bounds__(256) f32_gemm_kernel(const float* __restrict__
 __global__ void f32_rope_append_kernel(const float* __restrict__ qkv, const int* __restrict__ pos, const int* __restrict__ slot,
                                        int n_heads, int head_dim, const float* __restrict__ rope_cos,
                                        const float* __restrict__ rope_sin, int max_pos, float* __restrict__ qbuf,
-                                       float* __restrict__ kcache, float* __restrict__ vcache) {
+                                       float* __restrict__ kcache, float* __restrict__ vcache,
+                                       const int* __restrict__ tok_user, CohortKV ckv) {
     const int t = blockIdx.x;
     const int HD = n_heads * head_dim, half = head_dim >> 1;
     int p = pos[t];
     p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
-    const long long srow = static_cast<long long>(slot[t]) * HD;
+    const long long srow = static_cast<long long>(slot[t]) * HD + (tok_user ? ckv.kv_off[tok_user[t]] : 0);   // cohort: own cache
     const float* row = qkv + static_cast<long long>(t) * 3 * HD;
     for (int e = threadIdx.x; e < n_heads * half; e += blockDim.x) {
         const int hd = e / half, i = e - hd * half;
@@ -104,14 +105,23 @@ __global__ void __launch_bounds__(128) f32_tree_attention_kernel(const float* __
                                                                  const int* __restrict__ prefix_len,
                                                                  const uint32_t* __restrict__ vis, int vis_base, int T,
                                                                  int S, int n_heads, int D, float scale,
-                                                                 float* __restrict__ out) {
+                                                                 float* __restrict__ out, const int* __restrict__ tok_user,
+                                                                 CohortKV ckv) {
     extern __shared__ float f32_att_smem[];                  // [4 warps][S] scores
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * 4 + warp;
     if (item >= T * n_heads) return;
     const int t = item / n_heads, head = item - t * n_heads;
     const int HD = n_heads * D;
-    float* sc = f32_att_smem + static_cast<size_t>(warp) * S;
+    float* sc = f32_att_smem + static_cast<size_t>(warp) * S;   // S = the launch's largest extent
+    if (tok_user) {
+        // cohort forward: the token attends its own user's cache, extent and prompt length (block-diagonal tree mask)
+        const int u = tok_user[t];
+        kcache += ckv.kv_off[u];
+        vcache += ckv.kv_off[u];
+        S = ckv.S[u];
+        vis_base = ckv.vis_base[u];
+    }
     const float* qv = q + static_cast<long long>(t) * HD + head * D;
     const int pl = prefix_len[t];
     const uint32_t* vrow = vis + static_cast<long long>(t) * VIS_WORDS;
@@ -180,7 +190,7 @@ int f32_gemm(const float* x, const float* w, int T, int N, int K, float* out, in
 int f32_rope_append(const float* qkv, const BatchDesc& b, int T, int n_heads, int head_dim, const float* rope_cos,
                     const float* rope_sin, int max_pos, float* qbuf, float* kcache, float* vcache, cudaStream_t st) {
     f32_rope_append_kernel<<<T, 128, 0, st>>>(qkv, b.pos, b.slot, n_heads, head_dim, rope_cos, rope_sin, max_pos, qbuf, kcache,
-                                              vcache);
+                                              vcache, b.tok_user, b.ckv);
     ATS_LAUNCH_CHECK();
     return ATS_OK;
 }
@@ -191,7 +201,7 @@ int f32_tree_attention(const float* q, const float* kcache, const float* vcache,
     const int items = T * n_heads;
     f32_tree_attention_kernel<<<(items + 3) / 4, 128, smem, st>>>(q, kcache, vcache, b.prefix_len, b.vis, b.vis_base, T, S,
                                                                   n_heads, head_dim, 1.0f / sqrtf(static_cast<float>(head_dim)),
-                                                                  out);
+                                                                  out, b.tok_user, b.ckv);
     ATS_LAUNCH_CHECK();
     return ATS_OK;
 }

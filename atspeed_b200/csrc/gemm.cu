@@ -19,6 +19,8 @@
 // warps 2..5 = epilogue (tcgen05.ld 32 lanes each -> coalesced fp32 stores along the feature axis).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -43,18 +45,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+// every wait of the pipelines is bounded (common.cuh): a lost arrival traps with a HangDiag record instead of spinning
+struct WaitCtx {
+    SpinGuard g;
+    unsigned kernel, role, u_begin, u_end, T;
+};
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const WaitCtx& w, unsigned barrier, unsigned index,
+                                          unsigned unit) {
+    mbar_wait_guarded(smem_u32(bar), parity, w.g, w.kernel, w.role, barrier, index, unit, w.u_begin, w.u_end, w.T);
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile(
@@ -173,9 +171,9 @@ struct GemmParams {
     int tmem_cols, acc_stride;
     int n_bufs, buf_stride;   // accumulator double buffering in TMEM: segment s uses buffer s % n_bufs
     int b_box_bytes;          // bytes the activation TMA box(es) deliver per stage (== T_pad * 128 except in timing experiments)
-    int dbg;                  // TIMING EXPERIMENTS (ATSPEED_GEMM_DBG): bit 0 = no epilogue stores, bit 1 = no MMA instructions
     int tma_store;            // epilogue writes through shared memory + cp.async.bulk.tensor stores (tmO*) instead of STG
     int n_mma, N_mma;         // 2-CTA kernel: the token axis (padded to 64) is covered by n_mma MMAs of N_mma columns each
+    SpinGuard guard;          // bound + diagnostic record of every mbarrier wait
 };
 
 // Work decomposition ("stream-K with consumer-side fix-up").  The (tile, k-block) units of the whole GEMM are
@@ -237,6 +235,10 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
+    WaitCtx wc;
+    wc.g = p.guard; wc.kernel = HANG_K_GEMM; wc.u_begin = u_begin; wc.u_end = u_end; wc.T = p.T;
+    wc.role = warp == 0 ? HANG_R_PRODUCER : (warp == 1 ? HANG_R_MMA : HANG_R_EPILOGUE);
+
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
@@ -268,13 +270,14 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             int s = npre == p.stages ? 0 : npre;
             uint32_t ph = npre == p.stages ? 1 : 0;
             for (int u = u_begin + npre; u < u_end; ++u) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_wait(&empty_bar[s], ph ^ 1, wc, HANG_B_EMPTY, s, u);
                 load_a(s);
                 load_b(s, kb);
                 advance();
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
@@ -284,22 +287,22 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             int s = 0; uint32_t ph = 0;
             int kb = u_begin % KB;
             int buf = 0;                       // accumulator buffer of the current segment (alternates when double-buffered)
-            uint32_t use[2] = {0, 0};          // how many segments each buffer has held so far
+            uint32_t use0 = 0, use1 = 0;       // how many segments each buffer has held so far (scalars: no local memory)
             for (int u = u_begin; u < u_end; ++u) {
                 const bool seg_start = (u == u_begin) || kb == 0;
-                if (seg_start && use[buf] > 0) {
+                const uint32_t used = buf ? use1 : use0;
+                if (seg_start && used > 0) {
                     // the epilogue must have drained this buffer's previous segment before it is overwritten
-                    mbar_wait(&accum_empty[buf], (use[buf] - 1) & 1);
+                    mbar_wait(&accum_empty[buf], (used - 1) & 1, wc, HANG_B_ACCUM_EMPTY, buf, u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t tacc = tmem_base + buf * p.buf_stride;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(&full_bar[s], ph, wc, HANG_B_FULL, s, u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    if (p.dbg & 2) break;
                     const uint32_t acc = (!seg_start || k > 0) ? 1u : 0u;
                     const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
                     const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
@@ -314,11 +317,12 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 if (++kb == KB) kb = 0;
                 if (u + 1 == u_end || kb == 0) {             // segment complete
                     umma_commit(&accum_full[buf]);
-                    ++use[buf];
+                    if (buf) ++use1; else ++use0;
                     if (p.n_bufs == 2) buf ^= 1;
                 }
             }
         }
+        __syncwarp();
     } else {
         // ===== epilogue: TMEM -> registers -> global fp32 partial-sum slice =====
         asm volatile("griddepcontrol.wait;" ::: "memory");    // `out` may still be read by the previous consumer
@@ -333,7 +337,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             tile_of(tile, wid, m0);
             const int slice = blockIdx.x - (tile * KB) / p.U;
             const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
-            mbar_wait(&accum_full[buf], use & 1);
+            mbar_wait(&accum_full[buf], use & 1, wc, HANG_B_ACCUM_FULL, buf, u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (p.tma_store) {
                 // TMEM -> registers -> [16 tokens][128 features] fp32 staging tile -> ONE bulk tensor store per 8 KB: the
@@ -355,7 +359,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                         for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (elected && !(p.dbg & 1)) {
+                        if (elected) {
                             tma_store_3d(tmO, stg, m0 + half * BLOCK_M, c, slice);   // clipped to [rows_i, T, slices]
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
@@ -372,7 +376,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     uint32_t r[16];
                     tmem_ld16(tbase + static_cast<uint32_t>(c), r);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (row_ok && !(p.dbg & 1)) {
+                    if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
@@ -463,6 +467,10 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
+    WaitCtx wc;
+    wc.g = p.guard; wc.kernel = HANG_K_GEMM_PAIR; wc.u_begin = u_begin; wc.u_end = u_end; wc.T = p.T;
+    wc.role = warp == 0 ? HANG_R_PRODUCER : (warp == 1 ? HANG_R_MMA : HANG_R_EPILOGUE);
+
     if (warp == 0) {
         // ===== TMA producer (one thread in each CTA) =====
         if (lane == 0) {
@@ -490,13 +498,14 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             int s = npre == p.stages ? 0 : npre;
             uint32_t ph = npre == p.stages ? 1 : 0;
             for (int u = u_begin + npre; u < u_end; ++u) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_wait(&empty_bar[s], ph ^ 1, wc, HANG_B_EMPTY, s, u);
                 load_a(s);
                 load_b(s, kb);
                 advance();
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the LEADER CTA =====
         if (lane == 0 && leader) {
@@ -504,15 +513,16 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             int s = 0; uint32_t ph = 0;
             int kb = u_begin % KB;
             int buf = 0;
-            uint32_t use[2] = {0, 0};
+            uint32_t use0 = 0, use1 = 0;
             for (int u = u_begin; u < u_end; ++u) {
                 const bool seg_start = (u == u_begin) || kb == 0;
-                if (seg_start && use[buf] > 0) {
-                    mbar_wait(&accum_empty[buf], (use[buf] - 1) & 1);     // both CTAs' epilogues drained this buffer
+                const uint32_t used = buf ? use1 : use0;
+                if (seg_start && used > 0) {
+                    mbar_wait(&accum_empty[buf], (used - 1) & 1, wc, HANG_B_ACCUM_EMPTY, buf, u);   // both CTAs' epilogues drained it
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t tacc = tmem_base + buf * p.buf_stride;
-                mbar_wait(&full_bar[s], ph);                              // both CTAs' tiles of this stage have landed
+                mbar_wait(&full_bar[s], ph, wc, HANG_B_FULL, s, u);                              // both CTAs' tiles of this stage have landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
@@ -529,11 +539,12 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                 if (++kb == KB) kb = 0;
                 if (u + 1 == u_end || kb == 0) {
                     umma_commit_2sm(&accum_full[buf]);                    // accumulators complete in both CTAs
-                    ++use[buf];
+                    if (buf) ++use1; else ++use0;
                     if (p.n_bufs == 2) buf ^= 1;
                 }
             }
         }
+        __syncwarp();                                        // .aligned cluster barrier / dealloc below need the whole warp
     } else {
         // ===== epilogue (both CTAs): this CTA's 128 rows of the pair's tile =====
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -550,7 +561,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             tile_of(tile, wid, m0);
             const int slice = pair - (tile * KB) / p.U;
             const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
-            mbar_wait(&accum_full[buf], use & 1);
+            mbar_wait(&accum_full[buf], use & 1, wc, HANG_B_ACCUM_FULL, buf, u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
             const uint32_t tbase = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
@@ -569,12 +580,12 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                     for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (elected && !(p.dbg & 1)) {
+                    if (elected) {
                         tma_store_3d(tmO, stg, m0, c, slice);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++st_chunk;
-                } else if (row_ok && !(p.dbg & 1)) {
+                } else if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
@@ -588,227 +599,6 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                      // nobody frees TMEM / exits while the peer may still touch it
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"(static_cast<uint32_t>(p.tmem_cols)));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL, OFF BY DEFAULT (ATSPEED_GEMM_4CTA=1; written at the end of round 1 without a GPU to run it on -- see
-// DESIGN.md section 8): clusters of FOUR CTAs = two CTA pairs that work on two adjacent 256-row weight tiles over the same
-// k-range and SHARE the activation tile.  The pair kernel above is L2->SM-bandwidth bound at T > 256 (each pair pulls the
-// whole [T, 64] activation k-block out of L2 for every k-block of its weight tile); here the token half that CTA `rip` of a
-// pair holds is needed by CTAs {rip, rip + 2}, so each of the two loads one QUARTER and TMA-multicasts it into both.
-// Everything else is the pair kernel with "pair" -> "cluster", BM = 512 and these barrier changes:
-//   full[s]   (leader of each pair)  unchanged: expects the bytes landing in ITS pair's two CTAs;
-//   empty[s]  (every CTA)            counts 2: a slot is free when BOTH pairs' MMAs on it have retired, because the other
-//                                    pair's producer writes into this CTA's shared memory (commit mask 0b1111);
-//   accum_full / accum_empty         per pair (commit mask 0b0011 or 0b1100, arrivals at the pair's leader).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d_2sm_mc(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1,
-                                                   uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%4, %5}], [%2], %3;"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0),
-        "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm_mask(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"(cta_mask)
-                 : "memory");
-}
-
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_wx_tcgen05_4cta(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
-                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
-                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-                     const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t accum_full[2], accum_empty[2];
-    __shared__ uint32_t tmem_base_smem;
-
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();                 // 0..3
-    const uint32_t pr = rank >> 1, rip = rank & 1;           // pair within the cluster, rank within the pair
-    const bool leader = rip == 0;
-    const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pr));
-    const uint16_t b_mask = static_cast<uint16_t>((1u << rip) | (1u << (rip + 2)));   // the two CTAs that hold this token half
-    const int cl = blockIdx.x >> 2;
-    const int T64 = p.n_mma * p.N_mma;
-    const int b_half_rows = p.N_mma >> 1;                    // tokens of one MMA held by this CTA
-    const int b_q_rows = p.N_mma >> 2;                       // ... of which this CTA loads the quarter `pr`
-    const int b_mma_bytes = b_half_rows * BLOCK_K * 2;
-    const int b_q_bytes = b_q_rows * BLOCK_K * 2;            // a multiple of 1024 (N_mma % 32 == 0): swizzle-consistent
-    const int a_bytes = A_TILE_BYTES;
-    const int stage_bytes = a_bytes + p.n_mma * b_mma_bytes;
-    const int KB = p.n_kblocks;
-    const int u_begin = cl * p.U;
-    const int u_end = min(u_begin + p.U, p.total_units);
-    const int n_units = u_end - u_begin;
-
-    auto tile_of = [&](int tile, int& wid, int& m0) {
-        wid = 0;
-        if (tile >= p.tiles[0]) { tile -= p.tiles[0]; wid = 1; }
-        if (wid == 1 && tile >= p.tiles[1]) { tile -= p.tiles[1]; wid = 2; }
-        m0 = tile * 512 + static_cast<int>(pr) * 256 + static_cast<int>(rip) * BLOCK_M;   // this CTA's 128 rows
-    };
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&accum_full[b], 1);
-            mbar_init(&accum_empty[b], 8);        // 4 epilogue warps of each CTA of the pair
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmW0); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmX);
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                     "r"(static_cast<uint32_t>(p.tmem_cols)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();                                      // barriers of all four CTAs initialised, TMEM allocated
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_smem;
-
-    if (warp == 0) {
-        // ===== TMA producer (one thread in each CTA) =====
-        if (lane == 0) {
-            int tile = u_begin / KB, kb = u_begin - tile * KB, wid, m0;
-            tile_of(tile, wid, m0);
-            auto advance = [&]() {
-                if (++kb == KB) { kb = 0; ++tile; tile_of(tile, wid, m0); }
-            };
-            auto load_a = [&](int s) {
-                const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
-                if (leader) mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
-                tma_load_2d_2sm(tmW, &full_bar[s], smem + static_cast<size_t>(s) * stage_bytes, kb * BLOCK_K, m0);
-            };
-            auto load_b = [&](int s, int kbb) {
-                // quarter `pr` of this CTA's token half of every MMA, delivered to this CTA and to CTA rip of the other pair
-                uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes + static_cast<int>(pr) * b_q_bytes;
-                for (int i = 0; i < p.n_mma; ++i)
-                    tma_load_2d_2sm_mc(&tmX, &full_bar[s], b_dst + i * b_mma_bytes, kbb * BLOCK_K,
-                                       i * p.N_mma + static_cast<int>(rip) * b_half_rows + static_cast<int>(pr) * b_q_rows, b_mask);
-            };
-            const int npre = n_units < p.stages ? n_units : p.stages;
-            const int kb_first = kb;
-            for (int i = 0; i < npre; ++i) { load_a(i); advance(); }
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            for (int i = 0, kbb = kb_first; i < npre; ++i) { load_b(i, kbb); if (++kbb == KB) kbb = 0; }
-            int s = npre == p.stages ? 0 : npre;
-            uint32_t ph = npre == p.stages ? 1 : 0;
-            for (int u = u_begin + npre; u < u_end; ++u) {
-                mbar_wait(&empty_bar[s], ph ^ 1);                         // both pairs are done with this slot
-                load_a(s);
-                load_b(s, kb);
-                advance();
-                if (++s == p.stages) { s = 0; ph ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer: one thread of each pair's leader CTA =====
-        if (lane == 0 && leader) {
-            const uint32_t idesc = make_idesc_m(256, static_cast<uint32_t>(p.N_mma));
-            int s = 0; uint32_t ph = 0;
-            int kb = u_begin % KB;
-            int buf = 0;
-            uint32_t use[2] = {0, 0};
-            for (int u = u_begin; u < u_end; ++u) {
-                const bool seg_start = (u == u_begin) || kb == 0;
-                if (seg_start && use[buf] > 0) {
-                    mbar_wait(&accum_empty[buf], (use[buf] - 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                const uint32_t tacc = tmem_base + buf * p.buf_stride;
-                mbar_wait(&full_bar[s], ph);                              // this pair's tiles of the stage have landed
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-                const uint32_t b_addr = a_addr + a_bytes;
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    const uint32_t acc = (!seg_start || k > 0) ? 1u : 0u;
-                    const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
-                    umma_bf16_2sm(tacc, da, make_smem_desc(b_addr + k * UMMA_K * 2), idesc, acc);
-                    if (p.n_mma == 2)
-                        umma_bf16_2sm(tacc + p.N_mma, da, make_smem_desc(b_addr + b_mma_bytes + k * UMMA_K * 2), idesc, acc);
-                }
-                umma_commit_2sm_mask(&empty_bar[s], 0xF);                 // one of the two arrivals that free the slot
-                if (++s == p.stages) { s = 0; ph ^= 1; }
-                if (++kb == KB) kb = 0;
-                if (u + 1 == u_end || kb == 0) {
-                    umma_commit_2sm_mask(&accum_full[buf], pair_mask);    // accumulators complete in this pair's CTAs
-                    ++use[buf];
-                    if (p.n_bufs == 2) buf ^= 1;
-                }
-            }
-        }
-    } else {
-        // ===== epilogue (all four CTAs): this CTA's 128 rows of its pair's tile =====
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        const int q = warp & 3;
-        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
-        int st_chunk = 0;
-        int seg = 0;
-        const bool elected = threadIdx.x == 64;
-        const int f = q * 32 + lane;
-        for (int u = u_begin; u < u_end; ++seg) {
-            const int tile = u / KB;
-            const int seg_end = min((tile + 1) * KB, u_end);
-            int wid, m0;
-            tile_of(tile, wid, m0);
-            const int slice = cl - (tile * KB) / p.U;
-            const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
-            mbar_wait(&accum_full[buf], use & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
-            const uint32_t tbase = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
-            const int row = m0 + f;
-            const bool row_ok = row < p.n_rows[wid];
-            float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
-            for (int c = 0; c < T64 && c < p.T; c += 16) {
-                uint32_t r[16];
-                tmem_ld16(tbase + static_cast<uint32_t>(c), r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (p.tma_store) {
-                    float* stg = stage_out + (st_chunk & 1) * (16 * 128);
-                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (elected && !(p.dbg & 1)) {
-                        tma_store_3d(tmO, stg, m0, c, slice);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    ++st_chunk;
-                } else if (row_ok && !(p.dbg & 1)) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], 2 * pr);   // this pair's leader waits for its 8 warps
-            u = seg_end;
-        }
-        if (p.tma_store && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();                                      // nobody frees TMEM / exits while a peer may still touch it
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(static_cast<uint32_t>(p.tmem_cols)));
@@ -852,18 +642,16 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, lon
     return ATS_OK;
 }
 
-// Large token counts (cohort forwards) run the CTA-pair kernel; ATSPEED_GEMM_2CTA=0 keeps the single-CTA kernel.
+// The CTA-pair kernel (cta_group::2) for T > 256 is OPT-IN (ATSPEED_GEMM_2CTA=1): under several concurrent streams it
+// stalled on the device in round 1, so every configuration -- 1 GPU and N GPUs alike -- runs the
+// single-CTA kernel for every T unless the caller asks for the pair kernel.  ATSPEED_GEMM_2CTA_MIN: smallest padded token
+// count that uses it (experiments).  The environment is read per call: tests toggle it inside one process.
 bool gemm_use_2cta(int T) {
     const char* e = getenv("ATSPEED_GEMM_2CTA");
-    const char* m = getenv("ATSPEED_GEMM_2CTA_MIN");       // experiments: smallest padded token count that uses the pair kernel
+    if (!(e && atoi(e) == 1)) return false;
+    const char* m = getenv("ATSPEED_GEMM_2CTA_MIN");
     const int T_pad = (T + 15) & ~15;
-    return !(e && atoi(e) == 0) && T_pad > (m ? atoi(m) : 256);
-}
-
-// EXPERIMENTAL (off unless ATSPEED_GEMM_4CTA=1): clusters of four CTAs with multicast activations, gemm_wx_tcgen05_4cta.
-bool gemm_use_4cta(int T) {
-    const char* e = getenv("ATSPEED_GEMM_4CTA");
-    return e && atoi(e) == 1 && gemm_use_2cta(T);
+    return T_pad > (m ? atoi(m) : 256);
 }
 
 // Choose the tile height, the persistent grid and the unit range of every CTA for one GEMM shape.
@@ -877,53 +665,6 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     pl->T = T;
     pl->T_pad = (T + 15) & ~15;
     pl->KB = (w.K + BLOCK_K - 1) / BLOCK_K;
-    if (gemm_use_4cta(T) && num_sms >= 4) {
-        // EXPERIMENTAL 4-CTA clusters (gemm_wx_tcgen05_4cta): 512-row tile groups (two 256-row pair tiles) owned by clusters
-        // of four SMs; token axis exactly as in the pair kernel.  Same unit / slice arithmetic with BM = 512.
-        pl->two_cta = 1;
-        pl->four_cta = 1;
-        const int T64 = (T + 63) & ~63;
-        pl->n_mma = T64 > 256 ? 2 : 1;
-        pl->N_mma = T64 / pl->n_mma;
-        pl->BM = 512;
-        pl->total_tiles = 0;
-        for (int i = 0; i < 3; ++i) {
-            pl->tiles[i] = i < w.n ? (w.rows[i] + 511) / 512 : 0;
-            pl->tilebase[i] = pl->total_tiles;
-            pl->total_tiles += pl->tiles[i];
-        }
-        int clusters = num_sms / 4;
-        if (const char* e = getenv("ATSPEED_GEMM_4CTA_CLUSTERS")) { if (atoi(e) > 0 && atoi(e) < clusters) clusters = atoi(e); }
-        const int units = pl->total_tiles * pl->KB;
-        if (allow_cut) {
-            const int grid = units < clusters ? units : clusters;
-            pl->U = (units + grid - 1) / grid;
-            const int min_u = pl->KB < 8 ? pl->KB : 8;
-            if (pl->U < min_u) pl->U = min_u;
-            const int s = clusters / pl->total_tiles;   // narrow outputs: whole k-splits per tile group
-            if (s >= 2 && s <= pl->KB && pl->total_tiles * s * 10 >= clusters * 8) pl->U = (pl->KB + s - 1) / s;
-        } else {
-            pl->U = ((pl->total_tiles + clusters - 1) / clusters) * pl->KB;
-        }
-        pl->grid = 4 * ((units + pl->U - 1) / pl->U);
-        pl->max_slices = 1;
-        for (int t = 0; t < pl->total_tiles; ++t) {
-            const int n = (t * pl->KB + pl->KB - 1) / pl->U - (t * pl->KB) / pl->U + 1;
-            if (n > pl->max_slices) pl->max_slices = n;
-        }
-        const int stage_bytes = A_TILE_BYTES + (T64 / 2) * BLOCK_K * 2;
-        int stages = (220 * 1024 - OUT_STAGE_BYTES) / stage_bytes;
-        if (stages > MAX_STAGES) stages = MAX_STAGES;
-        if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
-        pl->stages = stages;
-        int acc = 32;
-        while (acc < T64) acc <<= 1;
-        pl->acc_stride = acc;
-        pl->n_bufs = 2 * acc <= 512 ? 2 : 1;
-        pl->buf_stride = acc;
-        pl->tmem_cols = pl->n_bufs * acc;
-        return ATS_OK;
-    }
     if (gemm_use_2cta(T) && num_sms >= 2) {
         // CTA-pair kernel (gemm_wx_tcgen05_2cta): 256-row tiles owned by SM pairs, tokens padded to 64 and covered by one
         // or two M=256 MMAs of N_mma columns (each CTA holds N_mma/2 tokens of each)
@@ -973,13 +714,10 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     for (int i = 0; i < w.n; ++i) tiles128 += (w.rows[i] + 127) / 128;
     // Two stacked 128-row MMAs per activation tile halve the L2->SM re-reads of the activations (the limiter at
     // T >~ 100, profiles/r01_ncu_full_v2.txt); they need 2 x T_pad TMEM columns and only pay off on wide outputs.
-    const char* force = getenv("ATSPEED_GEMM_BM");
     // (gemm_sweep: at T_pad <= 128 BM = 256 streams 4.7-5.9 TB/s where BM = 128 stalls at 3.3-3.8 -- one CTA per SM keeps too
     // few TMA boxes in flight; beyond that the [T_pad, 64] activation box dominates and the extra partial-sum traffic of
     // 256-row tiles costs more than it saves)
     pl->BM = (pl->T_pad <= 128 && tiles128 >= 2) ? 256 : 128;
-    if (force && atoi(force) == 128) pl->BM = 128;
-    if (force && atoi(force) == 256 && pl->T_pad <= 256) pl->BM = 256;
     pl->total_tiles = 0;
     for (int i = 0; i < 3; ++i) {
         pl->tiles[i] = i < w.n ? (w.rows[i] + pl->BM - 1) / pl->BM : 0;
@@ -987,7 +725,6 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
         pl->total_tiles += pl->tiles[i];
     }
     const int units = pl->total_tiles * pl->KB;
-    if (const char* e = getenv("ATSPEED_GEMM_CTAS")) { if (atoi(e) > 0) num_sms = atoi(e); }   // experiments only
     if (allow_cut) {
         int grid = units < num_sms ? units : num_sms;
         pl->U = (units + grid - 1) / grid;
@@ -1013,7 +750,6 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     const int stage_bytes = pl->BM * BLOCK_K * 2 + pl->T_pad * BLOCK_K * 2;
     int stages = (220 * 1024 - OUT_STAGE_BYTES) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (const char* e = getenv("ATSPEED_GEMM_STAGES")) { if (atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
     if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
     ATS_CHECK_ARG(stages >= 2, "gemm: T=%d leaves room for %d pipeline stages", T, stages);
     pl->stages = stages;
@@ -1022,7 +758,6 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     pl->acc_stride = acc;
     const int per_buf = pl->BM == 256 ? 2 * acc : acc;
     pl->n_bufs = 2 * per_buf <= 512 ? 2 : 1;                 // double-buffer so an epilogue overlaps the next segment
-    if (const char* e = getenv("ATSPEED_GEMM_BUFS")) { if (atoi(e) == 1) pl->n_bufs = 1; }
     pl->buf_stride = per_buf;
     pl->tmem_cols = pl->n_bufs * per_buf;
     ATS_CHECK_ARG(pl->tmem_cols <= 512, "gemm: %d TMEM columns", pl->tmem_cols);
@@ -1053,17 +788,15 @@ int gemm_make_xmap(XMap* xm, const void* x, int T, int K) {
         // CTA-pair kernel: one box = the N_mma/2 tokens of one MMA that one CTA of the pair holds
         const int T64 = (T + 63) & ~63;
         const int n_mma = T64 > 256 ? 2 : 1;
-        const int div = gemm_use_4cta(T) ? 4 : 2;     // 4-CTA clusters: each CTA loads a quarter of an MMA's tokens
-        ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, T64 / n_mma / div));
+        ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, T64 / n_mma / 2));
         xm->tm1 = xm->tm0;
-        xm->T = T; xm->K = K; xm->box0 = T64 / n_mma / div;
+        xm->T = T; xm->K = K; xm->box0 = T64 / n_mma / 2;
         return ATS_OK;
     }
     const int T_pad = (T + 15) & ~15;
     // activations: tokens 0..255 through tm0 (box = min(T_pad,256) rows), tokens 256..T_pad-1 through tm1
     // (box = T_pad-256 rows); rows past T are zero-filled by TMA, and each box always delivers its full byte count.
     int box0 = T_pad > 256 ? 256 : T_pad;
-    if (const char* e = getenv("ATSPEED_GEMM_BBOX")) { if (atoi(e) >= 16 && atoi(e) < box0 && T_pad <= 256) box0 = atoi(e); }  // TIMING ONLY
     xm->box0 = box0;
     ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, box0));
     ATS_TRY(make_tmap_bf16_kmajor(&xm->tm1, x, T, K, T_pad > 256 ? T_pad - 256 : 16));
@@ -1079,8 +812,6 @@ int gemm_make_omap(OMap* om, const GemmWeights& w, float* out, int ldo, long lon
     om->out = out; om->ldo = ldo; om->slice_stride = slice_stride; om->T = T;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return ATS_OK;
-    const char* e = getenv("ATSPEED_GEMM_TMASTORE");
-    if (e && atoi(e) == 0) return ATS_OK;
     const long long sstride = max_slices > 1 ? slice_stride : static_cast<long long>(T) * ldo;
     if ((ldo & 3) || (sstride & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return ATS_OK;
     for (int i = 0; i < w.n; ++i) {
@@ -1096,6 +827,33 @@ int gemm_make_omap(OMap* om, const GemmWeights& w, float* out, int ldo, long lon
     }
     for (int i = w.n; i < 3; ++i) om->tm[i] = om->tm[0];
     om->ok = 1;
+    return ATS_OK;
+}
+
+// Per-device one-time set-up: both kernels may use the whole 227 KiB of shared memory.  Done under std::call_once so the
+// lane threads of one process (bench.py runs three) cannot race on it.
+static int gemm_init_device(int* max_dyn_out) {
+    static std::once_flag once[64];
+    static int max_dyn[64];
+    static cudaError_t err[64];
+    int dev = 0;
+    ATS_CUDA(cudaGetDevice(&dev));
+    ATS_CHECK_ARG(dev >= 0 && dev < 64, "gemm: device ordinal %d", dev);
+    std::call_once(once[dev], [dev]() {
+        cudaFuncAttributes fa;
+        int md = 227 * 1024;
+        err[dev] = cudaSuccess;
+        for (const void* fn : {reinterpret_cast<const void*>(gemm_wx_tcgen05), reinterpret_cast<const void*>(gemm_wx_tcgen05_2cta)}) {
+            cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+            const int want = 227 * 1024 - static_cast<int>(fa.sharedSizeBytes);   // static barriers share the 227 KiB budget
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+            if (e != cudaSuccess) { err[dev] = e; return; }
+            if (want < md) md = want;
+        }
+        max_dyn[dev] = md;
+    });
+    if (err[dev] != cudaSuccess) { set_error("gemm: shared-memory set-up failed: %s", cudaGetErrorString(err[dev])); return ATS_ERR_CUDA; }
+    *max_dyn_out = max_dyn[dev];
     return ATS_OK;
 }
 
@@ -1121,22 +879,18 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     p.n_bufs = pl.n_bufs; p.buf_stride = pl.buf_stride;
     p.b_box_bytes = (pl.T_pad > 256 ? pl.T_pad : xm.box0) * BLOCK_K * 2;
     p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
+    p.guard = spin_guard();
+    p.tma_store = om.ok;
     const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
                                        : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
     size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + OUT_STAGE_BYTES + 1024;
     // One GEMM CTA per SM, always: a CTA holds its TMEM columns from prologue to exit and, with PDL and several streams,
-    // CTAs of different launches overlap in time.  Two CTA PAIRS sharing a TPC can each win tcgen05.alloc on one SM and
-    // wait forever for the other (observed as a hang with small-K draft-model GEMMs whose rings need < half an SM's
-    // shared memory); asking for more than half of the SM's shared memory makes co-residency impossible.
+    // CTAs of different launches overlap in time.  A CTA that was launched early (PDL) and already holds TMEM while it
+    // waits for its predecessor must never share an SM with a predecessor CTA that has not allocated yet; asking for more
+    // than half of the SM's shared memory makes co-residency impossible.
     if (smem_bytes < EXCLUSIVE_SMEM_BYTES) smem_bytes = EXCLUSIVE_SMEM_BYTES;
-    static int max_dyn = 0;
-    if (!max_dyn) {
-        cudaFuncAttributes fa;
-        ATS_CUDA(cudaFuncGetAttributes(&fa, gemm_wx_tcgen05));
-        const int want = 227 * 1024 - static_cast<int>(fa.sharedSizeBytes);   // static barriers share the 227 KiB budget
-        ATS_CUDA(cudaFuncSetAttribute(gemm_wx_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-        max_dyn = want;
-    }
+    int max_dyn = 0;
+    ATS_TRY(gemm_init_device(&max_dyn));
     ATS_CHECK_ARG(static_cast<int>(smem_bytes) <= max_dyn, "gemm: %zu bytes of shared memory > %d", smem_bytes, max_dyn);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1149,50 +903,22 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // previous kernel; see griddepcontrol.wait
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    if (const char* e = getenv("ATSPEED_GEMM_DBG")) p.dbg = atoi(e);
-    const CUtensorMap* tw = pl.BM == 256 ? w.tmap256 : w.tmap;
-    p.tma_store = om.ok;
-    if (pl.four_cta) {
-        static int max_dyn4 = 0;
-        if (!max_dyn4) {
-            cudaFuncAttributes fa;
-            ATS_CUDA(cudaFuncGetAttributes(&fa, gemm_wx_tcgen05_4cta));
-            const int want = 227 * 1024 - static_cast<int>(fa.sharedSizeBytes);
-            ATS_CUDA(cudaFuncSetAttribute(gemm_wx_tcgen05_4cta, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-            max_dyn4 = want;
-        }
-        ATS_CHECK_ARG(static_cast<int>(smem_bytes) <= max_dyn4 && (pl.grid & 3) == 0, "gemm (4-CTA): smem %zu grid %d", smem_bytes, pl.grid);
-        ATS_CHECK_ARG(xm.box0 * 4 * pl.n_mma == pl.n_mma * pl.N_mma, "gemm (4-CTA): activation map box %d does not match N_mma %d",
-                      xm.box0, pl.N_mma);
-        tw = w.tmap;      // each CTA loads its own 128-row box
-        ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_4cta, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, om.tm[0],
-                                    om.tm[1], om.tm[2], p));
-        return ATS_OK;
-    }
     if (pl.two_cta) {
-        static int max_dyn2 = 0;
-        if (!max_dyn2) {
-            cudaFuncAttributes fa;
-            ATS_CUDA(cudaFuncGetAttributes(&fa, gemm_wx_tcgen05_2cta));
-            const int want = 227 * 1024 - static_cast<int>(fa.sharedSizeBytes);
-            ATS_CUDA(cudaFuncSetAttribute(gemm_wx_tcgen05_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-            max_dyn2 = want;
-        }
-        ATS_CHECK_ARG(static_cast<int>(smem_bytes) <= max_dyn2 && (pl.grid & 1) == 0, "gemm (2-CTA): smem %zu grid %d", smem_bytes, pl.grid);
-        tw = w.tmap;      // each CTA of the pair loads its own 128-row box
+        ATS_CHECK_ARG((pl.grid & 1) == 0, "gemm (2-CTA): grid %d", pl.grid);
+        const CUtensorMap* tw = w.tmap;      // each CTA of the pair loads its own 128-row box
         ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, om.tm[0],
                                     om.tm[1], om.tm[2], p));
         return ATS_OK;
     }
+    const CUtensorMap* tw = pl.BM == 256 ? w.tmap256 : w.tmap;
     ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1,
                                 om.tm[0], om.tm[1], om.tm[2], p));
     return ATS_OK;
 }
 
 bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("ATSPEED_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
-    return v == 1;
+    static const bool on = []() { const char* e = getenv("ATSPEED_PDL"); return !(e && atoi(e) == 0); }();   // thread-safe static init
+    return on;
 }
 
 }  // namespace atspeed

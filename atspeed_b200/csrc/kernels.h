@@ -25,7 +25,6 @@ struct GemmPlan {
     int max_slices;         // most slices any tile of this launch has
     int stages, tmem_cols, acc_stride, n_bufs, buf_stride;
     int two_cta, n_mma, N_mma;   // CTA-pair kernel (T > 256): see gemm_wx_tcgen05_2cta
-    int four_cta;                // EXPERIMENTAL 4-CTA clusters with multicast activations (ATSPEED_GEMM_4CTA=1), BM = 512
 };
 // What a consumer of the partial sums needs to know: how many slices hold column `col`.
 struct SplitMap {
@@ -40,7 +39,6 @@ struct SplitMap {
 };
 struct XMap { CUtensorMap tm0, tm1; int T, K, box0; };   // activation operand [T, K] bf16 (two boxes: tokens < 256, >= 256)
 bool gemm_use_2cta(int T);
-bool gemm_use_4cta(int T);
 int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, GemmPlan* plan);
 int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms);
 SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& plan);

@@ -20,18 +20,10 @@ namespace atspeed {
 
 static constexpr int GATHER_CHUNK = 16 * 1024;
 
-__global__ void __launch_bounds__(32)
-kv_gather_bulk_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base, long long src_plane_stride,
-                      long long dst_plane_stride, int row_bytes, const int* __restrict__ src_rows,
-                      const int* __restrict__ dst_rows, const int* __restrict__ n_rows_dev) {
-    extern __shared__ __align__(128) uint8_t buf[];
-    __shared__ __align__(8) uint64_t bar;
-    const int i = blockIdx.x, plane = blockIdx.y;
-    if (n_rows_dev != nullptr && i >= *n_rows_dev) return;
-    if (threadIdx.x != 0) return;
-    const uint8_t* src = src_base + plane * src_plane_stride + static_cast<long long>(src_rows[i]) * row_bytes;
-    uint8_t* dst = dst_base + plane * dst_plane_stride + static_cast<long long>(dst_rows[i]) * row_bytes;
-    const uint32_t bar_a = smem_u32(&bar), buf_a = smem_u32(buf);
+// one thread: row `src` -> shared memory -> row `dst`, GATHER_CHUNK bytes at a time (bounded wait: common.cuh)
+__device__ __forceinline__ void copy_row_bulk(const uint8_t* src, uint8_t* dst, int row_bytes, uint8_t* buf, uint64_t* bar,
+                                              const SpinGuard& guard) {
+    const uint32_t bar_a = smem_u32(bar), buf_a = smem_u32(buf);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     uint32_t phase = 0;
@@ -41,23 +33,27 @@ kv_gather_bulk_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict_
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_a),
                      "l"(src + off), "r"(n), "r"(bar_a)
                      : "memory");
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "W_%=:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@p bra D_%=;\n\t"
-            "bra W_%=;\n\t"
-            "D_%=:\n\t"
-            "}" ::"r"(bar_a),
-            "r"(phase)
-            : "memory");
+        mbar_wait_guarded(bar_a, phase, guard, HANG_K_KVGATHER, HANG_R_COPY, HANG_B_ROW, 0, static_cast<unsigned>(off), 0,
+                          static_cast<unsigned>(row_bytes), 0);
         phase ^= 1;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(buf_a), "r"(n)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // buffer reusable / safe to exit
     }
+}
+
+__global__ void __launch_bounds__(32)
+kv_gather_bulk_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base, long long src_plane_stride,
+                      long long dst_plane_stride, int row_bytes, const int* __restrict__ src_rows,
+                      const int* __restrict__ dst_rows, const int* __restrict__ n_rows_dev, SpinGuard guard) {
+    extern __shared__ __align__(128) uint8_t buf[];
+    __shared__ __align__(8) uint64_t bar;
+    const int i = blockIdx.x, plane = blockIdx.y;
+    if (n_rows_dev != nullptr && i >= *n_rows_dev) return;
+    if (threadIdx.x != 0) return;
+    copy_row_bulk(src_base + plane * src_plane_stride + static_cast<long long>(src_rows[i]) * row_bytes,
+                  dst_base + plane * dst_plane_stride + static_cast<long long>(dst_rows[i]) * row_bytes, row_bytes, buf, &bar, guard);
 }
 
 int kv_gather_rows_oop(const void* src_base, void* dst_base, long long src_plane_stride, long long dst_plane_stride,
@@ -71,48 +67,22 @@ int kv_gather_rows_oop(const void* src_base, void* dst_base, long long src_plane
     const int smem = row_bytes < GATHER_CHUNK ? row_bytes : GATHER_CHUNK;
     dim3 grid(max_rows, n_planes);
     kv_gather_bulk_kernel<<<grid, 32, smem, st>>>(static_cast<const uint8_t*>(src_base), static_cast<uint8_t*>(dst_base),
-                                                  src_plane_stride, dst_plane_stride, row_bytes, src, dst, n_rows_dev);
+                                                  src_plane_stride, dst_plane_stride, row_bytes, src, dst, n_rows_dev, spin_guard());
     ATS_LAUNCH_CHECK();
     return ATS_OK;
 }
 
+// cohort variant: grid.z = user; user u moves rows inside its own cache (base + byte_off[u]) using its own lists
 __global__ void __launch_bounds__(32)
-kv_gather_cohort_kernel(uint8_t* __restrict__ base, long long plane_stride, int row_bytes, GatherCohort gc) {
+kv_gather_cohort_kernel(uint8_t* __restrict__ base, long long plane_stride, int row_bytes, GatherCohort gc, SpinGuard guard) {
     extern __shared__ __align__(128) uint8_t buf[];
     __shared__ __align__(8) uint64_t bar;
     const int i = blockIdx.x, plane = blockIdx.y, u = blockIdx.z;
     if (i >= *gc.n_rows[u]) return;
     if (threadIdx.x != 0) return;
     uint8_t* ub = base + gc.byte_off[u] + plane * plane_stride;
-    const uint8_t* src = ub + static_cast<long long>(gc.src[u][i]) * row_bytes;
-    uint8_t* dst = ub + static_cast<long long>(gc.dst[u][i]) * row_bytes;
-    const uint32_t bar_a = smem_u32(&bar), buf_a = smem_u32(buf);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    uint32_t phase = 0;
-    for (int off = 0; off < row_bytes; off += GATHER_CHUNK) {
-        const uint32_t n = static_cast<uint32_t>(row_bytes - off < GATHER_CHUNK ? row_bytes - off : GATHER_CHUNK);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(n) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_a),
-                     "l"(src + off), "r"(n), "r"(bar_a)
-                     : "memory");
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "W_%=:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@p bra D_%=;\n\t"
-            "bra W_%=;\n\t"
-            "D_%=:\n\t"
-            "}" ::"r"(bar_a),
-            "r"(phase)
-            : "memory");
-        phase ^= 1;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(buf_a), "r"(n)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
+    copy_row_bulk(ub + static_cast<long long>(gc.src[u][i]) * row_bytes, ub + static_cast<long long>(gc.dst[u][i]) * row_bytes,
+                  row_bytes, buf, &bar, guard);
 }
 
 int kv_gather_rows_cohort(void* base, long long plane_stride, int n_planes, int row_bytes, const GatherCohort& gc,
@@ -121,7 +91,7 @@ int kv_gather_rows_cohort(void* base, long long plane_stride, int n_planes, int 
     ATS_CHECK_ARG(gc.n >= 1 && gc.n <= MAX_USERS && max_rows >= 1 && n_planes >= 1, "kv_gather: users=%d rows=%d", gc.n, max_rows);
     const int smem = row_bytes < GATHER_CHUNK ? row_bytes : GATHER_CHUNK;
     dim3 grid(max_rows, n_planes, gc.n);
-    kv_gather_cohort_kernel<<<grid, 32, smem, st>>>(static_cast<uint8_t*>(base), plane_stride, row_bytes, gc);
+    kv_gather_cohort_kernel<<<grid, 32, smem, st>>>(static_cast<uint8_t*>(base), plane_stride, row_bytes, gc, spin_guard());
     ATS_LAUNCH_CHECK();
     return ATS_OK;
 }

@@ -23,8 +23,10 @@ lists per step.  `--impl reference` times the CPU oracle port alone (rank 0 only
 
 Also on the line: `pass_consistency` (the host-buffer pass re-runs the device-resident pass's last step: the ranked lists
 must be identical), `kernel_groups` (share of a user's GPU time and algorithmic GB/s per kernel family), `hf_gpu_baseline`
-(transformers generate(num_beams=K) on the same GPU, N = 1).  stderr carries phase breadcrumbs; a watchdog ends a stalled
-run with every thread's stack and the partial result (`"incomplete"`), see DESIGN.md section 6.
+(transformers generate(num_beams=K) on the same GPU, N = 1: the north star's ">= 2x HF beam search" comparison, reference
+code/inference.py:177-181 `speedupTF`).  stderr carries phase breadcrumbs; a watchdog ends a stalled run with every thread's
+stack, the partial result (`"incomplete"`) and a NON-ZERO exit code, see DESIGN.md section 6.  Every N runs the same kernel
+configuration (the CTA-pair GEMM is opt-in through ATSPEED_GEMM_2CTA=1 at any N; `config.gemm_pair_kernel` says which).
 """
 import argparse
 import json
@@ -71,7 +73,12 @@ def parse():
     ap.add_argument("--N", type=int, default=40)
     ap.add_argument("--gamma", type=int, default=3)
     ap.add_argument("--target", default="7b")
-    ap.add_argument("--draft", default="68m")
+    ap.add_argument("--draft", default="68m",
+                    help="draft shape; 'corr2' = a CORRELATED draft: the target's first 2 layers, embedding and lm_head plus 3 %% "
+                         "noise (random independent weights accept ~0 steps; this exercises speculation at the target's shape)")
+    ap.add_argument("--check-users", type=int, default=0,
+                    help="parity record at the benchmark shape: this many users also go through oracle/bssd_ref.py on the host "
+                         "with the GPU's own weights (bf16 contract); ranked lists + accepted lengths compared (slow: ~10 s/user)")
     ap.add_argument("--constraint", default="strict", choices=["strict", "positional"])
     ap.add_argument("--profile-users", type=int, default=4)
     ap.add_argument("--lanes", type=int, default=3,
@@ -82,14 +89,15 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--emulate-shard", default=None, metavar="R/W",
                     help="diagnostic: on ONE GPU, process the user slice rank R of W would get (no collective), e.g. 0/8")
-    ap.add_argument("--hf-baseline-users", type=int, default=5,
-                    help="also time HF generate(num_beams=K) on the same GPU (N=1 only; 0 = skip)")
+    ap.add_argument("--hf-baseline-users", type=int, default=12,
+                    help="also time HF generate(num_beams=K) on the same GPU after 3 warm-up calls (N=1 only; 0 = skip)")
     return ap.parse_args()
 
 
 def workload_name(a):
     mode = "AtSpeed-R relaxed acceptance (do_sample, top_k=50, T=1)" if a.do_sample else "AtSpeed-S strict top-K verify"
-    return (f"LLaMA-{a.target}-shape target + LLaMA-{a.draft}-shape draft, {mode}, "
+    draft = "correlated 2-layer draft cut from the target (+3% noise)" if a.draft == "corr2" else f"LLaMA-{a.draft}-shape draft"
+    return (f"LLaMA-{a.target}-shape target + {draft}, {mode}, "
             f"{a.dataset} test users, {a.constraint} constraint, K={a.K} N={a.N} gamma={a.gamma} max_new_tokens=4, "
             f"{a.users_per_step} users/step/GPU, " +
             (f"cohorts of up to {a.cohort} users per forward (<={a.cohort_tokens} tokens), {a.lanes} cohorts in flight per GPU"
@@ -112,6 +120,60 @@ def gpu_weights(spec, seed, device):
                             "ln1": torch.ones(spec.hidden, device=device, dtype=torch.bfloat16),
                             "ln2": torch.ones(spec.hidden, device=device, dtype=torch.bfloat16)})
     return W
+
+
+def correlated_draft_weights(tdm, n_layers, noise, device):
+    """The target's embedding, first `n_layers` layers, final norm and lm_head, each matrix perturbed by `noise` x its own
+    standard deviation: a draft whose beams agree with the target often enough to exercise accepted steps (SURVEY hard part 5)."""
+    g = torch.Generator(device=device).manual_seed(3)
+
+    def pert(t):
+        if t.dim() < 2:
+            return t.clone()
+        n = torch.randn(t.shape, generator=g, device=device, dtype=torch.float32)
+        return (t.float() + noise * t.float().std() * n).to(torch.bfloat16)
+
+    return {"embed": pert(tdm.embed), "norm": tdm.norm.clone(), "lm_head": pert(tdm.lm_head),
+            "layers": [{k: pert(v) for k, v in ly.items()} for ly in tdm.layers[:n_layers]]}
+
+
+def check_users_against_oracle(a, ds, fn, tdm, ddm, sess, users, prompts_host):
+    """Parity record at the benchmark shape: the same users through oracle/bssd_ref.py on the host cores
+    with the GPU's own weights (bf16 contract of oracle/llama_ref.py), single search each.  Strict mode only."""
+    from oracle import bssd_ref
+    from oracle import llama_ref as LR
+    host_threads()
+    models = []
+    for dm in (tdm, ddm):
+        sp = dm.spec
+        sh = LR.LlamaShape(sp.vocab, sp.hidden, sp.n_layers, sp.n_heads, sp.mlp, sp.head_dim, sp.rope_theta, sp.eps)
+        W = {"embed": dm.embed, "norm": dm.norm, "lm_head": dm.lm_head, "layers": dm.layers}
+        models.append(LR.RefLlama(sh, W, "bf16"))
+    tol = 6e-2
+    rec = {"users": 0, "identical_ranked_lists": 0, "explained_by_near_tie": 0, "identical_accept_steps": 0, "unexplained": [],
+           "tolerance": tol, "cpu_s_per_user": 0.0}
+    t0 = time.perf_counter()
+    for u in users:
+        log("check-users: user %d through the oracle" % u)
+        bssd_ref.GAP_LOG = []
+        try:
+            ref = bssd_ref.bssd(models[0], models[1], prompts_host[u], a.K, a.N, a.gamma, 4, fn)
+            margin = min(bssd_ref.GAP_LOG) if bssd_ref.GAP_LOG else float("inf")
+        finally:
+            bssd_ref.GAP_LOG = None
+        o = sess.bssd_batch([prompts_host[u]], a.gamma)[0] if a.cohort > 1 else sess.bssd(prompts_host[u], a.gamma)
+        P = len(prompts_host[u])
+        mine, theirs = o["tokens"][:, :4].tolist(), ref.sequences[:, P:].tolist()
+        rec["users"] += 1
+        rec["identical_accept_steps"] += int(list(o["accept_steps"]) == list(ref.accept_steps))
+        if mine == theirs:
+            rec["identical_ranked_lists"] += 1
+        elif margin < tol:
+            rec["explained_by_near_tie"] += 1
+        else:
+            rec["unexplained"].append({"user": int(u), "smallest_oracle_margin": margin})
+    rec["cpu_s_per_user"] = (time.perf_counter() - t0) / max(1, rec["users"])
+    return rec
 
 
 class ClockSampler:
@@ -158,13 +220,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
-    written by tools/ncu_traffic.py from dram__bytes_read.sum + dram__bytes_write.sum); None if not captured."""
+def ncu_traffic(kernel, mode):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of THIS configuration
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from dram__bytes_read.sum + dram__bytes_write.sum per launch;
+    entries are keyed "<kernel>/<mode>", mode = "cohort" | "single"); None when that kernel/mode was not captured -- a
+    capture of another configuration is never substituted."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None, None
-    j = json.load(open(p)).get(kernel)
+    j = json.load(open(p)).get("%s/%s" % (kernel, mode))
     if not j:
         return None, None
     return j["dram_bytes_per_launch"], j
@@ -188,7 +252,7 @@ def cpu_models(a, vocab):
     from oracle import llama_ref as LR
     out = []
     for name, seed in ((a.target, 1), (a.draft, 2)):
-        s = SHAPES[name]
+        s = SHAPES[name] if name != "corr2" else dict(SHAPES[a.target], n_layers=2)
         sh = LR.LlamaShape(vocab, s["hidden"], 1, s["n_heads"], s["mlp"])
         W = LR.make_weights(sh, seed, std=0.02)
         W["layers"] = W["layers"] * s["n_layers"]
@@ -269,10 +333,13 @@ def atspeed_arm(a, rank, world, local_rank):
     fn = make_fn(ds, a.constraint)
     specs = []
     for name in (a.target, a.draft):
-        s = SHAPES[name]
+        s = SHAPES[name] if name != "corr2" else dict(SHAPES[a.target], n_layers=2)
         specs.append(ModelSpec(V, s["hidden"], s["n_layers"], s["n_heads"], s["hidden"] // s["n_heads"], s["mlp"]))
     tdm = DeviceModel(specs[0], gpu_weights(specs[0], 1, dev), dev)
-    ddm = DeviceModel(specs[1], gpu_weights(specs[1], 2, dev), dev)
+    if a.draft == "corr2":
+        ddm = DeviceModel(specs[1], correlated_draft_weights(tdm, 2, 0.03, dev), dev)
+    else:
+        ddm = DeviceModel(specs[1], gpu_weights(specs[1], 2, dev), dev)
     csr = compile_constraint(fn, ds.prompt_ids(0), 4, other_prompt=ds.prompt_ids(1))
     dtrie = DeviceTrie(csr, dev)
     skw = dict(do_sample=True, top_k=50, temperature=1.0, seed=2025) if a.do_sample else {}
@@ -412,7 +479,7 @@ def atspeed_arm(a, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (13.5 GB of weights streamed per forward)",
                        "parallelism": f"user-sharded x{world}, one all-gather of ranked lists per step",
-                       "gemm_pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "1") != "0"},
+                       "gemm_pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "0") == "1"},
             "clocks": clocks.summary(), "gpu_launches": int(launches),
             "accepted_tokens_per_verify": accept * a.K / max(1, runs)}
     STATE["partial"] = dict(base)          # what the watchdog prints if a later phase stalls
@@ -445,15 +512,43 @@ def atspeed_arm(a, rank, world, local_rank):
     e2e = {"value": users_total / float(e2e_s.item()), "unit": "users/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
     STATE["partial"] = dict(base, e2e=e2e, pass_consistency=consistency)
     log("host-buffer pass done: %.1f users/s (%s); single-search latency" % (e2e["value"], consistency))
-    # single-search latency (nothing else in flight on the GPU): what one user waits for
-    lat1 = []
-    for u in step_users[a.warmup][: min(U, 8)]:
+    # single-search latency (nothing else in flight on the GPU): what one user waits for; the ranked lists are kept for the
+    # parity record against HF generate on the same weights
+    lat1, ours = [], {}
+    hf_users = step_users[a.warmup][: min(U, max(8, a.hf_baseline_users))]
+    for u in hf_users:
         t0 = time.perf_counter()
-        if a.cohort > 1:
-            sess.bssd_batch([prompts_host[u]], a.gamma)
-        else:
-            sess.bssd(prompts_host[u], a.gamma)
+        o = sess.bssd_batch([prompts_host[u]], a.gamma)[0] if a.cohort > 1 else sess.bssd(prompts_host[u], a.gamma)
         lat1.append(time.perf_counter() - t0)
+        ours[u] = (o["tokens"], o["scores"])
+    out = dict(base)
+    out.update({"e2e": e2e,
+                "latency_ms_p50": float(np.percentile(np.asarray(lat1) * 1e3, 50)),
+                "latency_ms_p95": float(np.percentile(np.asarray(lat1) * 1e3, 95)),
+                "latency_ms_p50_loaded": float(np.percentile(np.asarray(lat) * 1e3, 50)),
+                "pass_consistency": consistency})
+    STATE["partial"] = dict(out)
+    if rank == 0 and world == 1 and a.check_users > 0 and not a.do_sample:
+        out["parity_vs_oracle"] = check_users_against_oracle(a, ds, fn, tdm, ddm, sess, hf_users[: a.check_users], prompts_host)
+        STATE["partial"] = dict(out)
+    # ---- CPU baseline (rank 0, N = 1): the oracle port on the host cores, bounded sample ----
+    if rank == 0:
+        if world == 1 and not a.no_cpu_baseline:
+            log("cpu_baseline: users through the oracle port")
+            host_threads()
+            models = cpu_models(a, V)
+            dt, n_cpu = 0.0, 0
+            while dt < 10.0 and n_cpu < 8:           # bounded sample: >= 10 s of CPU work or 8 users, whichever comes first
+                t1, _ = cpu_one_user(a, models, ds, fn, step_users[a.warmup][n_cpu % U])
+                dt, n_cpu = dt + t1, n_cpu + 1
+                log("cpu_baseline: %d user(s), %.1f s" % (n_cpu, dt))
+            del models
+            out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": "%d user(s) of the same workload through oracle/bssd_ref.py (fp32, layer weights "
+                                             "shared across layers); %.1f s of CPU work" % (n_cpu, dt)}
+        else:
+            out["cpu_baseline"] = None
+        STATE["partial"] = dict(out)
     # ---- profiled pass (roofline of the dominant kernel, share of step per kernel group) ----
     roofline, groups = None, None
     if rank == 0:
@@ -482,48 +577,42 @@ def atspeed_arm(a, rank, world, local_rank):
         # which resource bounds the launches in aggregate: time the algorithmic bytes need at the measured copy peak vs
         # time the FLOPs need at the measured sustained cuBLAS peak (cohort forwards are large enough to be tensor-bound)
         t_hbm, t_tensor = g["bytes"] / (peak * 1e9), g["flops"] / (peak_tf * 1e12)
-        traffic, tinfo = ncu_traffic("gemm_wx_tcgen05")
+        kname = "gemm_wx_tcgen05" + ("_2cta" if base["config"]["gemm_pair_kernel"] else "")
+        traffic, tinfo = ncu_traffic(kname, "cohort" if a.cohort > 1 else "single")
         if t_tensor > t_hbm:
-            roofline = {"kernel": "gemm_wx_tcgen05", "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            roofline = {"kernel": kname, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": ach_tf / peak_tf, "hbm_achieved_gbs": ach, "hbm_frac": ach / peak}
         else:
-            roofline = {"kernel": "gemm_wx_tcgen05", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+            roofline = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "tensor_achieved_tflops": ach_tf, "tensor_frac": ach_tf / peak_tf}
         roofline.update({"traffic": traffic, "traffic_source": tinfo, "peak_source": how,
                          "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]), "launches": g["launches"],
                          "algorithmic_bytes_per_launch": g["bytes"] / max(1, g["launches"]),
                          "flops_per_launch": g["flops"] / max(1, g["launches"]),
                          "roofline_time_frac": max(t_hbm, t_tensor) / sec if sec else 0.0})
-    out = dict(base)
-    out.update({"e2e": e2e,
-                "latency_ms_p50": float(np.percentile(np.asarray(lat1) * 1e3, 50)),
-                "latency_ms_p95": float(np.percentile(np.asarray(lat1) * 1e3, 95)),
-                "latency_ms_p50_loaded": float(np.percentile(np.asarray(lat) * 1e3, 50)),
-                "pass_consistency": consistency,
-                "kernel_groups": groups, "roofline": roofline})
+    out.update({"kernel_groups": groups, "roofline": roofline})
     STATE["partial"] = dict(out)
     if rank == 0:
-        if world == 1 and not a.no_cpu_baseline:
-            log("cpu_baseline: one user through the oracle port")
-            host_threads()
-            models = cpu_models(a, V)
-            dt, n_cpu = 0.0, 0
-            while dt < 10.0 and n_cpu < 8:           # bounded sample: >= 10 s of CPU work or 8 users, whichever comes first
-                t1, _ = cpu_one_user(a, models, ds, fn, step_users[a.warmup][n_cpu % U])
-                dt, n_cpu = dt + t1, n_cpu + 1
-                log("cpu_baseline: %d user(s), %.1f s" % (n_cpu, dt))
-            out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
-                                   "sample": "%d user(s) of the same workload through oracle/bssd_ref.py (fp32, layer weights "
-                                             "shared across layers); %.1f s of CPU work" % (n_cpu, dt)}
-        else:
-            out["cpu_baseline"] = None
+        # ---- HF generate on the same GPU, same shape, same weights: the north star's comparison (N = 1 only) ----
         if world == 1 and a.hf_baseline_users > 0:
             log("hf_gpu_baseline: transformers generate(num_beams=K) on the same GPU")
-            try:
-                out["hf_gpu_baseline"] = hf_baseline(a, ds, fn, dev, step_users[a.warmup][: a.hf_baseline_users])
-                out["hf_gpu_baseline"]["speedup_e2e"] = out["e2e"]["value"] / out["hf_gpu_baseline"]["users_per_s"]
-            except Exception as e:   # informative only: never fail the bench line on the comparison arm
-                out["hf_gpu_baseline"] = {"error": repr(e)[:200]}
+            box = {}
+
+            def run_hf():
+                try:
+                    W = {"embed": tdm.embed, "norm": tdm.norm, "lm_head": tdm.lm_head, "layers": tdm.layers}
+                    box["r"] = hf_baseline(a, ds, fn, dev, hf_users[: a.hf_baseline_users], W, ours)
+                except Exception as e:   # informative only: never fail the bench line on the comparison arm
+                    box["r"] = {"error": repr(e)[:300]}
+
+            th = threading.Thread(target=run_hf, daemon=True)
+            th.start()
+            th.join(float(os.environ.get("ATSPEED_BENCH_HF_LIMIT_S", 240)))
+            hf = box.get("r") or {"error": "timed out"}
+            if "users_per_s" in hf:
+                hf["speedup_e2e_throughput"] = out["e2e"]["value"] / hf["users_per_s"]           # cohorts x lanes vs HF
+                hf["speedup_single_search"] = hf["latency_ms_p50"] / out["latency_ms_p50"]       # one user alone vs HF (speedupTF)
+            out["hf_gpu_baseline"] = hf
         STATE["partial"] = None
         print(json.dumps(out), flush=True)
         STATE["printed"] = True
@@ -534,9 +623,13 @@ def atspeed_arm(a, rank, world, local_rank):
     log("done")
 
 
-def hf_baseline(a, ds, fn, dev, users):
-    """HF `generate(num_beams=K, prefix_allowed_tokens_fn=...)` on the same GPU and shape (reference
-    code/inference.py:177-178, the `TF_target` column): the north star's >= 2x comparison.  Informative only."""
+def hf_baseline(a, ds, fn, dev, users, weights=None, ours=None):
+    """HF `generate(num_beams=K, prefix_allowed_tokens_fn=...)` on the same GPU, shape and -- when `weights` is given -- the
+    same random-init weights (reference code/inference.py:177-178, the `TF_target` column): the north star's >= 2x
+    comparison, one user at a time as the reference runs it.  3 untimed warm-up calls, then every user of `users`.
+    `ours`: {user: (tokens [K,4], scores [K])} from this repo's single-search runs of the same users -> a parity record at
+    the benchmark shape (ranked lists identical / explained by a bf16 near-tie; HF's sequences_scores x 4 = summed
+    log-probs).  Never fails the bench line."""
     from transformers import LlamaConfig, LlamaForCausalLM
     s = SHAPES[a.target]
     cfg = LlamaConfig(vocab_size=ds.vocab_size, hidden_size=s["hidden"], intermediate_size=s["mlp"],
@@ -544,29 +637,70 @@ def hf_baseline(a, ds, fn, dev, users):
                       tie_word_embeddings=False, pad_token_id=0, bos_token_id=1, eos_token_id=2)
     with torch.device(dev):
         m = LlamaForCausalLM(cfg).to(torch.bfloat16).eval()
-    lat = []
-    for i, u in enumerate([users[0], users[0]] + list(users)):     # two untimed warm-up calls (lazy init, autotuning)
+    same_weights = False
+    if weights is not None:
+        sd = {"model.embed_tokens.weight": weights["embed"], "model.norm.weight": weights["norm"], "lm_head.weight": weights["lm_head"]}
+        names = {"wq": "self_attn.q_proj", "wk": "self_attn.k_proj", "wv": "self_attn.v_proj", "wo": "self_attn.o_proj",
+                 "wg": "mlp.gate_proj", "wu": "mlp.up_proj", "wd": "mlp.down_proj", "ln1": "input_layernorm",
+                 "ln2": "post_attention_layernorm"}
+        for i, ly in enumerate(weights["layers"]):
+            for k, n in names.items():
+                sd[f"model.layers.{i}.{n}.weight"] = ly[k]
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        same_weights = not [k for k in missing if "rotary" not in k and "inv_freq" not in k]
+    lat, lists = [], {}
+    seq = [users[0]] * 3 + list(users)                              # three untimed warm-up calls (lazy init, autotuning)
+    for i, u in enumerate(seq):
         ids = torch.tensor([ds.prompt_ids(u)], device=dev)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         with torch.no_grad():
-            m.generate(input_ids=ids, num_beams=a.K, num_return_sequences=a.K, max_new_tokens=4, do_sample=False,
-                       prefix_allowed_tokens_fn=fn, use_cache=True, pad_token_id=0)
+            o = m.generate(input_ids=ids, num_beams=a.K, num_return_sequences=a.K, max_new_tokens=4, do_sample=False,
+                           prefix_allowed_tokens_fn=fn, use_cache=True, pad_token_id=0, output_scores=True,
+                           return_dict_in_generate=True, length_penalty=1.0, early_stopping=False)
         torch.cuda.synchronize(dev)
-        if i >= 2:
+        if i >= 3:
             lat.append(time.perf_counter() - t0)
+            sc = getattr(o, "sequences_scores", None)
+            lists[u] = (o.sequences[:, ids.shape[1]:].cpu().numpy(), None if sc is None else (sc.float().cpu().numpy() * 4.0))
     del m
     torch.cuda.empty_cache()
-    p50 = float(np.percentile(np.asarray(lat) * 1e3, 50))
-    return {"users_per_s": 1e3 / p50, "users_per_s_mean": len(lat) / sum(lat), "latency_ms_p50": p50, "users": len(lat),
-            "what": "transformers LlamaForCausalLM.generate(num_beams=K) bf16, same GPU, same shape, one user at a time "
-                    "(users_per_s = 1 / p50 latency)"}
+    ms = np.asarray(lat) * 1e3
+    out = {"users_per_s": len(lat) / float(sum(lat)), "latency_ms_p50": float(np.percentile(ms, 50)),
+           "latency_ms_mean": float(ms.mean()), "latency_ms_min": float(ms.min()), "latency_ms_max": float(ms.max()),
+           "users": len(lat), "same_weights_as_target": bool(same_weights),
+           "what": "transformers LlamaForCausalLM.generate(num_beams=K, prefix_allowed_tokens_fn) bf16, same GPU, same shape, "
+                   "one user at a time as code/inference.py:177-178 runs it; users_per_s = users / sum of latencies"}
+    if ours and same_weights:
+        tol = 6e-2                      # bf16 near-tie tolerance on cumulative log-probs (tests/_common.py BF16_SCORE_TOL)
+        ident = near = 0
+        worst = 0.0
+        for u, (hf_t, hf_s) in lists.items():
+            if u not in ours:
+                continue
+            t, sc = ours[u]
+            a_l, b_l = [tuple(r) for r in t[:, :4].tolist()], [tuple(r) for r in hf_t[:, :4].tolist()]
+            if a_l == b_l:
+                ident += 1
+                if hf_s is not None:
+                    worst = max(worst, float(np.max(np.abs(np.asarray(sc) - hf_s[: len(sc)]))))
+            elif hf_s is not None:
+                # explained by a near-tie: every item that is in one list only sits within tol of the other list's cut-off
+                sa, sb = dict(zip(a_l, sc)), dict(zip(b_l, hf_s))
+                ok = all(abs(sa[x] - min(hf_s)) < tol for x in a_l if x not in sb) and \
+                     all(abs(sb[x] - min(sc)) < tol for x in b_l if x not in sa)
+                near += int(ok)
+        out["parity_vs_ours"] = {"users": len([u for u in lists if u in ours]), "identical_ranked_lists": ident,
+                                 "explained_by_near_tie": near, "max_abs_score_diff_identical": worst, "tolerance": tol,
+                                 "note": "bf16 contract: different GEMM summation orders flip near-ties (DESIGN.md section 2)"}
+    return out
 
 
 def arm_watchdog(total_s, stall_s):
     """A stalled GPU or collective must not hang the caller.  When the run exceeds `total_s`, or no phase breadcrumb has been
     written for `stall_s`, every thread's Python stack goes to stderr (where did the host stop?), rank 0 prints what it has
-    measured so far -- marked incomplete -- and the process exits (torchrun then stops the other ranks)."""
+    measured so far -- marked incomplete -- and the process exits with code 17 (torchrun then stops the other ranks).  The
+    only os._exit(0) is the case where the complete result line is already out and only the teardown stalled."""
     def fire(why):
         import faulthandler
         sys.stderr.write("bench.py watchdog [r%d]: %s; last phase: %s\n" % (STATE["rank"], why, STATE["phase"]))
@@ -578,12 +712,10 @@ def arm_watchdog(total_s, stall_s):
         if STATE.get("printed"):      # the result line is out; only the teardown stalled
             os._exit(0)
         part = STATE.get("partial")
-        if part is not None:      # set on every rank once the device-resident pass is through
-            if STATE["rank"] == 0:
-                part["incomplete"] = "stalled in phase '%s'; keys measured after it are absent" % STATE["phase"]
-                print(json.dumps(part), flush=True)
-            os._exit(0)
-        os._exit(17)
+        if part is not None and STATE["rank"] == 0:      # whatever was measured before the stall, marked as such
+            part["incomplete"] = "stalled in phase '%s'; keys measured after it are absent" % STATE["phase"]
+            print(json.dumps(part), flush=True)
+        os._exit(17)              # a stalled run is a FAILED run, with or without a partial line
 
     def watch():
         while True:
@@ -600,19 +732,14 @@ def arm_watchdog(total_s, stall_s):
 
 
 def multi_gpu_env(world):
-    """Conservative settings for N > 1 (only defaults: anything the caller exports wins).
-      * the one collective moves ~12 KB per step, so NVSwitch multicast (NVLS) buys nothing: leave its set-up out of the
-        communicator's initialisation;
-      * the CTA-pair GEMM (cta_group::2, T > 256) has only been validated in single-process runs -- the only verified
-        multi-GPU run (2 GPUs, profiles/r01_bench_n2.json) used the single-CTA kernel for every T, and the two 8-GPU
-        attempts that included the pair kernel did not finish.  Until that is understood the
-        multi-GPU bench runs the configuration that is known to work; the line says so in config.gemm_pair_kernel."""
+    """Communicator settings for N > 1 (only defaults: anything the caller exports wins): the one collective moves ~12 KB
+    per step, so NVSwitch multicast (NVLS) buys nothing -- leave its set-up out of the communicator's initialisation.  The
+    kernels are the same at every N (the CTA-pair GEMM is opt-in everywhere, config.gemm_pair_kernel)."""
     if world > 1:
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         os.environ.setdefault("NCCL_MNNVL_ENABLE", "0")      # one box: no multi-node NVLink / IMEX probing either
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
-        os.environ.setdefault("ATSPEED_GEMM_2CTA", "0")
 
 
 def main():
@@ -651,14 +778,18 @@ def main():
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
-        # every rank has passed its last collective and rank 0 has printed: tear the communicator down, but never let the
-        # teardown (which can wait on peers that are still profiling) keep the process alive
+        # every rank has passed its last collective and rank 0 has printed: tear the communicator down with a bound (the
+        # teardown can wait on peers), then leave through the interpreter's normal exit so atexit hooks run
         import torch.distributed as dist
         t = threading.Thread(target=dist.destroy_process_group, daemon=True)
         t.start()
         t.join(30.0)
-        os._exit(0)
+        if t.is_alive():
+            sys.stderr.write("bench.py [r%d]: communicator teardown did not finish in 30 s\n" % rank)
+            os._exit(0)           # the result line is out; only the teardown stalled
+    STATE["t_phase"] = time.perf_counter()
+    return 0
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

@@ -33,6 +33,10 @@ from .llama_ref import RefCache, RefLlama
 
 NEG_INF = float("-inf")
 GAP_LOG = None   # set to a list to record, for every greedy top-k, the score margin at the cut-off (near-tie diagnostics)
+# set to a list to record, for every greedy top-k, {"cand": {generated-sequence tuple: score} over ALL finite candidates,
+# "kept": [sequence tuples in rank order]} -- tests/test_gpu_e2e.py locates the level where a bf16 run leaves the oracle's
+# trajectory and checks the margin THERE
+LEVEL_LOG = None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -222,6 +226,11 @@ def _expand(logits_rows: torch.Tensor, frontier: List[Node], width: int, fn, pro
         if GAP_LOG is not None and len(vals) > width:
             GAP_LOG.append(float(vals[width - 1] - vals[width]))   # margin between the last kept and first dropped
         vals, idx = vals[:width], idx[:width]
+        if LEVEL_LOG is not None:
+            fin = torch.nonzero(torch.isfinite(flat)).view(-1)
+            gens = [tuple(n.gen()) for n in frontier]
+            LEVEL_LOG.append({"cand": {gens[int(i // V)] + (int(i % V),): float(flat[i]) for i in fin},
+                              "kept": [gens[int(i // V)] + (int(i % V),) for i in idx]})
     kids = [Node(int(i % V), frontier[int(i // V)], float(v)) for v, i in zip(vals, idx)]
     return kids, idx, probs, flat
 

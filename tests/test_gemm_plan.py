@@ -15,9 +15,15 @@ SHAPES = [(4096, (4096, 4096, 4096)), (4096, (4096,)), (4096, (11008, 11008)), (
 @pytest.mark.parametrize("K,rows", SHAPES)
 @pytest.mark.parametrize("T", [1, 10, 16, 50, 90, 128, 130, 220, 256, 289, 512])
 @pytest.mark.parametrize("cut", [1, 0])
-def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut):
+@pytest.mark.parametrize("pair", [0, 1])
+def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut, pair, monkeypatch):
+    """pair = 1: ATSPEED_GEMM_2CTA=1 opts into the CTA-pair kernel for T > 256 (off by default at every N)."""
     from atspeed_b200 import _lib
     lib = _lib.load()
+    if pair:
+        monkeypatch.setenv("ATSPEED_GEMM_2CTA", "1")
+    else:
+        monkeypatch.delenv("ATSPEED_GEMM_2CTA", raising=False)
     r = list(rows) + [0] * (3 - len(rows))
     info = (C.c_int32 * 16)()
     cols = sum(rows)
@@ -31,7 +37,7 @@ def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut):
         assert BM in (128, 256) and KB == -(-K // 64) and T_pad == -(-T // 16) * 16
         assert tiles == sum(-(-x // BM) for x in rows) == sum(tl)
         units = tiles * KB
-        assert two_cta == int(T_pad > 256), "the CTA-pair kernel serves exactly the forwards of more than 256 tokens"
+        assert two_cta == int(pair and T_pad > 256), "the CTA-pair kernel is opt-in and serves only forwards of > 256 tokens"
         n_workers = grid // 2 if two_cta else grid          # CTAs, or CTA pairs, that own a unit range
         assert (n_workers - 1) * U < units <= n_workers * U, "every worker owns at least one unit and the ranges cover all units"
         assert 2 <= stages <= 12 and tmem <= 512 and tmem & (tmem - 1) == 0
@@ -62,11 +68,17 @@ def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut):
         assert worst == max_slices
 
 
-def test_every_token_count_has_a_sane_plan():
+@pytest.mark.parametrize("pair", [0, 1])
+def test_every_token_count_has_a_sane_plan(pair, monkeypatch):
     """All T in 1..512 for the 7B and 68M projection shapes (cohort forwards pack arbitrary token counts): unit ranges
-    tile the work, rings fit in shared memory, accumulators fit in TMEM."""
+    tile the work, rings fit in shared memory, accumulators fit in TMEM -- for the default single-CTA kernel and for the
+    opt-in CTA-pair kernel."""
     from atspeed_b200 import _lib
     lib = _lib.load()
+    if pair:
+        monkeypatch.setenv("ATSPEED_GEMM_2CTA", "1")
+    else:
+        monkeypatch.delenv("ATSPEED_GEMM_2CTA", raising=False)
     shapes = {"qkv": (4096, (4096, 4096, 4096)), "o": (4096, (4096,)), "gu": (4096, (11008, 11008)), "down": (11008, (4096,)),
               "lm": (4096, (32859,)), "dqkv": (768, (768, 768, 768)), "do": (768, (768,)), "dgu": (768, (3072, 3072)),
               "ddown": (3072, (768,)), "dlm": (768, (33014,))}
@@ -78,53 +90,9 @@ def test_every_token_count_has_a_sane_plan():
             assert lib.atspeed_gemm_plan(T, K, r[0], r[1], r[2], 148, cut, info, None) == 0, (name, T)
             BM, KB, tiles, U, grid, ms, stages, tmem, bufs, T_pad, _, _, _, two, n_mma, N_mma = (int(x) for x in info)
             units = tiles * KB
+            assert two == int(pair and T_pad > 256)
             workers = grid // 2 if two else grid
             assert (workers - 1) * U < units <= workers * U and grid <= 148, (name, T)
             stage = 16384 + (n_mma * N_mma // 2) * 128 if two else BM * 128 + T_pad * 128
             assert 2 <= stages and stages * stage + 16384 + 1024 <= 226 * 1024, (name, T)
             assert tmem <= 512 and (bufs * n_mma * N_mma <= 512 if two else (BM // 128) * bufs * T_pad <= 512), (name, T)
-
-
-def test_experimental_4cta_plans(monkeypatch):
-    """ATSPEED_GEMM_4CTA=1 (off by default): clusters of four CTAs own 512-row tile groups.  Same invariants as
-    the other kernels -- cluster unit ranges tile the work, slice counts per column agree with the SplitMap arithmetic the
-    consumers use, rings and accumulators fit -- plus the quarter-box constraints of the multicast activation loads."""
-    from atspeed_b200 import _lib
-    lib = _lib.load()
-    info = (C.c_int32 * 16)()
-    shapes = [(4096, (4096, 4096, 4096)), (4096, (4096,)), (4096, (11008, 11008)), (11008, (4096,)), (4096, (32859,)),
-              (768, (768, 768, 768)), (3072, (768,)), (768, (33014,)), (192, (200, 72))]
-    monkeypatch.delenv("ATSPEED_GEMM_4CTA", raising=False)
-    assert lib.atspeed_gemm_plan(300, 4096, 4096, 0, 0, 148, 1, info, None) == 0 and info[13] == 1      # default: the pair kernel
-    monkeypatch.setenv("ATSPEED_GEMM_4CTA", "1")
-    for K, rows in shapes:
-        r = list(rows) + [0] * (3 - len(rows))
-        cols = sum(rows)
-        sl = (C.c_int32 * cols)()
-        for cut in (1, 0):
-            for T in (10, 256, 257, 289, 320, 390, 448, 512):
-                assert lib.atspeed_gemm_plan(T, K, r[0], r[1], r[2], 148, cut, info, sl) == 0, lib.atspeed_last_error()
-                BM, KB, tiles, U, grid, max_slices, stages, tmem, bufs, T_pad, t0, t1, t2, kind, n_mma, N_mma = (int(x) for x in info)
-                if T_pad <= 256:
-                    assert kind == 0 and BM in (128, 256)           # small forwards are untouched by the switch
-                    continue
-                assert kind == 2 and BM == 512 and grid % 4 == 0 and grid <= 148
-                assert tiles == sum(-(-x // 512) for x in rows) == t0 + t1 + t2
-                units, clusters = tiles * KB, grid // 4
-                assert (clusters - 1) * U < units <= clusters * U
-                assert n_mma in (1, 2) and N_mma % 32 == 0 and N_mma <= 256 and n_mma * N_mma >= T > n_mma * N_mma - 64
-                assert (N_mma // 4) * 128 % 1024 == 0               # a quarter box keeps the 128-byte swizzle phase
-                assert 2 <= stages and stages * (16384 + (n_mma * N_mma // 2) * 128) + 16384 + 1024 <= 226 * 1024
-                assert tmem <= 512 and bufs * n_mma * N_mma <= 512
-                if not cut:
-                    assert U % KB == 0 and max_slices == 1
-                slices = np.frombuffer(sl, dtype=np.int32)
-                col, t, worst = 0, 0, 0
-                for w in rows:
-                    for i in range(-(-w // 512)):
-                        n = ((t + 1) * KB - 1) // U - (t * KB) // U + 1
-                        worst = max(worst, n)
-                        assert (slices[col + i * 512: col + min(w, (i + 1) * 512)] == n).all()
-                        t += 1
-                    col += w
-                assert worst == max_slices

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from _common import BF16_SCORE_TOL, constraint_fn, dataset, lists_match, stack_weights
+from _common import BF16_SCORE_TOL, constraint_fn, dataset, lists_match, oracle_model, stack_weights
 
 pytestmark = pytest.mark.gpu
 
@@ -71,9 +71,17 @@ def test_cohort_matches_single_user_sessions(models, draft, kind, K, N, gamma, m
         exact += int(g["tokens"].tolist() == want["tokens"].tolist())
         same_accept += int(g["accept_steps"] == want["accept_steps"])
         if not ok:
-            # an intermediate-level near-tie: accepted only if the two runs took different accepted lengths or the scores
-            # of the differing beams sit within the tolerance of the cut-off (a real bug moves scores by far more)
-            assert abs(float(np.min(g["scores"])) - float(np.min(want["scores"]))) < 20 * BF16_SCORE_TOL, f"user {u}: {msg}"
+            # bf16 only (the cohort KERNELS are oracle-exact: tests/test_gpu_cohort_fp32.py): a different token count per
+            # forward moves the GEMM's k-cuts, which may flip a near-tie at an intermediate level.  Accepted only when the
+            # oracle's own search has a cut-off margin below the bf16 tolerance at some level for this user.
+            from oracle import bssd_ref
+            bssd_ref.GAP_LOG = []
+            try:
+                bssd_ref.target_generate(oracle_model("ref_bf16", "beauty", "target"), p, K, 4, constraint_fn("beauty", kind))
+                margin = min(bssd_ref.GAP_LOG)
+            finally:
+                bssd_ref.GAP_LOG = None
+            assert margin < BF16_SCORE_TOL, f"user {u}: {msg} | smallest oracle cut-off margin {margin:.4f}"
     print(f"cohort(max_users={max_users}) vs single-user: {exact}/{len(users)} lists identical, "
           f"{same_accept}/{len(users)} identical accepted lengths")
     assert exact >= 0.7 * len(users)

@@ -1,9 +1,12 @@
 """Reduce one or more `ncu --set full` reports to profiles/ncu_traffic.json + a readable table:
 per kernel, DRAM bytes (read + write) and duration per launch, DRAM / tensor-pipe utilisation.
-usage: python tools/ncu_traffic.py out.json rep1.ncu-rep [rep2.ncu-rep ...]   (runs `ncu -i ... --page raw --csv`)"""
+usage: python tools/ncu_traffic.py out.json MODE rep1.ncu-rep [rep2.ncu-rep ...]   (runs `ncu -i ... --page raw --csv`)
+MODE names the configuration the capture was taken in ("cohort" | "single" | "standalone"); entries are stored under
+"<kernel>/<MODE>" and MERGED into out.json, so bench.py can only ever pick the capture of the configuration it timed."""
 import csv
 import io
 import json
+import os
 import subprocess
 import sys
 from collections import defaultdict
@@ -24,7 +27,7 @@ def num(x):
         return None
 
 
-def main(out_json, reps):
+def main(out_json, mode, reps):
     agg = defaultdict(lambda: defaultdict(list))
     for rep in reps:
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -45,14 +48,21 @@ def main(out_json, reps):
         n = len(d["us"])
         mean = lambda key: sum(d[key]) / len(d[key]) if d[key] else None
         by = (mean("rd") or 0) + (mean("wr") or 0)
-        res[k] = {"dram_bytes_per_launch": by, "dram_read_bytes_per_launch": mean("rd"), "dram_write_bytes_per_launch": mean("wr"),
+        res[k + "/" + mode] = {"dram_bytes_per_launch": by, "dram_read_bytes_per_launch": mean("rd"), "dram_write_bytes_per_launch": mean("wr"),
                   "launches_captured": n, "avg_us_under_ncu": mean("us"), "dram_throughput_pct": mean("dram_pct"),
                   "tensor_pipe_pct": mean("tensor_pct"), "l2_hit_pct": mean("l2_hit"), "lts_bytes_per_launch": mean("lts_bytes"),
                   "source": [r.split("/")[-1] for r in reps]}
         print(f"{k[:44]:<44} {n:>3} {mean('us'):>8.1f} {by / 1e6:>8.2f} {by / mean('us') / 1e3:>7.0f} "
               f"{(mean('dram_pct') or 0):>6.1f} {(mean('tensor_pct') or 0):>6.1f} {(mean('l2_hit') or 0):>7.1f} {int(mean('regs') or 0):>5}")
-    json.dump(res, open(out_json, "w"), indent=1)
+    old = {}
+    if os.path.exists(out_json):
+        try:
+            old = {k: v for k, v in json.load(open(out_json)).items() if "/" in k}      # un-tagged (round 1) entries are dropped
+        except Exception:
+            old = {}
+    old.update(res)
+    json.dump(old, open(out_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2:])
+    main(sys.argv[1], sys.argv[2], sys.argv[3:])
