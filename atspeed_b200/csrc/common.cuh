@@ -92,7 +92,16 @@ struct SpinGuard {            // passed by value to the kernels that wait on mba
     HangDiag* diag;           // device-visible address of the mapped record (nullptr: trap without a record)
     unsigned long long limit_ns;
 };
+// Optional per-CTA progress trace of the GEMM kernels (ATSPEED_GEMM_TRACE=1; diagnostics only, off by default): 16 words
+// per CTA in mapped pinned host memory, readable WHILE a launch is stuck (atspeed_debug_gemm_trace) -- for the waits the
+// guard above cannot bound (tcgen05.alloc, cluster barriers, griddepcontrol.wait).
+struct GemmTrace {
+    unsigned int* buf;        // nullptr: tracing off
+    unsigned int seq;         // launch sequence number
+};
+constexpr int TRACE_WORDS = 16, TRACE_CTAS = 256;
 SpinGuard spin_guard();                       // engine.cu: mapped record (allocated once per process) + the limit
+GemmTrace gemm_trace();                       // engine.cu: {nullptr, 0} unless ATSPEED_GEMM_TRACE=1
 void hang_diag_describe(char* buf, size_t n); // engine.cu: "" when no record has been written
 
 // ---------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -41,6 +42,31 @@ SpinGuard spin_guard() {
         }
     });
     return SpinGuard{g_diag_dev, g_spin_limit_ns};
+}
+
+static unsigned int* g_trace_host = nullptr;
+static unsigned int* g_trace_dev = nullptr;
+static std::atomic<unsigned int> g_trace_seq{0};
+
+GemmTrace gemm_trace() {
+    static std::once_flag once;
+    std::call_once(once, []() {
+        const char* e = getenv("ATSPEED_GEMM_TRACE");
+        if (!(e && atoi(e) == 1)) return;
+        void* h = nullptr;
+        void* d = nullptr;
+        const size_t bytes = sizeof(unsigned int) * TRACE_WORDS * TRACE_CTAS;
+        if (cudaHostAlloc(&h, bytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+            cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+            memset(h, 0, bytes);
+            g_trace_host = static_cast<unsigned int*>(h);
+            g_trace_dev = static_cast<unsigned int*>(d);
+        } else {
+            cudaGetLastError();
+        }
+    });
+    if (!g_trace_dev) return GemmTrace{nullptr, 0};
+    return GemmTrace{g_trace_dev, ++g_trace_seq};
 }
 
 void hang_diag_describe(char* buf, size_t n) {
@@ -463,6 +489,13 @@ static int search_step(atspeed_session* s, ModelRT& m, int level, int width, boo
 extern "C" {
 
 const char* atspeed_last_error(void) { return atspeed::last_error(); }
+
+int atspeed_debug_gemm_trace(uint32_t* out, int32_t max_words) {
+    if (!atspeed::g_trace_host || !out) return 0;
+    const int n = max_words < TRACE_WORDS * TRACE_CTAS ? max_words : TRACE_WORDS * TRACE_CTAS;
+    for (int i = 0; i < n; ++i) out[i] = static_cast<volatile unsigned int*>(atspeed::g_trace_host)[i];
+    return n;
+}
 int atspeed_abi_version(void) { return ATSPEED_ABI_VERSION; }
 
 int atspeed_session_workspace_bytes(const atspeed_model_desc* target, const atspeed_model_desc* draft,

@@ -174,7 +174,21 @@ struct GemmParams {
     int tma_store;            // epilogue writes through shared memory + cp.async.bulk.tensor stores (tmO*) instead of STG
     int n_mma, N_mma;         // 2-CTA kernel: the token axis (padded to 64) is covered by n_mma MMAs of N_mma columns each
     SpinGuard guard;          // bound + diagnostic record of every mbarrier wait
+    GemmTrace trace;          // optional per-CTA progress words (ATSPEED_GEMM_TRACE=1)
+    int pdl_late;             // DIAGNOSTIC (ATSPEED_PDL_LATE=1): trigger the dependent launch after the main loop, not at entry
+    int relinq_late;          // DIAGNOSTIC (ATSPEED_RELINQ_LATE=1): keep the TMEM allocation permit until just before dealloc
 };
+__device__ __forceinline__ void trace_put(const GemmTrace& t, int word, unsigned v) {
+    if (t.buf != nullptr && blockIdx.x < TRACE_CTAS) {
+        volatile unsigned int* w = t.buf + blockIdx.x * TRACE_WORDS + word;
+        *w = v;
+    }
+}
+__device__ __forceinline__ unsigned sm_id() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
 
 // Work decomposition ("stream-K with consumer-side fix-up").  The (tile, k-block) units of the whole GEMM are
 // numbered tile-major and cut into gridDim.x equal contiguous ranges, one per persistent CTA, so every SM streams the
@@ -423,10 +437,16 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
     __shared__ __align__(8) uint64_t accum_full[2], accum_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        trace_put(p.trace, 0, p.trace.seq);
+        trace_put(p.trace, 1, (2u << 24) | (rank << 16) | sm_id());
+        trace_put(p.trace, 7, (gridDim.x << 16) | static_cast<unsigned>(p.T));
+        trace_put(p.trace, 2, 1);
+    }
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1;
     const int T64 = p.n_mma * p.N_mma;                       // tokens padded to a multiple of 64
@@ -458,14 +478,19 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
         tma_prefetch_desc(&tmW0); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmX);
     }
     if (warp == 1) {
+        if (lane == 0) trace_put(p.trace, 3, 1);
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(static_cast<uint32_t>(p.tmem_cols)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        if (lane == 0) trace_put(p.trace, 3, 2);
+        if (!p.relinq_late) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        if (lane == 0) trace_put(p.trace, 3, 3);
     }
+    if (threadIdx.x == 0) trace_put(p.trace, 2, 2);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                      // barriers of BOTH CTAs initialised, TMEM allocated
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    if (threadIdx.x == 0) trace_put(p.trace, 2, 4);
 
     WaitCtx wc;
     wc.g = p.guard; wc.kernel = HANG_K_GEMM_PAIR; wc.u_begin = u_begin; wc.u_end = u_end; wc.T = p.T;
@@ -493,17 +518,21 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             const int npre = n_units < p.stages ? n_units : p.stages;
             const int kb_first = kb;
             for (int i = 0; i < npre; ++i) { load_a(i); advance(); }
+            trace_put(p.trace, 4, 0x10000u);                              // waiting for the predecessor grid
             asm volatile("griddepcontrol.wait;" ::: "memory");
+            trace_put(p.trace, 4, 0x20000u);
             for (int i = 0, kbb = kb_first; i < npre; ++i) { load_b(i, kbb); if (++kbb == KB) kbb = 0; }
             int s = npre == p.stages ? 0 : npre;
             uint32_t ph = npre == p.stages ? 1 : 0;
             for (int u = u_begin + npre; u < u_end; ++u) {
+                trace_put(p.trace, 4, 0x30000u | static_cast<unsigned>(u - u_begin));
                 mbar_wait(&empty_bar[s], ph ^ 1, wc, HANG_B_EMPTY, s, u);
                 load_a(s);
                 load_b(s, kb);
                 advance();
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
+            trace_put(p.trace, 4, 0xFFFFFu);
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -522,6 +551,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t tacc = tmem_base + buf * p.buf_stride;
+                trace_put(p.trace, 5, 0x30000u | static_cast<unsigned>(u - u_begin));
                 mbar_wait(&full_bar[s], ph, wc, HANG_B_FULL, s, u);                              // both CTAs' tiles of this stage have landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
@@ -543,11 +573,14 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                     if (p.n_bufs == 2) buf ^= 1;
                 }
             }
+            trace_put(p.trace, 5, 0xFFFFFu);
         }
         __syncwarp();                                        // .aligned cluster barrier / dealloc below need the whole warp
     } else {
         // ===== epilogue (both CTAs): this CTA's 128 rows of the pair's tile =====
+        if (threadIdx.x == 64) trace_put(p.trace, 6, 0x10000u);
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (threadIdx.x == 64) trace_put(p.trace, 6, 0x20000u);
         const int q = warp & 3;
         float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
         int st_chunk = 0;
@@ -561,6 +594,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             tile_of(tile, wid, m0);
             const int slice = pair - (tile * KB) / p.U;
             const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
+            if (elected) trace_put(p.trace, 6, 0x30000u | static_cast<unsigned>(seg));
             mbar_wait(&accum_full[buf], use & 1, wc, HANG_B_ACCUM_FULL, buf, u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
@@ -596,12 +630,19 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             u = seg_end;
         }
         if (p.tma_store && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (elected) trace_put(p.trace, 6, 0xFFFFFu);
     }
+    if (p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) trace_put(p.trace, 2, 5);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                      // nobody frees TMEM / exits while the peer may still touch it
+    if (threadIdx.x == 0) trace_put(p.trace, 2, 6);
     if (warp == 1) {
+        if (p.relinq_late) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        if (lane == 0) trace_put(p.trace, 3, 7);
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(static_cast<uint32_t>(p.tmem_cols)));
+        if (lane == 0) trace_put(p.trace, 3, 8);
     }
 }
 
@@ -880,6 +921,9 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     p.b_box_bytes = (pl.T_pad > 256 ? pl.T_pad : xm.box0) * BLOCK_K * 2;
     p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
     p.guard = spin_guard();
+    p.trace = pl.two_cta ? gemm_trace() : GemmTrace{nullptr, 0};
+    { const char* e = getenv("ATSPEED_PDL_LATE"); p.pdl_late = e && atoi(e) == 1; }
+    { const char* e = getenv("ATSPEED_RELINQ_LATE"); p.relinq_late = e && atoi(e) == 1; }
     p.tma_store = om.ok;
     const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
                                        : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;

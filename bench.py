@@ -672,27 +672,32 @@ def hf_baseline(a, ds, fn, dev, users, weights=None, ours=None):
            "what": "transformers LlamaForCausalLM.generate(num_beams=K, prefix_allowed_tokens_fn) bf16, same GPU, same shape, "
                    "one user at a time as code/inference.py:177-178 runs it; users_per_s = users / sum of latencies"}
     if ours and same_weights:
-        tol = 6e-2                      # bf16 near-tie tolerance on cumulative log-probs (tests/_common.py BF16_SCORE_TOL)
-        ident = near = 0
-        worst = 0.0
+        # parity record at the benchmark shape.  HF's bf16 modules and this repo's kernels round at the same points but sum
+        # in different orders, and with random-init weights the beam margins are tiny, so rank-for-rank equality of ten
+        # beams is rare; what must hold is that both searches find (almost) the same items with (almost) the same scores.
+        tol = 6e-2                      # bf16 tolerance on cumulative log-probs (tests/_common.py BF16_SCORE_TOL)
+        ident = top1 = n = 0
+        overlap, dscore = [], []
         for u, (hf_t, hf_s) in lists.items():
             if u not in ours:
                 continue
             t, sc = ours[u]
             a_l, b_l = [tuple(r) for r in t[:, :4].tolist()], [tuple(r) for r in hf_t[:, :4].tolist()]
-            if a_l == b_l:
-                ident += 1
-                if hf_s is not None:
-                    worst = max(worst, float(np.max(np.abs(np.asarray(sc) - hf_s[: len(sc)]))))
-            elif hf_s is not None:
-                # explained by a near-tie: every item that is in one list only sits within tol of the other list's cut-off
-                sa, sb = dict(zip(a_l, sc)), dict(zip(b_l, hf_s))
-                ok = all(abs(sa[x] - min(hf_s)) < tol for x in a_l if x not in sb) and \
-                     all(abs(sb[x] - min(sc)) < tol for x in b_l if x not in sa)
-                near += int(ok)
-        out["parity_vs_ours"] = {"users": len([u for u in lists if u in ours]), "identical_ranked_lists": ident,
-                                 "explained_by_near_tie": near, "max_abs_score_diff_identical": worst, "tolerance": tol,
-                                 "note": "bf16 contract: different GEMM summation orders flip near-ties (DESIGN.md section 2)"}
+            n += 1
+            ident += int(a_l == b_l)
+            top1 += int(a_l[:1] == b_l[:1])
+            overlap.append(len(set(a_l) & set(b_l)) / max(1, len(b_l)))
+            if hf_s is not None:
+                sb = dict(zip(b_l, hf_s))
+                dscore += [abs(float(x) - float(sb[k])) for k, x in zip(a_l, sc) if k in sb]
+        out["parity_vs_ours"] = {"users": n, "identical_ranked_lists": ident, "same_top1": top1,
+                                 "mean_item_overlap": float(np.mean(overlap)) if overlap else None,
+                                 "min_item_overlap": float(np.min(overlap)) if overlap else None,
+                                 "max_abs_score_diff_common_items": float(np.max(dscore)) if dscore else None,
+                                 "mean_abs_score_diff_common_items": float(np.mean(dscore)) if dscore else None,
+                                 "tolerance": tol,
+                                 "note": "informative: the rigorous check at this shape is --check-users (oracle, same bf16 "
+                                         "contract) and tests/test_zz_gpu_shape7b.py"}
     return out
 
 

@@ -38,6 +38,12 @@ extern "C" {
 
 const char* atspeed_last_error(void);
 int atspeed_abi_version(void);
+/* Diagnostics (nothing like it in the reference).  With ATSPEED_GEMM_TRACE=1 in the environment every GEMM CTA records its
+ * progress in mapped host memory: 16 words per CTA {launch seq, kernel<<24|cluster rank<<16|SM id, CTA phase, TMEM phase,
+ * producer unit, MMA unit, epilogue segment, grid<<16|T, ...}; this copies up to max_words of it, returns the words copied
+ * (0 = tracing off).  Readable while a launch is stuck.  Every mbarrier wait of the library is bounded separately
+ * (ATSPEED_SPIN_LIMIT_MS, default 4000): an expired wait traps and atspeed_last_error() names kernel/CTA/role/barrier. */
+int atspeed_debug_gemm_trace(uint32_t* out, int32_t max_words);
 
 /* ------------------------------------------------------------------------------------------------
  * Model + session

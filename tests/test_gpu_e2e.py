@@ -136,14 +136,15 @@ def _gpu_target_levels(out, L):
     return levels
 
 
-def _split_level_margin(out, case, prompt, fn):
+def _split_level_margin(out, case, prompt, fn, model=None):
     """Locate the first level at which the GPU run's target beams differ (as a set) from the oracle's plain beam search
     (strict BSSD is lossless, so that IS the reference trajectory) and measure the margin there, in the oracle's scores,
     between the best beam the GPU dropped and the worst beam it kept instead."""
     from oracle import bssd_ref
     bssd_ref.LEVEL_LOG = []
     try:
-        bssd_ref.target_generate(oracle_model("ref_bf16", case["dataset"], "target"), prompt, case["K"], 4, fn)
+        bssd_ref.target_generate(model if model is not None else oracle_model("ref_bf16", case["dataset"], "target"), prompt,
+                                 case["K"], 4, fn)
         log = bssd_ref.LEVEL_LOG
     finally:
         bssd_ref.LEVEL_LOG = None
