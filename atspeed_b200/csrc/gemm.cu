@@ -175,8 +175,6 @@ struct GemmParams {
     int n_mma, N_mma;         // 2-CTA kernel: the token axis (padded to 64) is covered by n_mma MMAs of N_mma columns each
     SpinGuard guard;          // bound + diagnostic record of every mbarrier wait
     GemmTrace trace;          // optional per-CTA progress words (ATSPEED_GEMM_TRACE=1)
-    int pdl_late;             // DIAGNOSTIC (ATSPEED_PDL_LATE=1): trigger the dependent launch after the main loop, not at entry
-    int relinq_late;          // DIAGNOSTIC (ATSPEED_RELINQ_LATE=1): keep the TMEM allocation permit until just before dealloc
 };
 __device__ __forceinline__ void trace_put(const GemmTrace& t, int word, unsigned v) {
     if (t.buf != nullptr && blockIdx.x < TRACE_CTAS) {
@@ -437,7 +435,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
     __shared__ __align__(8) uint64_t accum_full[2], accum_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
-    if (!p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -477,12 +475,19 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmW0); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmX);
     }
+    // BOTH CTAs of the pair must be running before tcgen05.alloc.cta_group::2: the allocation is a handshake between the
+    // two CTAs through mbarriers in their reserved shared memory (the leader allocates in both SMs and posts the address to
+    // the peer).  Co-scheduling guarantees that the peer WILL be resident, not that it has started: a leader that runs ahead
+    // posts into a CTA that does not exist yet and both then wait forever inside tcgen05.alloc -- the round-1 device stall
+    // (no mbarrier of this kernel involved, GPU 98 % busy).  CUTLASS / DeepGEMM open their 2-SM kernels
+    // with this same cluster barrier.
+    cluster_sync_all();
     if (warp == 1) {
         if (lane == 0) trace_put(p.trace, 3, 1);
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(static_cast<uint32_t>(p.tmem_cols)));
         if (lane == 0) trace_put(p.trace, 3, 2);
-        if (!p.relinq_late) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
         if (lane == 0) trace_put(p.trace, 3, 3);
     }
     if (threadIdx.x == 0) trace_put(p.trace, 2, 2);
@@ -632,13 +637,11 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
         if (p.tma_store && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (elected) trace_put(p.trace, 6, 0xFFFFFu);
     }
-    if (p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) trace_put(p.trace, 2, 5);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                      // nobody frees TMEM / exits while the peer may still touch it
     if (threadIdx.x == 0) trace_put(p.trace, 2, 6);
     if (warp == 1) {
-        if (p.relinq_late) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
         if (lane == 0) trace_put(p.trace, 3, 7);
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(static_cast<uint32_t>(p.tmem_cols)));
@@ -683,13 +686,14 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, lon
     return ATS_OK;
 }
 
-// The CTA-pair kernel (cta_group::2) for T > 256 is OPT-IN (ATSPEED_GEMM_2CTA=1): under several concurrent streams it
-// stalled on the device in round 1, so every configuration -- 1 GPU and N GPUs alike -- runs the
-// single-CTA kernel for every T unless the caller asks for the pair kernel.  ATSPEED_GEMM_2CTA_MIN: smallest padded token
-// count that uses it (experiments).  The environment is read per call: tests toggle it inside one process.
+// Forwards of more than 256 tokens (cohort forwards) run the CTA-pair kernel (cta_group::2); ATSPEED_GEMM_2CTA=0 keeps the
+// single-CTA kernel for every T, ATSPEED_GEMM_2CTA_MIN sets the smallest padded token count that uses the pair kernel
+// (experiments).  The same rule holds at every GPU count.  (Round 1's device stall of this kernel was the missing cluster
+// barrier in front of tcgen05.alloc.cta_group::2 -- see the kernel's prologue and DESIGN.md section 6; tests/test_zz_gpu_soak.py
+// is its regression test.)  The environment is read per call: tests toggle it inside one process.
 bool gemm_use_2cta(int T) {
     const char* e = getenv("ATSPEED_GEMM_2CTA");
-    if (!(e && atoi(e) == 1)) return false;
+    if (e && atoi(e) == 0) return false;
     const char* m = getenv("ATSPEED_GEMM_2CTA_MIN");
     const int T_pad = (T + 15) & ~15;
     return T_pad > (m ? atoi(m) : 256);
@@ -922,8 +926,6 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
     p.guard = spin_guard();
     p.trace = pl.two_cta ? gemm_trace() : GemmTrace{nullptr, 0};
-    { const char* e = getenv("ATSPEED_PDL_LATE"); p.pdl_late = e && atoi(e) == 1; }
-    { const char* e = getenv("ATSPEED_RELINQ_LATE"); p.relinq_late = e && atoi(e) == 1; }
     p.tma_store = om.ok;
     const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
                                        : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;

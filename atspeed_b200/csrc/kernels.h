@@ -5,6 +5,7 @@
 namespace atspeed {
 
 // ---- gemm.cu ------------------------------------------------------------------------------------
+constexpr int MAX_USERS = 16;     // users whose trees may share one forward (cohort.cu)
 struct GemmWeights {
     int n;                 // 1..3 weight matrices sharing one input
     int K;                 // input features
@@ -12,6 +13,32 @@ struct GemmWeights {
     int colbase[3];        // first output column of each
     CUtensorMap tmap[3];   // [rows_i, K] bf16, K-major, box 64 x 128, SWIZZLE_128B
     CUtensorMap tmap256[3];   // same tensors, box 64 x 256: one TMA operation per 256-row tile (BM = 256)
+    CUtensorMap tmap64[3];    // same tensors, box 64 x 64: gate / up halves of an interleaved SiLU tile (fused epilogue)
+};
+// Fused epilogues (gemm.cu): instead of fp32 partial-sum slices for a row-wise consumer kernel, the GEMM itself finishes
+// the op that follows it in the LLaMA layer.  A tile whose k-range is cut across CTAs is completed INSIDE the kernel: the
+// CTA that holds the tile's first k-block owns it; the other CTAs store their raw fp32 partial and raise a flag; the owner
+// adds the partials in slice order (the order the consumer kernels used: same bits) and applies the epilogue.
+enum : int { EPI_SLICES = 0, EPI_QKV_ROPE = 1, EPI_SILU_MUL = 2 };
+struct FusedEpi {
+    int kind;
+    float* part;             // [workers x CTAs per worker x halves][T_pad][128] fp32 raw partial of a non-owner segment
+    unsigned int* flags;     // [workers x CTAs per worker]: epoch of the launch whose partial is complete
+    unsigned int epoch;      // unique per launch within the session (never 0)
+    // EPI_QKV_ROPE: q|k|v projections -> RoPE(q, k) at pos -> q to qbuf [T, H*D], k/v to the cache rows slot[t]
+    // (elementwise.cu qkv_rope_append restated per tile: one 128-row tile holds whole heads)
+    const int* pos;
+    const int* slot;
+    const int* tok_user;     // cohort forward: user of each token (index into kv_off); nullptr otherwise
+    const float* rope_cos;
+    const float* rope_sin;
+    int max_pos, head_dim, HD;
+    __nv_bfloat16 *qbuf, *kcache, *vcache;
+    long long kv_off[MAX_USERS];
+    // EPI_SILU_MUL: gate|up projections -> m = bf16(bf16(silu(g)) * u)  (elementwise.cu silu_mul restated per tile: a tile
+    // holds the gate rows AND the up rows of the same features)
+    __nv_bfloat16* m;
+    int mlp;
 };
 int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, long long rows, long long cols, int box_rows);
 // One launch's work decomposition (host-computed, see gemm.cu): persistent CTAs each own a contiguous range of
@@ -25,6 +52,7 @@ struct GemmPlan {
     int max_slices;         // most slices any tile of this launch has
     int stages, tmem_cols, acc_stride, n_bufs, buf_stride;
     int two_cta, n_mma, N_mma;   // CTA-pair kernel (T > 256): see gemm_wx_tcgen05_2cta
+    int epi_kind;                // EPI_*: EPI_SLICES plans feed a consumer kernel, the others finish tiles in the kernel
 };
 // What a consumer of the partial sums needs to know: how many slices hold column `col`.
 struct SplitMap {
@@ -40,6 +68,10 @@ struct SplitMap {
 struct XMap { CUtensorMap tm0, tm1; int T, K, box0; };   // activation operand [T, K] bf16 (two boxes: tokens < 256, >= 256)
 bool gemm_use_2cta(int T);
 int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, GemmPlan* plan);
+// plan of a fused-epilogue launch (kind = EPI_QKV_ROPE: w = {q, k, v}; EPI_SILU_MUL: w = {gate, up})
+int gemm_make_plan_fused(const GemmWeights& w, int T, int num_sms, int kind, GemmPlan* plan);
+size_t gemm_fused_part_elems(int T_max, int num_sms);     // floats of FusedEpi::part that cover every plan up to T_max
+int gemm_wx_fused(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, const FusedEpi& epi, cudaStream_t stream);
 int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms);
 SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& plan);
 int gemm_make_xmap(XMap* xm, const void* x, int T, int K);
@@ -51,7 +83,6 @@ bool pdl_enabled();   // ATSPEED_PDL=0 disables programmatic dependent launch (d
 // ---- elementwise.cu -----------------------------------------------------------------------------
 // Several users' trees in ONE forward ("cohort", cohort.cu): every user keeps its own KV cache, prompt length and
 // attention extent; tokens of user i occupy batch positions [tok0[i], tok0[i] + T[i]).  n == 0: single-user forward.
-constexpr int MAX_USERS = 16;
 struct CohortKV {
     int n;
     long long kv_off[MAX_USERS];   // element offset of the user's cache inside the model's KV allocation

@@ -26,7 +26,8 @@ must be identical), `kernel_groups` (share of a user's GPU time and algorithmic 
 (transformers generate(num_beams=K) on the same GPU, N = 1: the north star's ">= 2x HF beam search" comparison, reference
 code/inference.py:177-181 `speedupTF`).  stderr carries phase breadcrumbs; a watchdog ends a stalled run with every thread's
 stack, the partial result (`"incomplete"`) and a NON-ZERO exit code, see DESIGN.md section 6.  Every N runs the same kernel
-configuration (the CTA-pair GEMM is opt-in through ATSPEED_GEMM_2CTA=1 at any N; `config.gemm_pair_kernel` says which).
+configuration (the CTA-pair GEMM serves forwards of > 256 tokens at any N unless ATSPEED_GEMM_2CTA=0; `config.gemm_pair_kernel`
+says which).
 """
 import argparse
 import json
@@ -74,8 +75,10 @@ def parse():
     ap.add_argument("--gamma", type=int, default=3)
     ap.add_argument("--target", default="7b")
     ap.add_argument("--draft", default="68m",
-                    help="draft shape; 'corr2' = a CORRELATED draft: the target's first 2 layers, embedding and lm_head plus 3 %% "
-                         "noise (random independent weights accept ~0 steps; this exercises speculation at the target's shape)")
+                    help="draft shape; 'corr<n>' (e.g. corr24) = a CORRELATED draft: the target's first n layers, embedding and "
+                         "lm_head plus 3 %% noise.  Independent random weights accept only the structurally forced last step; "
+                         "this exercises real accepted steps at the target's shape (a random-init net needs most of its layers "
+                         "to agree with itself: corr2 accepts nothing extra, measured)")
     ap.add_argument("--check-users", type=int, default=0,
                     help="parity record at the benchmark shape: this many users also go through oracle/bssd_ref.py on the host "
                          "with the GPU's own weights (bf16 contract); ranked lists + accepted lengths compared (slow: ~10 s/user)")
@@ -94,9 +97,15 @@ def parse():
     return ap.parse_args()
 
 
+def corr_layers(name):
+    """'corr<n>' -> n (a correlated draft made of the target's first n layers), anything else -> 0."""
+    return int(name[4:]) if name.startswith("corr") and name[4:].isdigit() else 0
+
+
 def workload_name(a):
     mode = "AtSpeed-R relaxed acceptance (do_sample, top_k=50, T=1)" if a.do_sample else "AtSpeed-S strict top-K verify"
-    draft = "correlated 2-layer draft cut from the target (+3% noise)" if a.draft == "corr2" else f"LLaMA-{a.draft}-shape draft"
+    draft = (f"correlated {corr_layers(a.draft)}-layer draft cut from the target (+3% noise)" if corr_layers(a.draft)
+             else f"LLaMA-{a.draft}-shape draft")
     return (f"LLaMA-{a.target}-shape target + {draft}, {mode}, "
             f"{a.dataset} test users, {a.constraint} constraint, K={a.K} N={a.N} gamma={a.gamma} max_new_tokens=4, "
             f"{a.users_per_step} users/step/GPU, " +
@@ -252,7 +261,7 @@ def cpu_models(a, vocab):
     from oracle import llama_ref as LR
     out = []
     for name, seed in ((a.target, 1), (a.draft, 2)):
-        s = SHAPES[name] if name != "corr2" else dict(SHAPES[a.target], n_layers=2)
+        s = SHAPES[name] if not corr_layers(name) else dict(SHAPES[a.target], n_layers=corr_layers(name))
         sh = LR.LlamaShape(vocab, s["hidden"], 1, s["n_heads"], s["mlp"])
         W = LR.make_weights(sh, seed, std=0.02)
         W["layers"] = W["layers"] * s["n_layers"]
@@ -333,11 +342,11 @@ def atspeed_arm(a, rank, world, local_rank):
     fn = make_fn(ds, a.constraint)
     specs = []
     for name in (a.target, a.draft):
-        s = SHAPES[name] if name != "corr2" else dict(SHAPES[a.target], n_layers=2)
+        s = SHAPES[name] if not corr_layers(name) else dict(SHAPES[a.target], n_layers=corr_layers(name))
         specs.append(ModelSpec(V, s["hidden"], s["n_layers"], s["n_heads"], s["hidden"] // s["n_heads"], s["mlp"]))
     tdm = DeviceModel(specs[0], gpu_weights(specs[0], 1, dev), dev)
-    if a.draft == "corr2":
-        ddm = DeviceModel(specs[1], correlated_draft_weights(tdm, 2, 0.03, dev), dev)
+    if corr_layers(a.draft):
+        ddm = DeviceModel(specs[1], correlated_draft_weights(tdm, corr_layers(a.draft), 0.03, dev), dev)
     else:
         ddm = DeviceModel(specs[1], gpu_weights(specs[1], 2, dev), dev)
     csr = compile_constraint(fn, ds.prompt_ids(0), 4, other_prompt=ds.prompt_ids(1))
@@ -479,7 +488,7 @@ def atspeed_arm(a, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (13.5 GB of weights streamed per forward)",
                        "parallelism": f"user-sharded x{world}, one all-gather of ranked lists per step",
-                       "gemm_pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "0") == "1"},
+                       "gemm_pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "1") != "0"},
             "clocks": clocks.summary(), "gpu_launches": int(launches),
             "accepted_tokens_per_verify": accept * a.K / max(1, runs)}
     STATE["partial"] = dict(base)          # what the watchdog prints if a later phase stalls
@@ -601,7 +610,7 @@ def atspeed_arm(a, rank, world, local_rank):
             def run_hf():
                 try:
                     W = {"embed": tdm.embed, "norm": tdm.norm, "lm_head": tdm.lm_head, "layers": tdm.layers}
-                    box["r"] = hf_baseline(a, ds, fn, dev, hf_users[: a.hf_baseline_users], W, ours)
+                    box["r"] = hf_baseline(a, ds, fn, dev, hf_users[: a.hf_baseline_users], W, ours, sess)
                 except Exception as e:   # informative only: never fail the bench line on the comparison arm
                     box["r"] = {"error": repr(e)[:300]}
 
@@ -623,7 +632,7 @@ def atspeed_arm(a, rank, world, local_rank):
     log("done")
 
 
-def hf_baseline(a, ds, fn, dev, users, weights=None, ours=None):
+def hf_baseline(a, ds, fn, dev, users, weights=None, ours=None, sess=None):
     """HF `generate(num_beams=K, prefix_allowed_tokens_fn=...)` on the same GPU, shape and -- when `weights` is given -- the
     same random-init weights (reference code/inference.py:177-178, the `TF_target` column): the north star's >= 2x
     comparison, one user at a time as the reference runs it.  3 untimed warm-up calls, then every user of `users`.
@@ -648,6 +657,27 @@ def hf_baseline(a, ds, fn, dev, users, weights=None, ours=None):
                 sd[f"model.layers.{i}.{n}.weight"] = ly[k]
         missing, unexpected = m.load_state_dict(sd, strict=False)
         same_weights = not [k for k in missing if "rotary" not in k and "inv_freq" not in k]
+    logit_cmp = None
+    if sess is not None and same_weights:
+        # the forward itself at the benchmark shape: last-position logits of the prompt, HF bf16 module vs this repo's kernels
+        # (same weights); the search above compounds these differences over 4 levels of near-tied beams
+        d_max = d_mean = 0.0
+        std = ov = 0.0
+        lo, hi = ds.level_ranges()[0]
+        n_cmp = min(3, len(users))
+        for u in users[:n_cmp]:
+            prompt = ds.prompt_ids(u)
+            P = len(prompt)
+            i32 = lambda x: torch.tensor(list(x), dtype=torch.int32, device=dev)
+            mine = sess.forward_raw(0, i32(prompt), i32(range(P)), i32(range(P)), i32(range(1, P + 1)),
+                                    torch.zeros(P, 16, dtype=torch.int32, device=dev), P, P, i32([P - 1]))[0]
+            with torch.no_grad():
+                theirs = m(input_ids=torch.tensor([prompt], device=dev)).logits[0, -1].float().cpu().numpy()
+            d = np.abs(mine - theirs)
+            d_max, d_mean, std = max(d_max, float(d.max())), d_mean + float(d.mean()) / n_cmp, std + float(theirs.std()) / n_cmp
+            ov += len(set(np.argsort(-mine[lo:hi + 1])[:10]) & set(np.argsort(-theirs[lo:hi + 1])[:10])) / 10.0 / n_cmp
+        logit_cmp = {"prompts": n_cmp, "max_abs_diff": d_max, "mean_abs_diff": d_mean, "logit_std": std,
+                     "top10_overlap_first_code_token": ov}
     lat, lists = [], {}
     seq = [users[0]] * 3 + list(users)                              # three untimed warm-up calls (lazy init, autotuning)
     for i, u in enumerate(seq):
@@ -668,7 +698,7 @@ def hf_baseline(a, ds, fn, dev, users, weights=None, ours=None):
     ms = np.asarray(lat) * 1e3
     out = {"users_per_s": len(lat) / float(sum(lat)), "latency_ms_p50": float(np.percentile(ms, 50)),
            "latency_ms_mean": float(ms.mean()), "latency_ms_min": float(ms.min()), "latency_ms_max": float(ms.max()),
-           "users": len(lat), "same_weights_as_target": bool(same_weights),
+           "users": len(lat), "same_weights_as_target": bool(same_weights), "prompt_logits_vs_ours": logit_cmp,
            "what": "transformers LlamaForCausalLM.generate(num_beams=K, prefix_allowed_tokens_fn) bf16, same GPU, same shape, "
                    "one user at a time as code/inference.py:177-178 runs it; users_per_s = users / sum of latencies"}
     if ours and same_weights:
@@ -739,7 +769,7 @@ def arm_watchdog(total_s, stall_s):
 def multi_gpu_env(world):
     """Communicator settings for N > 1 (only defaults: anything the caller exports wins): the one collective moves ~12 KB
     per step, so NVSwitch multicast (NVLS) buys nothing -- leave its set-up out of the communicator's initialisation.  The
-    kernels are the same at every N (the CTA-pair GEMM is opt-in everywhere, config.gemm_pair_kernel)."""
+    kernels are the same at every N (config.gemm_pair_kernel)."""
     if world > 1:
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         os.environ.setdefault("NCCL_MNNVL_ENABLE", "0")      # one box: no multi-node NVLink / IMEX probing either

@@ -76,7 +76,7 @@ def test_bench_control_flow_single_process():
         assert r.returncode == 0, r.stderr[-2000:]
         line = json.loads(r.stdout.strip().splitlines()[-1])
         assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
-        assert line["n_gpus"] == 1 and line["config"]["gemm_pair_kernel"] is False and "incomplete" not in line
+        assert line["n_gpus"] == 1 and line["config"]["gemm_pair_kernel"] is True and "incomplete" not in line
         assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
         assert "device pass: timed region" in r.stderr and "done" in r.stderr and "[stub] atexit hook ran" in r.stderr
@@ -94,7 +94,7 @@ def test_bench_control_flow_two_ranks_gloo():
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     line = json.loads(lines[0])
-    assert line["n_gpus"] == 2 and line["config"]["gemm_pair_kernel"] is False and line["cpu_baseline"] is None
+    assert line["n_gpus"] == 2 and line["config"]["gemm_pair_kernel"] is True and line["cpu_baseline"] is None
     assert line["gpu_launches"] > 0 and line["scaling"] == "weak"
     for rank in (0, 1):
         assert f"[bench r{rank} " in r.stderr and "all-gather done" in r.stderr

@@ -17,13 +17,13 @@ SHAPES = [(4096, (4096, 4096, 4096)), (4096, (4096,)), (4096, (11008, 11008)), (
 @pytest.mark.parametrize("cut", [1, 0])
 @pytest.mark.parametrize("pair", [0, 1])
 def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut, pair, monkeypatch):
-    """pair = 1: ATSPEED_GEMM_2CTA=1 opts into the CTA-pair kernel for T > 256 (off by default at every N)."""
+    """pair = 1: the default -- the CTA-pair kernel serves T > 256; pair = 0: ATSPEED_GEMM_2CTA=0 keeps the single-CTA kernel."""
     from atspeed_b200 import _lib
     lib = _lib.load()
     if pair:
-        monkeypatch.setenv("ATSPEED_GEMM_2CTA", "1")
-    else:
         monkeypatch.delenv("ATSPEED_GEMM_2CTA", raising=False)
+    else:
+        monkeypatch.setenv("ATSPEED_GEMM_2CTA", "0")
     r = list(rows) + [0] * (3 - len(rows))
     info = (C.c_int32 * 16)()
     cols = sum(rows)
@@ -37,7 +37,7 @@ def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut, pair, monke
         assert BM in (128, 256) and KB == -(-K // 64) and T_pad == -(-T // 16) * 16
         assert tiles == sum(-(-x // BM) for x in rows) == sum(tl)
         units = tiles * KB
-        assert two_cta == int(pair and T_pad > 256), "the CTA-pair kernel is opt-in and serves only forwards of > 256 tokens"
+        assert two_cta == int(pair and T_pad > 256), "the CTA-pair kernel serves exactly the forwards of more than 256 tokens"
         n_workers = grid // 2 if two_cta else grid          # CTAs, or CTA pairs, that own a unit range
         assert (n_workers - 1) * U < units <= n_workers * U, "every worker owns at least one unit and the ranges cover all units"
         assert 2 <= stages <= 12 and tmem <= 512 and tmem & (tmem - 1) == 0
@@ -71,14 +71,14 @@ def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut, pair, monke
 @pytest.mark.parametrize("pair", [0, 1])
 def test_every_token_count_has_a_sane_plan(pair, monkeypatch):
     """All T in 1..512 for the 7B and 68M projection shapes (cohort forwards pack arbitrary token counts): unit ranges
-    tile the work, rings fit in shared memory, accumulators fit in TMEM -- for the default single-CTA kernel and for the
-    opt-in CTA-pair kernel."""
+    tile the work, rings fit in shared memory, accumulators fit in TMEM -- with the CTA-pair kernel for T > 256 (default) and
+    with the single-CTA kernel everywhere (ATSPEED_GEMM_2CTA=0)."""
     from atspeed_b200 import _lib
     lib = _lib.load()
     if pair:
-        monkeypatch.setenv("ATSPEED_GEMM_2CTA", "1")
-    else:
         monkeypatch.delenv("ATSPEED_GEMM_2CTA", raising=False)
+    else:
+        monkeypatch.setenv("ATSPEED_GEMM_2CTA", "0")
     shapes = {"qkv": (4096, (4096, 4096, 4096)), "o": (4096, (4096,)), "gu": (4096, (11008, 11008)), "down": (11008, (4096,)),
               "lm": (4096, (32859,)), "dqkv": (768, (768, 768, 768)), "do": (768, (768,)), "dgu": (768, (3072, 3072)),
               "ddown": (3072, (768,)), "dlm": (768, (33014,))}

