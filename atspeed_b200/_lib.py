@@ -31,6 +31,11 @@ class Config(C.Structure):
                 ("seed", C.c_uint64), ("max_users", C.c_int32), ("cohort_tokens", C.c_int32)]
 
 
+class PromptTemplate(C.Structure):
+    _fields_ = [("bos", C.c_int32), ("n_prefix", C.c_int32), ("n_suffix", C.c_int32), ("n_resp", C.c_int32),
+                ("n_sep_even", C.c_int32), ("n_sep_odd", C.c_int32), ("ids", C.c_int32 * 120)]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_run", C.c_int32), ("total_accept_steps", C.c_int32), ("accept_steps", C.c_int32 * 8),
                 ("target_forwards", C.c_int32), ("draft_forwards", C.c_int32), ("kernel_launches", C.c_int32)]
@@ -88,6 +93,8 @@ SYMBOLS = {
     "atspeed_gemm_scratch_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "atspeed_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "atspeed_build_prompts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.POINTER(PromptTemplate), C.c_void_p, C.c_void_p]),
     "atspeed_tree_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libatspeed_b200.so")
-SOURCES = ["engine.cu", "gemm.cu", "elementwise.cu", "attention.cu", "topk.cu", "kvgather.cu", "beam.cu", "forward_f32.cu", "cohort.cu"]
+SOURCES = ["engine.cu", "gemm.cu", "elementwise.cu", "attention.cu", "topk.cu", "kvgather.cu", "beam.cu", "forward_f32.cu", "cohort.cu", "prompt.cu"]
 HEADERS = ["common.cuh", "kernels.h", "beam.cuh", "noise.cuh", "session.h", os.path.join("..", "..", "include", "atspeed.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

@@ -6,21 +6,23 @@
 // (b) a 512-bit mask over the accepted/tree slots that follow the prompt -- a few words per token,
 // produced on the device by the beam kernels (beam.cu), never a dense mask.
 //
-// One CTA = 64 queries of one head (4 warps x 16 rows); the key tiles some query of the CTA can see are
-// streamed 64 keys at a time through a double-buffered cp.async ring, fragments come from ldmatrix
-// (transposing for V), flash-style online softmax in fp32.  QK^T and PV run on the warp-level
-// tensor-core path (mma.sync m16n8k16 bf16): at T <= 512 tokens x <= ~700 keys the whole problem is
-// < 2 GFLOP per layer, far below what would amortise a TMEM round trip; the kernel is latency-bound.
-// P is split into hi+lo bf16 parts so the PV product is accurate to ~2^-16, which keeps this kernel
-// within fp32-softmax tolerance of oracle/llama_ref.py.
+// One CTA = 64 queries of one head and one user (4 warps x 16 rows).  The prompt keys -- seen by every query of the block --
+// are streamed 64 at a time through a double-buffered cp.async ring, fragments come from ldmatrix (transposing for V),
+// flash-style online softmax in fp32, QK^T and PV on the warp-level tensor-core path (mma.sync m16n8k16 bf16; P is split
+// into hi+lo bf16 parts so the PV product is accurate to ~2^-16, the fp32-softmax contract of oracle/llama_ref.py).  The
+// accepted / tree slots are NOT run through dense tiles: a beam sees <= ~8 of them, so each query folds its visible slots
+// in one by one (sparse phase, see the kernel).  Round 1 ran 64-key tiles over the tree region as well: 31 us per layer at
+// T = 300..512, latency-bound on > 95 % masked MMAs (profiles/r02_att_bench.txt).
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "kernels.h"
 
 namespace atspeed {
 
-static constexpr int ATT_BQ = 64;   // queries per CTA (default); ATSPEED_ATT_BQ=32 selects the experimental 2-warp CTAs
+static constexpr int ATT_BQ = 64;   // queries per CTA
 static constexpr int ATT_BK = 64;   // keys per tile
 static constexpr int ATT_THREADS = 128;
 
@@ -34,26 +36,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// 64-bit visibility window for keys [key0, key0+64) of one query row
-__device__ __forceinline__ uint64_t vis_window(const uint32_t* vrow, int key0, int vis_base) {
-    uint64_t out = 0;
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        const int b = key0 + 32 * w - vis_base;   // bit index of this word's first key
-        uint32_t word = 0;
-        if (b >= 0) {
-            const int i = b >> 5, sh = b & 31;
-            const uint32_t lo = i < VIS_WORDS ? vrow[i] : 0u;
-            const uint32_t hi = (i + 1) < VIS_WORDS ? vrow[i + 1] : 0u;
-            word = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
-        } else if (b > -32) {
-            word = vrow[0] << (-b);
-        }
-        out |= static_cast<uint64_t>(word) << (32 * w);
-    }
-    return out;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -71,28 +53,31 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
 }
 
-// BQ = queries per CTA = 16 per warp.  BQ = 64 is the measured default; BQ = 32 (EXPERIMENTAL, ATSPEED_ATT_BQ=32, written
-// without a GPU to run it on) doubles the number of CTAs: at T ~ 300 the BQ = 64 grid is ~1 four-warp CTA per SM and the
-// kernel is latency-bound (6.8 % of peak warps active, profiles/r01_ncu_full_v3.txt); two smaller CTAs per SM interleave.
-// PLO = true (default, the tested configuration): P = hi + lo bf16 parts, the PV product is accurate to ~2^-16 as the oracle's
-// contract asks.  PLO = false (EXPERIMENTAL, ATSPEED_ATT_PLO=0, never executed): P is rounded to bf16 once -- what an HF bf16
-// module does (softmax in fp32, `.to(bf16)`, then P @ V) -- and a third of the kernel's MMAs disappear.
-template <int D, int BQ, bool PLO>
-__global__ void __launch_bounds__(BQ * 2)
+// Two phases per CTA (64 queries of one head, one user):
+//   dense  : keys [0, max prefix_len) -- the prompt, which every query of the block sees (causally for prompt tokens) --
+//            in 64-key tiles on the warp-level tensor-core path, flash-style online softmax;
+//   sparse : the accepted / tree slots behind the prompt.  A beam sees only its own ancestor chain there (<= ~8 of the
+//            ~170 slots), so a dense pass over those tiles would be > 95 % masked work: instead every query walks the set
+//            bits of its 512-bit visibility mask and folds each visible key into its running (max, sum, output) state with
+//            plain fp32 dot products -- two threads per query, each half of the head dimension.
+// The dense phase hands its per-row softmax state to the sparse phase through shared memory (the K/V ring is free by then).
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS)
 tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                       const __nv_bfloat16* __restrict__ vcache, const int* __restrict__ prefix_len,
                       const uint32_t* __restrict__ vis, int vis_base, int T, int S, int n_heads, float scale,
                       __nv_bfloat16* __restrict__ out, CohortKV ckv) {
+    constexpr int BQ = ATT_BQ;
     constexpr int LDS = D + 8;                     // padded row (bf16 elements): conflict-free ldmatrix, rows 16-byte aligned
+    constexpr int LDO = D + 4;                     // padded fp32 row of the state hand-off
+    constexpr int DH = D / 2;                      // dimensions per thread in the sparse phase
     extern __shared__ __align__(16) uint8_t att_smem[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
-    __nv_bfloat16* sKV = sQ + BQ * LDS;        // [2 buffers][K | V][ATT_BK][LDS]
+    __nv_bfloat16* sKV = sQ + BQ * LDS;        // [2 buffers][K | V][ATT_BK][LDS]; afterwards: fp32 [BQ][LDO] output state
     __shared__ uint32_t sVis[BQ * VIS_WORDS];
     __shared__ int sPl[BQ];
     __shared__ int sMaxPl;
-    __shared__ uint32_t sAny[VIS_WORDS];
-    __shared__ int sTiles[64];                     // key tiles some query of this CTA can see
-    __shared__ int sNTiles;
+    __shared__ float sM[BQ], sL[BQ];
 
     pdl_launch_dependents();
     pdl_wait();
@@ -119,48 +104,30 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
 
     if (threadIdx.x == 0) sMaxPl = 0;
-    if (threadIdx.x < VIS_WORDS) sAny[threadIdx.x] = 0;
     __syncthreads();
     // stage the Q tile with cp.async (group 0), prefix lengths and visibility words directly
-    for (int i = threadIdx.x; i < BQ * (D / 8); i += (BQ * 2)) {
+    for (int i = threadIdx.x; i < BQ * (D / 8); i += ATT_THREADS) {
         const int r = i / (D / 8), c = (i % (D / 8)) * 8;
         const bool ok = q0 + r < T;
         cp_async16(&sQ[r * LDS + c], q + static_cast<long long>(ok ? q0 + r : 0) * HD + head * D + c, ok);
     }
     cp_async_commit();
-    for (int i = threadIdx.x; i < BQ; i += (BQ * 2)) {
-        const int pl = (q0 + i < T) ? prefix_len[q0 + i] : 0;
+    for (int i = threadIdx.x; i < BQ; i += ATT_THREADS) {
+        const int pl = (q0 + i < T) ? min(prefix_len[q0 + i], S) : 0;
         sPl[i] = pl;
         atomicMax(&sMaxPl, pl);
     }
-    for (int i = threadIdx.x; i < BQ * VIS_WORDS; i += (BQ * 2)) {
+    for (int i = threadIdx.x; i < BQ * VIS_WORDS; i += ATT_THREADS) {
         const int r = i / VIS_WORDS, w = i % VIS_WORDS;
-        const uint32_t v = (q0 + r < T) ? vis[static_cast<long long>(q0 + r) * VIS_WORDS + w] : 0u;
-        sVis[i] = v;
-        if (v) atomicOr(&sAny[w], v);
+        sVis[i] = (q0 + r < T) ? vis[static_cast<long long>(q0 + r) * VIS_WORDS + w] : 0u;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // tiles no query of this CTA can see are skipped (block-uniform list)
-        int n = 0;
-        const int max_pl = sMaxPl;
-        for (int key0 = 0; key0 < S && n < 64; key0 += ATT_BK) {
-            bool need = key0 < max_pl;
-            if (!need && key0 + ATT_BK > vis_base) {
-                const int b0 = key0 - vis_base, b1 = b0 + ATT_BK - 1;
-                for (int w = (b0 < 0 ? 0 : b0 >> 5); w <= (b1 >> 5) && w < VIS_WORDS; ++w) need |= sAny[w] != 0;
-            }
-            if (need) sTiles[n++] = key0;
-        }
-        sNTiles = n;
-    }
-    __syncthreads();
-    const int n_tiles = sNTiles;
+    const int n_tiles = (sMaxPl + ATT_BK - 1) / ATT_BK;      // dense phase: the keys some query sees through its prefix
 
     auto load_tile = [&](int buf, int key0) {
         __nv_bfloat16* sK = sKV + static_cast<size_t>(buf) * 2 * ATT_BK * LDS;
         __nv_bfloat16* sV = sK + ATT_BK * LDS;
-        for (int i = threadIdx.x; i < ATT_BK * (D / 8); i += (BQ * 2)) {
+        for (int i = threadIdx.x; i < ATT_BK * (D / 8); i += ATT_THREADS) {
             const int r = i / (D / 8), c = (i % (D / 8)) * 8;
             const bool ok = key0 + r < S;
             const long long off = static_cast<long long>(ok ? key0 + r : 0) * HD + head * D + c;
@@ -169,14 +136,14 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
         }
     };
 
-    const int r0 = warp * 16 + g, r1 = r0 + 8;         // the two query rows this thread owns
+    const int r0 = warp * 16 + g, r1 = r0 + 8;         // the two query rows this thread owns in the dense phase
     const int pl0 = sPl[r0], pl1 = sPl[r1];
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float o[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 
-    if (n_tiles > 0) load_tile(0, sTiles[0]);
+    if (n_tiles > 0) load_tile(0, 0);
     cp_async_commit();
     // ldmatrix lane addressing (see the fragment layouts of mma.m16n8k16):
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;        // A operand (Q), 16x16 tiles
@@ -184,9 +151,9 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_col = (lane >> 4) * 8;        // B operand (V, transposed)
 
     for (int it = 0; it < n_tiles; ++it) {
-        const int key0 = sTiles[it];
+        const int key0 = it * ATT_BK;
         const int buf = it & 1;
-        if (it + 1 < n_tiles) load_tile(buf ^ 1, sTiles[it + 1]);     // overlaps this tile's math
+        if (it + 1 < n_tiles) load_tile(buf ^ 1, key0 + ATT_BK);      // overlaps this tile's math
         cp_async_commit();
         cp_async_wait<1>();                                            // this tile (and Q) have landed
         __syncthreads();
@@ -209,19 +176,15 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
                 mma_bf16_16816(s[nb + 1], a[0], a[1], a[2], a[3], b[2], b[3]);
             }
         }
-        // ---- mask + online softmax ----
-        const uint64_t win0 = vis_window(&sVis[r0 * VIS_WORDS], key0, vis_base);
-        const uint64_t win1 = vis_window(&sVis[r1 * VIS_WORDS], key0, vis_base);
+        // ---- causal-prefix mask + online softmax ----
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int nb = 0; nb < ATT_BK / 8; ++nb) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int c = nb * 8 + 2 * t4 + e, key = key0 + c;
-                const bool v0 = key < S && (key < pl0 || ((win0 >> c) & 1ull));
-                const bool v1 = key < S && (key < pl1 || ((win1 >> c) & 1ull));
-                s[nb][e] = v0 ? s[nb][e] * scale : -INFINITY;
-                s[nb][2 + e] = v1 ? s[nb][2 + e] * scale : -INFINITY;
+                const int key = key0 + nb * 8 + 2 * t4 + e;
+                s[nb][e] = key < pl0 ? s[nb][e] * scale : -INFINITY;
+                s[nb][2 + e] = key < pl1 ? s[nb][2 + e] * scale : -INFINITY;
                 mx0 = fmaxf(mx0, s[nb][e]);
                 mx1 = fmaxf(mx1, s[nb][2 + e]);
             }
@@ -254,7 +217,7 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 #pragma unroll
         for (int i = 0; i < D / 8; ++i) { o[i][0] *= corr0; o[i][1] *= corr0; o[i][2] *= corr1; o[i][3] *= corr1; }
 
-        // ---- O += P V, P = hi + lo (two bf16 parts) ----
+        // ---- O += P V, P = hi + lo (two bf16 parts: the product is accurate to ~2^-16, the oracle's fp32-softmax contract) ----
 #pragma unroll
         for (int kk = 0; kk < ATT_BK / 16; ++kk) {
             // S accumulator layout of n-blocks 2kk, 2kk+1 == A fragment layout of a 16x16 tile
@@ -273,73 +236,127 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
                 uint32_t b[4];
                 ldmatrix_x4_trans(b, &sV[(kk * 16 + v_row) * LDS + nb * 8 + v_col]);
                 mma_bf16_16816(o[nb], ah0, ah1, ah2, ah3, b[0], b[1]);
-                if (PLO) mma_bf16_16816(o[nb], al0, al1, al2, al3, b[0], b[1]);
+                mma_bf16_16816(o[nb], al0, al1, al2, al3, b[0], b[1]);
                 mma_bf16_16816(o[nb + 1], ah0, ah1, ah2, ah3, b[2], b[3]);
-                if (PLO) mma_bf16_16816(o[nb + 1], al0, al1, al2, al3, b[2], b[3]);
+                mma_bf16_16816(o[nb + 1], al0, al1, al2, al3, b[2], b[3]);
             }
         }
         __syncthreads();   // this buffer is refilled by the next iteration's prefetch
     }
     cp_async_wait<0>();
-    // ---- normalise and store (bf16) ----
-    const float inv0 = l0 > 0.f ? 1.0f / l0 : 0.f, inv1 = l1 > 0.f ? 1.0f / l1 : 0.f;
-    const int tq0 = q0 + r0, tq1 = q0 + r1;
+    __syncthreads();       // Q has landed for everybody (n_tiles == 0) and the K/V ring is free: it now carries the row states
+    float* sO = reinterpret_cast<float*>(sKV);
 #pragma unroll
     for (int nb = 0; nb < D / 8; ++nb) {
-        const int c = head * D + nb * 8 + 2 * t4;
-        if (tq0 < T)
-            *reinterpret_cast<uint32_t*>(out + static_cast<long long>(tq0) * HD + c) =
-                pack_bf16(o[nb][0] * inv0, o[nb][1] * inv0);
-        if (tq1 < T)
-            *reinterpret_cast<uint32_t*>(out + static_cast<long long>(tq1) * HD + c) =
-                pack_bf16(o[nb][2] * inv1, o[nb][3] * inv1);
+        const int c = nb * 8 + 2 * t4;
+        sO[r0 * LDO + c] = o[nb][0]; sO[r0 * LDO + c + 1] = o[nb][1];
+        sO[r1 * LDO + c] = o[nb][2]; sO[r1 * LDO + c + 1] = o[nb][3];
+    }
+    if (t4 == 0) { sM[r0] = m0; sL[r0] = l0; sM[r1] = m1; sL[r1] = l1; }
+    __syncthreads();
+
+    // ---- sparse phase: two threads per query row, each DH dimensions ----
+    const int row = threadIdx.x >> 1, part = threadIdx.x & 1;
+    const int tq = q0 + row;
+    if (tq >= T) return;
+    const unsigned pair_mask = 3u << (lane & ~1);
+    const int pl = sPl[row];
+    float m = sM[row], l = sL[row];
+    float acc[DH], qf[DH];
+#pragma unroll
+    for (int i = 0; i < DH; ++i) {
+        acc[i] = sO[row * LDO + part * DH + i];
+        qf[i] = __bfloat162float(sQ[row * LDS + part * DH + i]);
+    }
+    const long long col0 = static_cast<long long>(head) * D + part * DH;
+    for (int w = 0; w < VIS_WORDS; ++w) {
+        uint32_t bits = sVis[row * VIS_WORDS + w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int key = vis_base + w * 32 + b;
+            if (key >= S || key < pl) continue;               // out of this forward's extent / already seen through the prefix
+            const uint4* kp = reinterpret_cast<const uint4*>(kcache + static_cast<long long>(key) * HD + col0);
+            const uint4* vp = reinterpret_cast<const uint4*>(vcache + static_cast<long long>(key) * HD + col0);
+            uint4 kr[DH / 8], vr[DH / 8];
+#pragma unroll
+            for (int i = 0; i < DH / 8; ++i) kr[i] = __ldg(kp + i);
+#pragma unroll
+            for (int i = 0; i < DH / 8; ++i) vr[i] = __ldg(vp + i);
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < DH / 8; ++i) {
+                const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 kf = __bfloat1622float2(k2[j]);
+                    dot += qf[i * 8 + 2 * j] * kf.x + qf[i * 8 + 2 * j + 1] * kf.y;
+                }
+            }
+            dot += __shfl_xor_sync(pair_mask, dot, 1);
+            const float sc = dot * scale;
+            const float mn = fmaxf(m, sc);
+            const float corr = m == -INFINITY ? 0.f : expf(m - mn);
+            const float pw = expf(sc - mn);
+            l = l * corr + pw;
+            m = mn;
+#pragma unroll
+            for (int i = 0; i < DH / 8; ++i) {
+                const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 vf = __bfloat1622float2(v2[j]);
+                    acc[i * 8 + 2 * j] = acc[i * 8 + 2 * j] * corr + pw * vf.x;
+                    acc[i * 8 + 2 * j + 1] = acc[i * 8 + 2 * j + 1] * corr + pw * vf.y;
+                }
+            }
+        }
+    }
+    // ---- normalise and store (bf16) ----
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    __nv_bfloat16* dst = out + static_cast<long long>(tq) * HD + col0;
+#pragma unroll
+    for (int i = 0; i < DH / 8; ++i) {
+        uint4 pk;
+        pk.x = pack_bf16(acc[i * 8 + 0] * inv, acc[i * 8 + 1] * inv);
+        pk.y = pack_bf16(acc[i * 8 + 2] * inv, acc[i * 8 + 3] * inv);
+        pk.z = pack_bf16(acc[i * 8 + 4] * inv, acc[i * 8 + 5] * inv);
+        pk.w = pack_bf16(acc[i * 8 + 6] * inv, acc[i * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + i * 8) = pk;
     }
 }
 
 int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                    const BatchDesc& b, int T, int S, int n_heads, int head_dim, __nv_bfloat16* out, cudaStream_t st) {
     ATS_CHECK_ARG(T >= 1 && S >= 1, "attention: T=%d S=%d", T, S);
-    static int bq_env = -1, plo_env = -1;   // queries per CTA: 64 unless ATSPEED_ATT_BQ=32; hi+lo P unless ATSPEED_ATT_PLO=0
-    if (bq_env < 0) { const char* e = getenv("ATSPEED_ATT_BQ"); bq_env = (e && atoi(e) == 32) ? 32 : ATT_BQ; }
-    if (plo_env < 0) { const char* e = getenv("ATSPEED_ATT_PLO"); plo_env = (e && atoi(e) == 0) ? 0 : 1; }
-    const int BQ = bq_env;
-    const bool plo = plo_env != 0;
-    int q_blocks = (T + BQ - 1) / BQ;
+    int q_blocks = (T + ATT_BQ - 1) / ATT_BQ;
     if (b.ckv.n > 0) {
         q_blocks = 0;
-        for (int u = 0; u < b.ckv.n; ++u) q_blocks += (b.ckv.T[u] + BQ - 1) / BQ;
+        for (int u = 0; u < b.ckv.n; ++u) q_blocks += (b.ckv.T[u] + ATT_BQ - 1) / ATT_BQ;
     }
     dim3 grid(q_blocks, n_heads);
     const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
-    const size_t smem = static_cast<size_t>(BQ + 4 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
-#define ATS_ATT(DD, QQ, LL)                                                                                              \
-    do {                                                                                                                 \
-        static bool attr_set = false;                                                                                    \
-        if (!attr_set) {                                                                                                 \
-            ATS_CUDA(cudaFuncSetAttribute(tree_attention_kernel<DD, QQ, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          96 * 1024));                                                                   \
-            attr_set = true;                                                                                             \
-        }                                                                                                                \
-        ATS_CUDA(launch_pdl(tree_attention_kernel<DD, QQ, LL>, grid, dim3(QQ * 2), smem, st, q, kcache, vcache,           \
+    const size_t smem = static_cast<size_t>(ATT_BQ + 4 * ATT_BK) * (head_dim + 8) * sizeof(__nv_bfloat16);
+#define ATS_ATT(DD)                                                                                                       \
+    do {                                                                                                                  \
+        static std::once_flag once;                                                                                       \
+        static cudaError_t err = cudaSuccess;                                                                             \
+        std::call_once(once, []() {                                                                                       \
+            err = cudaFuncSetAttribute(tree_attention_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+        });                                                                                                               \
+        ATS_CUDA(err);                                                                                                    \
+        ATS_CUDA(launch_pdl(tree_attention_kernel<DD>, grid, dim3(ATT_THREADS), smem, st, q, kcache, vcache,              \
                             b.prefix_len, b.vis, b.vis_base, T, S, n_heads, scale, out, b.ckv));                        \
     } while (0)
-#define ATS_ATT_BQ(DD)                               \
-    do {                                             \
-        if (BQ == 32 && plo) ATS_ATT(DD, 32, true);  \
-        else if (BQ == 32) ATS_ATT(DD, 32, false);   \
-        else if (plo) ATS_ATT(DD, 64, true);         \
-        else ATS_ATT(DD, 64, false);                 \
-    } while (0)
     switch (head_dim) {
-        case 16: ATS_ATT_BQ(16); break;
-        case 32: ATS_ATT_BQ(32); break;
-        case 64: ATS_ATT_BQ(64); break;
-        case 128: ATS_ATT_BQ(128); break;
+        case 16: ATS_ATT(16); break;
+        case 32: ATS_ATT(32); break;
+        case 64: ATS_ATT(64); break;
+        case 128: ATS_ATT(128); break;
         default:
             set_error("attention: head_dim=%d not in {16,32,64,128}", head_dim);
             return ATS_ERR_ARG;
     }
-#undef ATS_ATT_BQ
 #undef ATS_ATT
     return ATS_OK;
 }

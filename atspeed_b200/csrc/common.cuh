@@ -87,7 +87,7 @@ struct HangDiag {
 };
 enum : unsigned { HANG_K_GEMM = 1, HANG_K_GEMM_PAIR = 2, HANG_K_KVGATHER = 3 };
 enum : unsigned { HANG_R_PRODUCER = 1, HANG_R_MMA = 2, HANG_R_EPILOGUE = 3, HANG_R_COPY = 4 };
-enum : unsigned { HANG_B_EMPTY = 1, HANG_B_FULL = 2, HANG_B_ACCUM_FULL = 3, HANG_B_ACCUM_EMPTY = 4, HANG_B_ROW = 5 };
+enum : unsigned { HANG_B_EMPTY = 1, HANG_B_FULL = 2, HANG_B_ACCUM_FULL = 3, HANG_B_ACCUM_EMPTY = 4, HANG_B_ROW = 5, HANG_B_FLAG = 6 };
 struct SpinGuard {            // passed by value to the kernels that wait on mbarriers
     HangDiag* diag;           // device-visible address of the mapped record (nullptr: trap without a record)
     unsigned long long limit_ns;

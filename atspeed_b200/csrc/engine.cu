@@ -75,8 +75,8 @@ void hang_diag_describe(char* buf, size_t n) {
     if (!d || d->flag == 0) return;
     static const char* const kern[] = {"?", "gemm_wx_tcgen05", "gemm_wx_tcgen05_2cta", "kv_gather"};
     static const char* const role[] = {"?", "TMA producer", "MMA issuer", "epilogue", "copy thread"};
-    static const char* const bar[] = {"?", "empty", "full", "accum_full", "accum_empty", "row"};
-    const unsigned k = d->kernel < 4 ? d->kernel : 0, r = d->role < 5 ? d->role : 0, b = d->barrier < 6 ? d->barrier : 0;
+    static const char* const bar[] = {"?", "empty", "full", "accum_full", "accum_empty", "row", "partial-sum flag of worker"};
+    const unsigned k = d->kernel < 4 ? d->kernel : 0, r = d->role < 5 ? d->role : 0, b = d->barrier < 7 ? d->barrier : 0;
     snprintf(buf, n,
              " [device stall: %s block %u thread %u (%s) waited %.0f ms for %s[%u] parity %u, unit %u of [%u,%u), T=%u%s]",
              kern[k], d->block, d->thread, role[r], d->waited_ns * 1e-6, bar[b], d->index, d->parity, d->unit, d->u_begin,
@@ -227,6 +227,8 @@ static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_des
     s->lse = c.take<float>(s->R_max);
     s->prompts_dev = c.take<int>(static_cast<size_t>(U) * s->cfg.max_prompt);
     s->prompt_dev = s->prompts_dev;
+    s->fused_part = c.take<float>(gemm_fused_part_elems(s->T_max, s->num_sms));
+    s->fused_flags = c.take<unsigned int>(1024);
     s->collect_dev = c.take<int>(U * 4);
     s->res_tok_dev = c.take<int>(static_cast<size_t>(U) * MAX_K * MAX_NEW);
     s->res_score_dev = c.take<float>(static_cast<size_t>(U) * MAX_K);
@@ -288,6 +290,7 @@ static int build_gemm(GemmWeights& g, int K, std::initializer_list<std::pair<con
         g.colbase[g.n] = col;
         ATS_TRY(make_tmap_bf16_kmajor(&g.tmap[g.n], w.first, w.second, K, 128));
         ATS_TRY(make_tmap_bf16_kmajor(&g.tmap256[g.n], w.first, w.second, K, 256));
+        ATS_TRY(make_tmap_bf16_kmajor(&g.tmap64[g.n], w.first, w.second, K, 64));
         col += w.second;
         ++g.n;
     }
@@ -357,14 +360,25 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
     const auto* embed = static_cast<const __nv_bfloat16*>(d.embed);
     // work decomposition of the four projection shapes at this T (identical for every layer) + activation operand maps
     const LayerRT& L0 = m.layers[0];
+    // fused epilogues (opt-in, ATSPEED_FUSED_EPI=1): the q|k|v GEMM applies RoPE and appends to the KV cache, the gate|up GEMM
+    // applies SiLU * up; default: fp32 partial-sum slices + row-wise consumer kernels for both
+    const bool fused = s->fused;
     GemmPlan p_qkv, p_o, p_gu, p_down, p_lm;
-    ATS_TRY(gemm_make_plan(L0.qkv, T, s->num_sms, true, &p_qkv));
+    if (fused) {
+        ATS_TRY(gemm_make_plan_fused(L0.qkv, T, s->num_sms, EPI_QKV_ROPE, &p_qkv));
+        ATS_TRY(gemm_make_plan_fused(L0.gu, T, s->num_sms, EPI_SILU_MUL, &p_gu));
+    } else {
+        ATS_TRY(gemm_make_plan(L0.qkv, T, s->num_sms, true, &p_qkv));
+        ATS_TRY(gemm_make_plan(L0.gu, T, s->num_sms, true, &p_gu));
+    }
     ATS_TRY(gemm_make_plan(L0.o, T, s->num_sms, true, &p_o));
-    ATS_TRY(gemm_make_plan(L0.gu, T, s->num_sms, true, &p_gu));
     ATS_TRY(gemm_make_plan(L0.down, T, s->num_sms, true, &p_down));
     ATS_TRY(gemm_make_plan(m.lm, R, s->num_sms, false, &p_lm));
-    const SplitMap sm_qkv = gemm_split_map(L0.qkv, p_qkv), sm_o = gemm_split_map(L0.o, p_o),
-                   sm_gu = gemm_split_map(L0.gu, p_gu), sm_down = gemm_split_map(L0.down, p_down);
+    const SplitMap sm_o = gemm_split_map(L0.o, p_o), sm_down = gemm_split_map(L0.down, p_down);
+    SplitMap sm_qkv, sm_gu;
+    memset(&sm_qkv, 0, sizeof(sm_qkv));
+    memset(&sm_gu, 0, sizeof(sm_gu));
+    if (!fused) { sm_qkv = gemm_split_map(L0.qkv, p_qkv); sm_gu = gemm_split_map(L0.gu, p_gu); }
     XMap xm_x, xm_a, xm_m, xm_sel;
     ATS_TRY(gemm_make_xmap(&xm_x, m.x, T, d.hidden));
     ATS_TRY(gemm_make_xmap(&xm_a, m.a, T, m.HD));
@@ -372,9 +386,23 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
     ATS_TRY(gemm_make_xmap(&xm_sel, m.xsel, R, d.hidden));
     const int c_qkv = 3 * m.HD, c_gu = 2 * d.mlp;
     OMap om_qkv, om_o, om_gu, om_down, om_lm;
-    ATS_TRY(gemm_make_omap(&om_qkv, L0.qkv, m.part, c_qkv, static_cast<long long>(T) * c_qkv, T, p_qkv.max_slices));
+    if (!fused) {
+        ATS_TRY(gemm_make_omap(&om_qkv, L0.qkv, m.part, c_qkv, static_cast<long long>(T) * c_qkv, T, p_qkv.max_slices));
+        ATS_TRY(gemm_make_omap(&om_gu, L0.gu, m.part, c_gu, static_cast<long long>(T) * c_gu, T, p_gu.max_slices));
+    }
     ATS_TRY(gemm_make_omap(&om_o, L0.o, m.part, d.hidden, static_cast<long long>(T) * d.hidden, T, p_o.max_slices));
-    ATS_TRY(gemm_make_omap(&om_gu, L0.gu, m.part, c_gu, static_cast<long long>(T) * c_gu, T, p_gu.max_slices));
+    FusedEpi e_qkv, e_gu;
+    memset(&e_qkv, 0, sizeof(e_qkv));
+    memset(&e_gu, 0, sizeof(e_gu));
+    if (fused) {
+        e_qkv.kind = EPI_QKV_ROPE; e_qkv.part = s->fused_part; e_qkv.flags = s->fused_flags;
+        e_qkv.pos = b.pos; e_qkv.slot = b.slot; e_qkv.tok_user = b.tok_user;
+        e_qkv.rope_cos = d.rope_cos; e_qkv.rope_sin = d.rope_sin; e_qkv.max_pos = d.max_pos; e_qkv.head_dim = d.head_dim; e_qkv.HD = m.HD;
+        e_qkv.qbuf = m.q;
+        for (int i = 0; i < MAX_USERS; ++i) e_qkv.kv_off[i] = b.ckv.kv_off[i];
+        e_gu.kind = EPI_SILU_MUL; e_gu.part = s->fused_part; e_gu.flags = s->fused_flags; e_gu.m = m.m; e_gu.mlp = d.mlp;
+    }
+    auto next_epoch = [&]() { if (++s->fused_epoch == 0) ++s->fused_epoch; return s->fused_epoch; };
     ATS_TRY(gemm_make_omap(&om_down, L0.down, m.part, d.hidden, static_cast<long long>(T) * d.hidden, T, p_down.max_slices));
     ATS_TRY(gemm_make_omap(&om_lm, m.lm, m.logits, m.ldl, 0, R, 1));
     PROF(s, CAT_ELEM, 0, embed_rows(embed, b.tok, T, d.hidden, d.vocab, m.h, st));
@@ -384,23 +412,33 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
         LayerRT& L = m.layers[l];
         __nv_bfloat16* kc = m.kv + static_cast<long long>(l) * 2 * m.kv_plane;
         __nv_bfloat16* vc = kc + m.kv_plane;
-        PROF_GEMM(s, L.qkv, T, gemm_wx(L.qkv, xm_x, p_qkv, om_qkv, st));
-        PROF(s, CAT_ELEM, 0,
-             qkv_rope_append(m.part, sm_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
-                             d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
+        if (fused) {
+            e_qkv.kcache = kc; e_qkv.vcache = vc; e_qkv.epoch = next_epoch();
+            PROF_GEMM(s, L.qkv, T, gemm_wx_fused(L.qkv, xm_x, p_qkv, e_qkv, st));
+        } else {
+            PROF_GEMM(s, L.qkv, T, gemm_wx(L.qkv, xm_x, p_qkv, om_qkv, st));
+            PROF(s, CAT_ELEM, 0,
+                 qkv_rope_append(m.part, sm_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
+                                 d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
+        }
         PROF(s, CAT_ATTN, 0, tree_attention(m.q, kc, vc, b, T, S, d.n_heads, d.head_dim, m.a, st));
         PROF_GEMM(s, L.o, T, gemm_wx(L.o, xm_a, p_o, om_o, st));
         PROF(s, CAT_ELEM, 0,
              residual_rmsnorm(m.h, m.part, sm_o, static_cast<long long>(T) * d.hidden, d.hidden, L.ln2, T, d.hidden,
                               d.rms_eps, m.x, st));
-        PROF_GEMM(s, L.gu, T, gemm_wx(L.gu, xm_x, p_gu, om_gu, st));
-        PROF(s, CAT_ELEM, 0, silu_mul(m.part, sm_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
+        if (fused) {
+            e_gu.epoch = next_epoch();
+            PROF_GEMM(s, L.gu, T, gemm_wx_fused(L.gu, xm_x, p_gu, e_gu, st));
+        } else {
+            PROF_GEMM(s, L.gu, T, gemm_wx(L.gu, xm_x, p_gu, om_gu, st));
+            PROF(s, CAT_ELEM, 0, silu_mul(m.part, sm_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
+        }
         PROF_GEMM(s, L.down, T, gemm_wx(L.down, xm_m, p_down, om_down, st));
         const __nv_bfloat16* next_ln = l + 1 < d.n_layers ? m.layers[l + 1].ln1 : nullptr;
         PROF(s, CAT_ELEM, 0,
              residual_rmsnorm(m.h, m.part, sm_down, static_cast<long long>(T) * d.hidden, d.hidden, next_ln, T,
                               d.hidden, d.rms_eps, m.x, st));
-        s->launches += 9;
+        s->launches += fused ? 7 : 9;
     }
     PROF(s, CAT_ELEM, 0,
          rmsnorm_rows(m.h, static_cast<const __nv_bfloat16*>(d.final_norm), R, d.hidden, d.rms_eps, m.xsel, rows_idx, st));
@@ -568,6 +606,11 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
         if (s->sample_B > MAX_BEAMS) s->sample_B = MAX_BEAMS;
     }
     s->launches = 0;
+    s->fused_epoch = 0;
+    // opt-in (ATSPEED_FUSED_EPI=1): correct on every tile path (tests/test_gpu_fused_epilogue.py) but measured SLOWER than the
+    // row-wise consumer kernels (124 vs 139 users/s, profiles/r02_fused_epilogue_ab.txt): with one TMEM accumulator at T > 256
+    // the epilogue is exposed, and 128 epilogue threads per SM do math that the row-wise kernels spread over 2048
+    { const char* e = getenv("ATSPEED_FUSED_EPI"); s->fused = e && atoi(e) == 1; }
     s->prof_on = false;
     s->prof_n = 0;
     for (double& b : s->prof_bytes) b = 0;

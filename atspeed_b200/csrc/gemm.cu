@@ -175,6 +175,7 @@ struct GemmParams {
     int n_mma, N_mma;         // 2-CTA kernel: the token axis (padded to 64) is covered by n_mma MMAs of N_mma columns each
     SpinGuard guard;          // bound + diagnostic record of every mbarrier wait
     GemmTrace trace;          // optional per-CTA progress words (ATSPEED_GEMM_TRACE=1)
+    FusedEpi epi;             // kind != EPI_SLICES: tiles are finished inside the kernel (kernels.h)
 };
 __device__ __forceinline__ void trace_put(const GemmTrace& t, int word, unsigned v) {
     if (t.buf != nullptr && blockIdx.x < TRACE_CTAS) {
@@ -186,6 +187,275 @@ __device__ __forceinline__ unsigned sm_id() {
     unsigned r;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
     return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused epilogues (FusedEpi, kernels.h): shared by the single-CTA and the CTA-pair kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flag_release(unsigned int* flag, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int flag_acquire(const unsigned int* flag) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return v;
+}
+// bounded like every other wait of the kernel: the CTA waited for is one with a HIGHER index that writes its partial as the
+// first thing it does, so this never waits long unless that CTA is not resident yet (it is dispatched in index order)
+__device__ __forceinline__ void flag_wait(const unsigned int* flag, unsigned int epoch, const WaitCtx& w, unsigned worker, unsigned unit) {
+    if (flag_acquire(flag) == epoch) return;
+    const unsigned long long t0 = global_timer_ns();
+    for (uint32_t spins = 1;; ++spins) {
+        if (flag_acquire(flag) == epoch) return;
+        if ((spins & 63u) == 0u && w.g.limit_ns != 0ull) {
+            const unsigned long long dt = global_timer_ns() - t0;
+            if (dt > w.g.limit_ns) hang_report(w.g, w.kernel, w.role, HANG_B_FLAG, worker, epoch, unit, w.u_begin, w.u_end, w.T, dt);
+        }
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+    r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+    return r;
+}
+// bf16(bf16(silu(g)) * u) with g, u rounded to bf16 first: the rounding points of an HF bf16 LlamaMLP (elementwise.cu silu_mul)
+__device__ __forceinline__ float silu_mul_bf16(float g, float u) {
+    g = bf16_round(g); u = bf16_round(u);
+    return bf16_round(g / (1.0f + expf(-g))) * u;
+}
+
+// Drain every segment of this CTA's unit range [u_begin, u_end).  `worker` = owner of the unit range (the CTA, or the CTA pair),
+// `sub` = this CTA's rank inside the worker.  One 128-row half of a tile sits in TMEM lanes 0..127 (lane = feature row),
+// token t in accumulator column t.  Called by the four epilogue warps (threads 64..191).
+//   non-owner segment (does not start at the tile's first k-block): raw fp32 partial -> FusedEpi::part, then the flag;
+//   owner segment: wait for the flags of the CTAs that hold the rest of the tile, add their partials in slice order, then
+//     EPI_QKV_ROPE : stage [16 tokens][128 features] in shared memory (a RoPE pair sits head_dim/2 lanes apart), rotate,
+//                    write q to qbuf and k / v to the KV-cache rows with 16-byte stores;
+//     EPI_SILU_MUL : interleaved tile (lanes 0..63 gate, 64..127 up of the same 64 features) through the same staging tile,
+//                    or stacked tile (BM = 256: gate in the first accumulator, up in the second, same lane) from registers.
+template <bool PAIR>
+__device__ __forceinline__ void fused_epilogue(const GemmParams& p, int worker, int sub, int u_begin, int u_end, uint32_t tmem_base,
+                                               float* stage_out, uint64_t* accum_full, uint64_t* accum_empty, const WaitCtx& wc,
+                                               int* s_pos, int* s_slotuser, long long* s_kvoff) {
+    const FusedEpi& e = p.epi;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
+    const int f = q * 32 + lane;                    // this thread's TMEM lane = feature row of the 128-row half
+    const int ti = threadIdx.x - 64;                // 0..127 among the epilogue threads
+    const bool elected = ti == 0;
+    const int KB = p.n_kblocks;
+    constexpr int NSUB = PAIR ? 2 : 1;
+    const int halves = PAIR ? 1 : (p.BM >> 7);
+    const int BMW = PAIR ? 256 : p.BM;              // weight rows per tile of a worker
+    const bool stacked = !PAIR && e.kind == EPI_SILU_MUL && p.BM == 256;
+    const long long half_elems = static_cast<long long>(p.T_pad) * 128;
+    float* my_part = e.part + static_cast<long long>(worker * NSUB + sub) * halves * half_elems;
+    const int tok = ti >> 3, g8 = (ti & 7) * 8;      // staged chunk: this thread's token and first of 8 consecutive features
+    const int hd = e.head_dim, hhalf = e.head_dim >> 1;
+    const int nchunk = (p.T + 15) >> 4;
+    // RoPE: the 8 features [g8, g8 + 8) and [g8 + 64, g8 + 72) of a staged tile use the SAME 8 cos / sin values (their indices
+    // inside the head differ by 64: a multiple of head_dim, or exactly head_dim / 2 for heads of 128), so one set per token
+    // serves both groups; whether a group is the low or the high half of its rotary pairs is decided per group below
+    const int ci = (g8 % hd) % hhalf;
+    if (e.kind == EPI_QKV_ROPE) {
+        // per-token metadata once per CTA (positions, cache rows): the chunk loop below must not wait for global memory
+        for (int i = ti; i < p.T; i += 128) {
+            int pp = e.pos[i];
+            s_pos[i] = pp < 0 ? 0 : (pp >= e.max_pos ? e.max_pos - 1 : pp);
+            s_slotuser[i] = e.slot[i] | ((e.tok_user ? e.tok_user[i] : 0) << 24);
+        }
+        if (ti < MAX_USERS) s_kvoff[ti] = e.tok_user ? e.kv_off[ti] : 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    int seg = 0, chunk = 0;
+    for (int u = u_begin; u < u_end; ++seg) {
+        const int tile = u / KB;
+        const int seg_end = min((tile + 1) * KB, u_end);
+        const bool owner = u == tile * KB;
+        const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
+        mbar_wait(&accum_full[buf], use & 1, wc, HANG_B_ACCUM_FULL, buf, u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tb = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
+        if (!owner) {
+            for (int half = 0; half < halves; ++half) {
+                float* dst = my_part + half * half_elems + f;
+                for (int c = 0; c < p.T; c += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tb + half * p.acc_stride + static_cast<uint32_t>(c), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dst[static_cast<long long>(c + j) * 128] = __uint_as_float(r[j]);   // rows < T_pad
+                }
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (elected) flag_release(e.flags + worker * NSUB + sub, e.epoch);
+        } else {
+            const int n_extra = ((tile + 1) * KB - 1) / p.U - worker;     // workers after this one that hold a part of the tile
+            if (n_extra > 0) {
+                if (elected)
+                    for (int s2 = 1; s2 <= n_extra; ++s2) flag_wait(e.flags + (worker + s2) * NSUB + sub, e.epoch, wc, worker + s2, u);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            // raw partial of slice s2 (the worker s2 places after this one), half `half`, this thread's feature row
+            auto part_of = [&](int s2, int half) -> const float* {
+                return e.part + (static_cast<long long>((worker + s2) * NSUB + sub) * halves + half) * half_elems + f;
+            };
+            int wid = 0, tw = tile;                   // weight and tile index inside it (EPI_QKV_ROPE)
+            if (e.kind == EPI_QKV_ROPE) {
+                if (tw >= p.tiles[0]) { tw -= p.tiles[0]; wid = 1; }
+                if (wid == 1 && tw >= p.tiles[1]) { tw -= p.tiles[1]; wid = 2; }
+            }
+            if (stacked) {
+                // gate = first accumulator, up = second, same lane: straight from registers.  The partials of the next chunk
+                // are requested before this chunk is processed (an L2 round trip per chunk would otherwise be exposed).
+                const int feat = tile * 128 + f;
+                float png[16], pnu[16];
+                if (n_extra > 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { png[j] = __ldcg(part_of(1, 0) + static_cast<long long>(j) * 128); pnu[j] = __ldcg(part_of(1, 1) + static_cast<long long>(j) * 128); }
+                }
+                for (int c = 0; c < p.T; c += 16) {
+                    uint32_t rg[16], ru[16];
+                    tmem_ld16(tb + static_cast<uint32_t>(c), rg);
+                    tmem_ld16(tb + p.acc_stride + static_cast<uint32_t>(c), ru);
+                    float g[16], uu[16];
+                    if (n_extra > 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { g[j] = png[j]; uu[j] = pnu[j]; }
+                        if (c + 16 < p.T) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                png[j] = __ldcg(part_of(1, 0) + static_cast<long long>(c + 16 + j) * 128);
+                                pnu[j] = __ldcg(part_of(1, 1) + static_cast<long long>(c + 16 + j) * 128);
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        g[j] = n_extra > 0 ? __uint_as_float(rg[j]) + g[j] : __uint_as_float(rg[j]);
+                        uu[j] = n_extra > 0 ? __uint_as_float(ru[j]) + uu[j] : __uint_as_float(ru[j]);
+                    }
+                    for (int s2 = 2; s2 <= n_extra; ++s2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            g[j] += __ldcg(part_of(s2, 0) + static_cast<long long>(c + j) * 128);
+                            uu[j] += __ldcg(part_of(s2, 1) + static_cast<long long>(c + j) * 128);
+                        }
+                    }
+                    if (feat < e.mlp) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c + j < p.T) e.m[static_cast<long long>(c + j) * e.mlp + feat] = __float2bfloat16_rn(silu_mul_bf16(g[j], uu[j]));
+                    }
+                }
+            } else {
+                const int total = halves * nchunk;
+                float pn[16];                                          // slice-1 partial of the NEXT chunk (prefetched)
+                float4 cnx[2], snx[2];                                 // cos / sin of this thread's token in the NEXT chunk
+                auto fetch_partial = [&](int idx) {
+                    const float* src = part_of(1, idx / nchunk) + static_cast<long long>((idx % nchunk) * 16) * 128;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pn[j] = __ldcg(src + static_cast<long long>(j) * 128);
+                };
+                auto fetch_rope = [&](int idx) {
+                    const int t = (idx % nchunk) * 16 + tok;
+                    if (e.kind == EPI_QKV_ROPE && wid != 2 && t < p.T) {
+                        const float* ct = e.rope_cos + static_cast<long long>(s_pos[t]) * hhalf + ci;
+                        const float* sn = e.rope_sin + static_cast<long long>(s_pos[t]) * hhalf + ci;
+                        cnx[0] = __ldg(reinterpret_cast<const float4*>(ct)); cnx[1] = __ldg(reinterpret_cast<const float4*>(ct) + 1);
+                        snx[0] = __ldg(reinterpret_cast<const float4*>(sn)); snx[1] = __ldg(reinterpret_cast<const float4*>(sn) + 1);
+                    }
+                };
+                if (n_extra > 0) fetch_partial(0);
+                fetch_rope(0);
+                for (int idx = 0; idx < total; ++idx, ++chunk) {
+                    const int half = idx / nchunk, c = (idx - half * nchunk) * 16;
+                    uint32_t r[16];
+                    tmem_ld16(tb + half * p.acc_stride + static_cast<uint32_t>(c), r);
+                    float v[16];
+                    const float4 cc0 = cnx[0], cc1 = cnx[1], ss0 = snx[0], ss1 = snx[1];
+                    if (n_extra > 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = pn[j];
+                        if (idx + 1 < total) fetch_partial(idx + 1);
+                    }
+                    if (idx + 1 < total) fetch_rope(idx + 1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = n_extra > 0 ? __uint_as_float(r[j]) + v[j] : __uint_as_float(r[j]);
+                    for (int s2 = 2; s2 <= n_extra; ++s2) {
+                        const float* src = part_of(s2, half) + static_cast<long long>(c) * 128;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __ldcg(src + static_cast<long long>(j) * 128);
+                    }
+                    // double-buffered staging tile: chunk k+2 overwrites buffer k only after every thread has passed the
+                    // barrier of chunk k+1, i.e. after it finished reading buffer k
+                    float* stg = stage_out + (chunk & 1) * (16 * 128);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) stg[j * 128 + f] = v[j];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int t = c + tok;
+                    if (t >= p.T) continue;
+                    const float* srow = stg + tok * 128;
+                    if (e.kind == EPI_SILU_MUL) {
+                        // lanes 0..63 = gate rows, 64..127 = up rows of features [f0, f0 + 64)
+                        const int feat = tile * (PAIR ? 128 : 64) + sub * 64 + g8;
+                        if (feat < e.mlp) {
+                            const float4 ga = *reinterpret_cast<const float4*>(srow + g8), gb = *reinterpret_cast<const float4*>(srow + g8 + 4);
+                            const float4 ua = *reinterpret_cast<const float4*>(srow + 64 + g8), ub = *reinterpret_cast<const float4*>(srow + 64 + g8 + 4);
+                            float o[8] = {silu_mul_bf16(ga.x, ua.x), silu_mul_bf16(ga.y, ua.y), silu_mul_bf16(ga.z, ua.z), silu_mul_bf16(ga.w, ua.w),
+                                          silu_mul_bf16(gb.x, ub.x), silu_mul_bf16(gb.y, ub.y), silu_mul_bf16(gb.z, ub.z), silu_mul_bf16(gb.w, ub.w)};
+                            *reinterpret_cast<uint4*>(e.m + static_cast<long long>(t) * e.mlp + feat) = pack_bf16x8(o);
+                        }
+                    } else {
+                        const int su = s_slotuser[t];
+                        const long long srow_kv = static_cast<long long>(su & 0xffffff) * e.HD + s_kvoff[(su >> 24) & (MAX_USERS - 1)];
+                        const float cs[8] = {cc0.x, cc0.y, cc0.z, cc0.w, cc1.x, cc1.y, cc1.z, cc1.w};
+                        const float sn[8] = {ss0.x, ss0.y, ss0.z, ss0.w, ss1.x, ss1.y, ss1.z, ss1.w};
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi) {
+                            const int grp = g8 + gi * 64;                         // 8 features [grp, grp + 8) of the staged 128
+                            const int col = tw * BMW + sub * 128 + half * 128 + grp;   // column inside the weight's output
+                            if (col >= p.n_rows[wid]) continue;
+                            float o[8];
+                            const float4 xa = *reinterpret_cast<const float4*>(srow + grp), xb = *reinterpret_cast<const float4*>(srow + grp + 4);
+                            const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                            if (wid == 2) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) o[k] = x[k];
+                            } else {
+                                // HF apply_rotary_pos_emb in bf16: (x * cos) + (rotate_half(x) * sin), every op rounded
+                                const bool rope_lo = (grp % hd) < hhalf;
+                                const int pgrp = rope_lo ? grp + hhalf : grp - hhalf;    // the RoPE partners, same staged tile
+                                const float4 ya = *reinterpret_cast<const float4*>(srow + pgrp), yb = *reinterpret_cast<const float4*>(srow + pgrp + 4);
+                                const float y[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const float xx = bf16_round(x[k]), yy = bf16_round(y[k]);
+                                    o[k] = rope_lo ? bf16_round(bf16_round(xx * cs[k]) + bf16_round(-yy * sn[k]))
+                                                   : bf16_round(bf16_round(xx * cs[k]) + bf16_round(yy * sn[k]));
+                                }
+                            }
+                            __nv_bfloat16* dst = wid == 0 ? e.qbuf + static_cast<long long>(t) * e.HD + col
+                                               : (wid == 1 ? e.kcache : e.vcache) + srow_kv + col;
+                            *reinterpret_cast<uint4*>(dst) = pack_bf16x8(o);
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&accum_empty[buf], 0);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
+        }
+        u = seg_end;
+    }
 }
 
 // Work decomposition ("stream-K with consumer-side fix-up").  The (tile, k-block) units of the whole GEMM are
@@ -205,6 +475,8 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t accum_full[2], accum_empty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) int s_pos[512], s_slotuser[512];     // fused RoPE epilogue: per-token position / cache row
+    __shared__ __align__(8) long long s_kvoff[MAX_USERS];
 
     // let the next kernel of the stream start its own prologue / weight prefetch as early as resources allow (PDL)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -265,7 +537,14 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
                 uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
                 mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(a_bytes + p.b_box_bytes));
-                tma_load_2d(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);      // BM = 256: the map's box is 256 rows
+                if (p.epi.kind == EPI_SILU_MUL) {
+                    // interleaved tile: the gate rows and the up rows of the SAME features (two boxes of BM/2 rows)
+                    const int rows = p.BM >> 1;
+                    tma_load_2d(&tmW0, &full_bar[s], a_dst, kb * BLOCK_K, tile * rows);
+                    tma_load_2d(&tmW1, &full_bar[s], a_dst + rows * BLOCK_K * 2, kb * BLOCK_K, tile * rows);
+                } else {
+                    tma_load_2d(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);      // BM = 256: the map's box is 256 rows
+                }
             };
             auto load_b = [&](int s, int kbb) {
                 uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
@@ -342,6 +621,9 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);   // 2 x 8 KB
         int st_chunk = 0;
         int seg = 0;
+        if (p.epi.kind != EPI_SLICES) {
+            fused_epilogue<false>(p, blockIdx.x, 0, u_begin, u_end, tmem_base, stage_out, accum_full, accum_empty, wc, s_pos, s_slotuser, s_kvoff);
+        } else
         for (int u = u_begin; u < u_end; ++seg) {
             const int tile = u / KB;
             const int seg_end = min((tile + 1) * KB, u_end);
@@ -434,6 +716,8 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t accum_full[2], accum_empty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) int s_pos[512], s_slotuser[512];     // fused RoPE epilogue: per-token position / cache row
+    __shared__ __align__(8) long long s_kvoff[MAX_USERS];
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -512,7 +796,15 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             auto load_a = [&](int s) {
                 const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
                 if (leader) mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
-                tma_load_2d_2sm(tmW, &full_bar[s], smem + static_cast<size_t>(s) * stage_bytes, kb * BLOCK_K, m0);
+                uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
+                if (p.epi.kind == EPI_SILU_MUL) {
+                    // this CTA's 128 rows = the gate rows and the up rows of ITS 64 features of the pair's 128-feature tile
+                    const int r0 = tile * 128 + static_cast<int>(rank) * 64;
+                    tma_load_2d_2sm(&tmW0, &full_bar[s], a_dst, kb * BLOCK_K, r0);
+                    tma_load_2d_2sm(&tmW1, &full_bar[s], a_dst + 64 * BLOCK_K * 2, kb * BLOCK_K, r0);
+                } else {
+                    tma_load_2d_2sm(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);
+                }
             };
             auto load_b = [&](int s, int kbb) {
                 uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
@@ -592,6 +884,9 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
         int seg = 0;
         const bool elected = threadIdx.x == 64;
         const int f = q * 32 + lane;
+        if (p.epi.kind != EPI_SLICES) {
+            fused_epilogue<true>(p, pair, static_cast<int>(rank), u_begin, u_end, tmem_base, stage_out, accum_full, accum_empty, wc, s_pos, s_slotuser, s_kvoff);
+        } else
         for (int u = u_begin; u < u_end; ++seg) {
             const int tile = u / KB;
             const int seg_end = min((tile + 1) * KB, u_end);
@@ -809,6 +1104,78 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     return ATS_OK;
 }
 
+// Plan of a fused-epilogue launch: plain stream-K (equal contiguous unit ranges, no whole-k-split variant: a tile cut in two
+// costs one partial store + one partial load inside the kernel instead of a consumer pass).  EPI_SILU_MUL tiles hold the gate
+// rows and the up rows of the same features: BM/2 features per tile of a single CTA, 128 per tile of a CTA pair.
+int gemm_make_plan_fused(const GemmWeights& w, int T, int num_sms, int kind, GemmPlan* pl) {
+    ATS_CHECK_ARG(T >= 1 && T <= 512, "gemm: T=%d out of range [1,512]", T);
+    ATS_CHECK_ARG(kind == EPI_QKV_ROPE ? w.n == 3 : (kind == EPI_SILU_MUL && w.n == 2 && w.rows[0] == w.rows[1]),
+                  "gemm: fused epilogue %d does not fit %d weight matrices", kind, w.n);
+    ATS_CHECK_ARG(num_sms >= 1, "gemm: num_sms=%d", num_sms);
+    memset(pl, 0, sizeof(*pl));
+    pl->epi_kind = kind;
+    pl->T = T;
+    pl->T_pad = (T + 15) & ~15;
+    pl->KB = (w.K + BLOCK_K - 1) / BLOCK_K;
+    pl->max_slices = 1;
+    const bool pair = gemm_use_2cta(T) && num_sms >= 2;
+    int workers = num_sms, stage_bytes;
+    if (pair) {
+        pl->two_cta = 1;
+        const int T64 = (T + 63) & ~63;
+        pl->n_mma = T64 > 256 ? 2 : 1;
+        pl->N_mma = T64 / pl->n_mma;
+        pl->BM = 256;
+        workers = num_sms / 2;
+        stage_bytes = A_TILE_BYTES + (T64 / 2) * BLOCK_K * 2;
+        int acc = 32;
+        while (acc < T64) acc <<= 1;
+        pl->acc_stride = acc;
+        pl->n_bufs = 2 * acc <= 512 ? 2 : 1;
+        pl->buf_stride = acc;
+        pl->tmem_cols = pl->n_bufs * acc;
+    } else {
+        int tiles128 = 0;
+        for (int i = 0; i < w.n; ++i) tiles128 += (w.rows[i] + 127) / 128;
+        pl->BM = (pl->T_pad <= 128 && tiles128 >= 2) ? 256 : 128;
+        stage_bytes = pl->BM * BLOCK_K * 2 + pl->T_pad * BLOCK_K * 2;
+        int acc = 32;
+        while (acc < pl->T_pad) acc <<= 1;
+        pl->acc_stride = acc;
+        const int per_buf = pl->BM == 256 ? 2 * acc : acc;
+        pl->n_bufs = 2 * per_buf <= 512 ? 2 : 1;
+        pl->buf_stride = per_buf;
+        pl->tmem_cols = pl->n_bufs * per_buf;
+    }
+    pl->total_tiles = 0;
+    for (int i = 0; i < 3; ++i) {
+        pl->tiles[i] = 0;
+        if (kind == EPI_QKV_ROPE && i < w.n) pl->tiles[i] = (w.rows[i] + pl->BM - 1) / pl->BM;
+        if (kind == EPI_SILU_MUL && i == 0) pl->tiles[i] = (w.rows[0] + pl->BM / 2 - 1) / (pl->BM / 2);
+        pl->tilebase[i] = pl->total_tiles;
+        pl->total_tiles += pl->tiles[i];
+    }
+    const int units = pl->total_tiles * pl->KB;
+    const int grid = units < workers ? units : workers;
+    pl->U = (units + grid - 1) / grid;
+    const int min_u = pl->KB < 8 ? pl->KB : 8;
+    if (pl->U < min_u) pl->U = min_u;
+    pl->grid = (pair ? 2 : 1) * ((units + pl->U - 1) / pl->U);
+    int stages = (220 * 1024 - OUT_STAGE_BYTES) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
+    ATS_CHECK_ARG(stages >= 2, "gemm: T=%d leaves room for %d pipeline stages", T, stages);
+    pl->stages = stages;
+    ATS_CHECK_ARG(pl->tmem_cols <= 512, "gemm: %d TMEM columns", pl->tmem_cols);
+    return ATS_OK;
+}
+
+// floats of FusedEpi::part: one [T_pad][128] tile per CTA and 128-row half (single CTA, BM = 256 at T <= 128: two halves)
+size_t gemm_fused_part_elems(int T_max, int num_sms) {
+    const size_t t = static_cast<size_t>(((T_max + 15) & ~15) > 256 ? ((T_max + 15) & ~15) : 256);
+    return static_cast<size_t>(num_sms) * t * 128;
+}
+
 // upper bound of partial-sum slices over every T the plan function can be asked for (workspace sizing)
 int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms) {
     int best = 1;
@@ -902,17 +1269,28 @@ static int gemm_init_device(int* max_dyn_out) {
     return ATS_OK;
 }
 
-// out[slice][t][...]. X: [T, K] bf16 row-major (through xm). W_i: [n_rows_i, K] bf16 row-major.
-int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap& om, cudaStream_t stream) {
-    float* out = om.out;
-    const int ldo = om.ldo;
-    const long long slice_stride = om.slice_stride;
-    ATS_CHECK_ARG(om.T == pl.T, "gemm: output map built for T=%d, plan for T=%d", om.T, pl.T);
+// out[slice][t][...]. X: [T, K] bf16 row-major (through xm). W_i: [n_rows_i, K] bf16 row-major.  om (EPI_SLICES plans) or
+// epi (fused plans) says where the result goes.
+static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap* om, const FusedEpi* epi,
+                       cudaStream_t stream) {
+    ATS_CHECK_ARG((om != nullptr) != (epi != nullptr) && (epi ? epi->kind == pl.epi_kind : pl.epi_kind == EPI_SLICES),
+                  "gemm: output description does not match the plan (epilogue kind %d)", pl.epi_kind);
+    ATS_CHECK_ARG(!om || om->T == pl.T, "gemm: output map built for T=%d, plan for T=%d", om ? om->T : 0, pl.T);
     ATS_CHECK_ARG(xm.T == pl.T && xm.K == w.K, "gemm: activation map (%d x %d) does not match the plan (%d x %d)", xm.T,
                   xm.K, pl.T, w.K);
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.out = out; p.ldo = ldo; p.slice_stride = slice_stride;
+    if (om) { p.out = om->out; p.ldo = om->ldo; p.slice_stride = om->slice_stride; p.tma_store = om->ok; }
+    if (epi) {
+        p.epi = *epi;
+        ATS_CHECK_ARG(epi->part && epi->flags && epi->epoch != 0, "gemm: fused epilogue without workspace / epoch");
+        if (epi->kind == EPI_QKV_ROPE)
+            ATS_CHECK_ARG(epi->head_dim >= 16 && 128 % epi->head_dim == 0 && epi->HD % 8 == 0 && epi->pos && epi->slot && epi->qbuf &&
+                              epi->kcache && epi->vcache && epi->rope_cos && epi->rope_sin,
+                          "gemm: RoPE epilogue needs head_dim in {16,32,64,128} (got %d) and all of its buffers", epi->head_dim);
+        else
+            ATS_CHECK_ARG(epi->m && epi->mlp % 8 == 0 && epi->mlp == w.rows[0], "gemm: SiLU epilogue: mlp=%d", epi->mlp);
+    }
     p.T = pl.T; p.T_pad = pl.T_pad; p.n_kblocks = pl.KB;
     for (int i = 0; i < 3; ++i) {
         p.n_rows[i] = i < w.n ? w.rows[i] : 0;
@@ -926,7 +1304,6 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
     p.guard = spin_guard();
     p.trace = pl.two_cta ? gemm_trace() : GemmTrace{nullptr, 0};
-    p.tma_store = om.ok;
     const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
                                        : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
     size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + OUT_STAGE_BYTES + 1024;
@@ -949,17 +1326,28 @@ int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // previous kernel; see griddepcontrol.wait
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    // weight operand maps: 128-row boxes, 256-row boxes for the stacked single-CTA tiles, and for the interleaved SiLU tiles
+    // the gate / up halves (BM/2 rows per box of a single CTA, 64 rows per CTA of a pair)
+    const CUtensorMap* tw = (!pl.two_cta && pl.BM == 256) ? w.tmap256 : w.tmap;
+    if (pl.epi_kind == EPI_SILU_MUL) tw = (pl.two_cta || pl.BM == 128) ? w.tmap64 : w.tmap;
+    const CUtensorMap& o0 = om ? om->tm[0] : tw[0];                     // fused launches never touch the output maps
+    const CUtensorMap& o1 = om ? om->tm[1] : tw[0];
+    const CUtensorMap& o2 = om ? om->tm[2] : tw[0];
     if (pl.two_cta) {
         ATS_CHECK_ARG((pl.grid & 1) == 0, "gemm (2-CTA): grid %d", pl.grid);
-        const CUtensorMap* tw = w.tmap;      // each CTA of the pair loads its own 128-row box
-        ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, om.tm[0],
-                                    om.tm[1], om.tm[2], p));
+        ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, o0, o1, o2, p));
         return ATS_OK;
     }
-    const CUtensorMap* tw = pl.BM == 256 ? w.tmap256 : w.tmap;
-    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1,
-                                om.tm[0], om.tm[1], om.tm[2], p));
+    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1, o0, o1, o2, p));
     return ATS_OK;
+}
+
+int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const OMap& om, cudaStream_t stream) {
+    return gemm_launch(w, xm, pl, &om, nullptr, stream);
+}
+
+int gemm_wx_fused(const GemmWeights& w, const XMap& xm, const GemmPlan& pl, const FusedEpi& epi, cudaStream_t stream) {
+    return gemm_launch(w, xm, pl, nullptr, &epi, stream);
 }
 
 bool pdl_enabled() {

@@ -59,6 +59,11 @@ struct atspeed_session {
     float* res_score_dev;                        // [max_users][K]
     long long kv_user_elems_tgt, kv_user_elems_dft;   // elements between two users' KV caches
     int* cohort_pinned;                          // pinned host staging of the cohort scheduler
+    // fused GEMM epilogues (gemm.cu FusedEpi): in-kernel partial-sum workspace, per-CTA flags, launch epoch
+    float* fused_part;
+    unsigned int* fused_flags;
+    unsigned int fused_epoch;
+    bool fused;                                  // false: ATSPEED_FUSED_EPI=0, the row-wise consumer kernels run instead
 
     atspeed_config cfg;
     atspeed::TreeGeom geom;

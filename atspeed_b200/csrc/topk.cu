@@ -56,9 +56,10 @@ __device__ __forceinline__ MaxSum ms_merge(MaxSum a, MaxSum b) {
     return r;
 }
 
-// UNR = 128-bit loads in flight per thread in the streaming pass.  2 is the tested default; 8 (EXPERIMENTAL,
-// ATSPEED_TOPK_UNROLL=8, never executed) is for launches with fewer rows than SMs, where one 256-thread CTA per SM with
-// 8 KB in flight cannot cover the HBM latency (the sum-exp is then accumulated in chunks of 8 vectors: last-bit differences).
+// UNR = 128-bit loads in flight per thread in the streaming pass.  With fewer rows than ~2 CTAs per SM the kernel is bound by
+// memory-level parallelism, not bandwidth: 8 loads in flight read a 121-row launch in 10.5 us instead of 16.6 us (fp32; bf16
+// 9.8 vs 12.7 us); with thousands of rows occupancy provides the parallelism and UNR = 2 is faster (bf16, 8192 rows: 4.9 vs
+// 4.0 TB/s).  Measured in profiles/r02_kernels_a_c_gbs.txt; the launcher picks by row count, ATSPEED_TOPK_UNROLL forces one.
 template <typename T, int UNR>
 __global__ void __launch_bounds__(TOPK_THREADS)
 mask_logsoftmax_topk_kernel(const T* __restrict__ logits, int V, long long ld, const int* __restrict__ row_node,
@@ -214,8 +215,8 @@ int mask_logsoftmax_topk(const void* logits, int logits_bf16, int rows, int V, l
                          float* cand_logp, int* cand_cnt, float* lse, cudaStream_t st) {
     ATS_CHECK_ARG(rows >= 1 && V >= 1 && B >= 1 && B <= MAX_BEAMS, "topk: rows=%d V=%d B=%d", rows, V, B);
     ATS_CHECK_ARG(ld >= V, "topk: row stride %lld < V %d", ld, V);
-    static int unr_env = -1;
-    if (unr_env < 0) { const char* e = getenv("ATSPEED_TOPK_UNROLL"); unr_env = (e && atoi(e) == 8) ? 8 : 2; }
+    static const int unr_forced = []() { const char* e = getenv("ATSPEED_TOPK_UNROLL"); return e ? atoi(e) : 0; }();
+    const int unr_env = unr_forced == 8 || unr_forced == 2 ? unr_forced : (rows <= 320 ? 8 : 2);
 #define ATS_TOPK(TT, UU)                                                                                                  \
     mask_logsoftmax_topk_kernel<TT, UU><<<rows, TOPK_THREADS, 0, st>>>(static_cast<const TT*>(logits), V, ld, row_node,    \
                                                                        n_rows_dev, trie.child_off, trie.child_tok,        \

@@ -118,6 +118,55 @@ class RecDataset:
         return self.decode_items(self.item_token_ids[self.ground_truth(u)])
 
 
+def prompt_len(n_history: int) -> int:
+    """Length of the prompt of a user with `n_history` history items (closed form of RecDataset.prompt_ids)."""
+    h = n_history
+    seps = ((h - 1 + 1) // 2) * len(_SEP1) + ((h - 1) // 2) * len(_SEP2) if h > 0 else 0
+    return 1 + len(_PREFIX) + 4 * h + seps + len(_SUFFIX) + len(RESPONSE_SEP)
+
+
+class DevicePromptBuilder:
+    """Prompts built ON THE DEVICE from history item ids (csrc/prompt.cu): the dataset's item -> 4 code-token
+    table and the concatenated user histories live in HBM; `build(users)` launches one kernel that writes the users' prompts
+    into one concatenated int32 tensor -- the input layout of Session.bssd_batch_device -- and returns it with the prompt
+    lengths (host closed form, no tokenisation).  Mirrors reference code/data.py:232-263 + code/collator.py:50-75."""
+
+    def __init__(self, ds: RecDataset, device):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+        self.ds, self.device, self.lib, self._C, self._torch = ds, torch.device(device), _lib.load(), C, torch
+        self.item_tok = torch.from_numpy(np.ascontiguousarray(ds.item_token_ids.astype(np.int32))).to(self.device)
+        self.hist_items = torch.from_numpy(np.ascontiguousarray(ds.hist_items.astype(np.int32))).to(self.device)
+        t = _lib.PromptTemplate()
+        t.bos, t.n_prefix, t.n_suffix, t.n_resp = BOS_ID, len(_PREFIX), len(_SUFFIX), len(RESPONSE_SEP)
+        t.n_sep_even, t.n_sep_odd = len(_SEP1), len(_SEP2)
+        for i, v in enumerate(list(_PREFIX) + list(_SUFFIX) + list(RESPONSE_SEP) + list(_SEP1) + list(_SEP2)):
+            t.ids[i] = int(v)
+        self.template = t
+
+    def build(self, users: Sequence[int]):
+        torch, C = self._torch, self._C
+        ds = self.ds
+        begin = np.asarray([ds.hist_off[u] for u in users], dtype=np.int64)
+        hlen = np.asarray([ds.hist_off[u + 1] - ds.hist_off[u] for u in users], dtype=np.int32)
+        lens = [prompt_len(int(h)) for h in hlen]
+        off = np.zeros(len(users), dtype=np.int64)
+        off[1:] = np.cumsum(lens)[:-1]
+        meta = torch.from_numpy(np.concatenate([begin, off])).to(self.device, non_blocking=True)
+        hl = torch.from_numpy(hlen).to(self.device, non_blocking=True)
+        out = torch.empty(int(sum(lens)), dtype=torch.int32, device=self.device)
+        n = len(users)
+        from . import _lib
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.atspeed_build_prompts(self.item_tok.data_ptr(), self.hist_items.data_ptr(), meta[:n].data_ptr(),
+                                                      hl.data_ptr(), meta[n:].data_ptr(), n, C.byref(self.template), out.data_ptr(),
+                                                      C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out, lens
+
+
 def load_dataset(name: str, data_dir: str | None = None) -> RecDataset:
     z = np.load(os.path.join(data_dir or _DATA_DIR, f"{name}.npz"))
     codes = z["item_codes"]

@@ -79,9 +79,10 @@ def parse():
                          "lm_head plus 3 %% noise.  Independent random weights accept only the structurally forced last step; "
                          "this exercises real accepted steps at the target's shape (a random-init net needs most of its layers "
                          "to agree with itself: corr2 accepts nothing extra, measured)")
-    ap.add_argument("--check-users", type=int, default=0,
+    ap.add_argument("--check-users", type=int, default=3,
                     help="parity record at the benchmark shape: this many users also go through oracle/bssd_ref.py on the host "
-                         "with the GPU's own weights (bf16 contract); ranked lists + accepted lengths compared (slow: ~10 s/user)")
+                         "with the GPU's own weights (bf16 contract); ranked lists + accepted lengths compared (~10 s + 3.5 s/user on "
+                         "32 cores; N = 1 only; 0 = skip)")
     ap.add_argument("--constraint", default="strict", choices=["strict", "positional"])
     ap.add_argument("--profile-users", type=int, default=4)
     ap.add_argument("--lanes", type=int, default=3,
@@ -410,10 +411,15 @@ def atspeed_arm(a, rank, world, local_rank):
     lane_tok = [torch.zeros((U + n_lanes - 1) // n_lanes, a.K, _lib.MAX_NEW, dtype=torch.int32, device=dev) for _ in range(n_lanes)]
     lane_sc = [torch.zeros((U + n_lanes - 1) // n_lanes, a.K, dtype=torch.float32, device=dev) for _ in range(n_lanes)]
 
+    # device-resident pass: the inputs are the users' history item ids, resident in HBM; the prompts are built on the device
+    # (csrc/prompt.cu) inside the timed region
+    from atspeed_b200.prompts import DevicePromptBuilder
+    builder = DevicePromptBuilder(ds, dev)
+
     def step_device(s, trace=False):
         if a.cohort > 1:
             def fn(ss, l, idx):
-                cat, lens = cat_dev[(s, l)]
+                cat, lens = builder.build([step_users[s][i] for i in idx])
                 sts = ss.bssd_batch_device(cat, lens, a.gamma, lane_tok[l], lane_sc[l])
                 tok_dev[idx] = lane_tok[l][: len(idx)]
                 return sts
@@ -487,6 +493,7 @@ def atspeed_arm(a, rank, world, local_rank):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (13.5 GB of weights streamed per forward)",
+                       "inputs": "history item ids resident in HBM; prompts built on the device inside the timed region (cohort mode)",
                        "parallelism": f"user-sharded x{world}, one all-gather of ranked lists per step",
                        "gemm_pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "1") != "0"},
             "clocks": clocks.summary(), "gpu_launches": int(launches),

@@ -290,6 +290,25 @@ int atspeed_tree_attention(const void* q, const void* kcache, const void* vcache
                            const uint32_t* vis, int32_t vis_base, int32_t T, int32_t S, int32_t n_heads,
                            int32_t head_dim, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-side prompt builder (the step in front of the path; reference code/data.py:232-263 _process_test_data +
+ * code/collator.py:50-75 TestCollator, which tokenise "<template> item, item, ... <template> Response:" on the host).
+ * A prompt's token ids are a pure function of the user's history item ids: [BOS] prefix, then 4 code-token ids per item with
+ * the separator run between items (alternating between its one- and two-piece tokenisation), suffix, the "Response:" run.
+ *   ids = prefix | suffix | resp | sep_even | sep_odd  (concatenated, in this order)
+ * For user i the kernel reads hist_len[i] item ids at hist_items + hist_begin[i] and writes its prompt at
+ * prompts_dev + out_off[i] (the concatenated layout atspeed_bssd_batch_device consumes).  The prompt length is
+ * 1 + n_prefix + 4h + ceil((h-1)/2)*n_sep_even + floor((h-1)/2)*n_sep_odd + n_suffix + n_resp, computed by the caller.
+ * Asynchronous on `stream`. */
+#define ATSPEED_PROMPT_TEMPLATE_IDS 120
+typedef struct atspeed_prompt_template {
+    int32_t bos, n_prefix, n_suffix, n_resp, n_sep_even, n_sep_odd;
+    int32_t ids[ATSPEED_PROMPT_TEMPLATE_IDS];
+} atspeed_prompt_template;
+int atspeed_build_prompts(const int32_t* item_tok_dev, const int32_t* hist_items_dev, const int64_t* hist_begin_dev,
+                          const int32_t* hist_len_dev, const int64_t* out_off_dev, int32_t n_users,
+                          const atspeed_prompt_template* tmpl, int32_t* prompts_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,17 @@ class _Sampler(bench.ClockSampler):
         return self
 
 
+class _Builder:
+    def __init__(self, ds, dev):
+        self.ds = ds
+
+    def build(self, users):
+        ps = [self.ds.prompt_ids(u) for u in users]
+        return torch.tensor([t for p in ps for t in p], dtype=torch.int32), [len(p) for p in ps]
+
+
+import atspeed_b200.prompts as P  # noqa: E402
+P.DevicePromptBuilder = _Builder
 E.DeviceModel, E.DeviceTrie, E.Session = _Model, _Trie, _Session
 bench.gpu_weights = lambda spec, seed, dev: {}
 bench.ClockSampler = _Sampler

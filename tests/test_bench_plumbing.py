@@ -71,7 +71,8 @@ KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "
 def test_bench_control_flow_single_process():
     """bench.py's own sequencing (phases, JSON keys) with the CUDA session stubbed out: catches a broken bench line on CPU."""
     for extra in ([], ["--cohort", "1", "--lanes", "2"]):
-        r = subprocess.run([sys.executable, STUB, "--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--hf-baseline-users", "0"]
+        r = subprocess.run([sys.executable, STUB, "--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--hf-baseline-users", "0",
+                            "--check-users", "0"]
                            + extra, cwd=ROOT, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         line = json.loads(r.stdout.strip().splitlines()[-1])

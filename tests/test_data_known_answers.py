@@ -44,3 +44,15 @@ def test_token_layout_users_and_trie_shape(name):
     assert [len(pos[d]) for d in range(4)] == f["positional"] and list(pos[4]) == [2]
     for d, (lo, hi) in enumerate(f["ranges"]):
         assert min(pos[d]) >= lo and max(pos[d]) <= hi
+
+
+def test_prompt_length_closed_form_matches_the_tokenisation():
+    """The device-side prompt builder (csrc/prompt.cu) gets its prompt lengths from prompts.prompt_len: it must equal the
+    length of the host tokenisation for every test user of both datasets."""
+    import numpy as np
+    from atspeed_b200.prompts import load_dataset, prompt_len
+    for name in ("beauty", "games"):
+        ds = load_dataset(name)
+        hl = np.diff(ds.hist_off)
+        for u in range(0, ds.n_users, 7):
+            assert prompt_len(int(hl[u])) == len(ds.prompt_ids(u)), (name, u)
