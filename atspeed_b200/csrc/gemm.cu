@@ -54,10 +54,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const 
                                           unsigned unit) {
     mbar_wait_guarded(smem_u32(bar), parity, w.g, w.kernel, w.role, barrier, index, unit, w.u_begin, w.u_end, w.T);
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+// L2 eviction-priority hints of the TMA loads (the encoded createpolicy values CUTLASS uses, cute/arch/copy_sm90_desc.hpp).
+// A weight tile is read by exactly one CTA (pair) once per launch and a launch streams 100-270 MB of them through the 126 MB
+// L2: evict-first, or they push out what IS reused -- the activation tile every CTA re-reads for every k-block (evict-last)
+// and the fp32 partial sums the consumer kernel is about to read (ncu, session I: the row-wise consumers hit L2 for 0.1-10 %
+// of their reads and ran at 2-3 TB/s of DRAM bandwidth on data the GEMM had written microseconds earlier).
+static constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+static constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, uint64_t hint) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
 // ---- cta_group::2 (CTA pair) forms ----
@@ -71,10 +78,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // executed by both CTAs of the pair; the transaction bytes are credited to the LEADER's barrier (peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, uint64_t hint) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
 __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -176,6 +183,7 @@ struct GemmParams {
     SpinGuard guard;          // bound + diagnostic record of every mbarrier wait
     GemmTrace trace;          // optional per-CTA progress words (ATSPEED_GEMM_TRACE=1)
     FusedEpi epi;             // kind != EPI_SLICES: tiles are finished inside the kernel (kernels.h)
+    int l2_hints;             // TMA loads carry L2 eviction priorities (ATSPEED_GEMM_L2HINT=0: plain loads)
 };
 __device__ __forceinline__ void trace_put(const GemmTrace& t, int word, unsigned v) {
     if (t.buf != nullptr && blockIdx.x < TRACE_CTAS) {
@@ -530,6 +538,8 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             // the kernel's critical path, so they contain no integer division
             int tile = u_begin / KB, kb = u_begin - tile * KB, wid, m0;
             tile_of(tile, wid, m0);
+            const uint64_t hint_w = p.l2_hints ? L2_EVICT_FIRST : 0x1000000000000000ull;      // weights: streamed once
+            const uint64_t hint_x = p.l2_hints ? L2_EVICT_LAST : 0x1000000000000000ull;       // activations: re-read by all
             auto advance = [&]() {
                 if (++kb == KB) { kb = 0; ++tile; tile_of(tile, wid, m0); }
             };
@@ -540,16 +550,16 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 if (p.epi.kind == EPI_SILU_MUL) {
                     // interleaved tile: the gate rows and the up rows of the SAME features (two boxes of BM/2 rows)
                     const int rows = p.BM >> 1;
-                    tma_load_2d(&tmW0, &full_bar[s], a_dst, kb * BLOCK_K, tile * rows);
-                    tma_load_2d(&tmW1, &full_bar[s], a_dst + rows * BLOCK_K * 2, kb * BLOCK_K, tile * rows);
+                    tma_load_2d(&tmW0, &full_bar[s], a_dst, kb * BLOCK_K, tile * rows, hint_w);
+                    tma_load_2d(&tmW1, &full_bar[s], a_dst + rows * BLOCK_K * 2, kb * BLOCK_K, tile * rows, hint_w);
                 } else {
-                    tma_load_2d(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);      // BM = 256: the map's box is 256 rows
+                    tma_load_2d(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0, hint_w);      // BM = 256: the map's box is 256 rows
                 }
             };
             auto load_b = [&](int s, int kbb) {
                 uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
-                tma_load_2d(&tmX, &full_bar[s], b_dst, kbb * BLOCK_K, 0);
-                if (p.T_pad > 256) tma_load_2d(&tmX1, &full_bar[s], b_dst + 256 * BLOCK_K * 2, kbb * BLOCK_K, 256);
+                tma_load_2d(&tmX, &full_bar[s], b_dst, kbb * BLOCK_K, 0, hint_x);
+                if (p.T_pad > 256) tma_load_2d(&tmX1, &full_bar[s], b_dst + 256 * BLOCK_K * 2, kbb * BLOCK_K, 256, hint_x);
             };
             // The weights do not depend on the previous kernel: fill the ring with weight tiles first, then wait for
             // the producer of the activations (griddepcontrol.wait), then add the activation tiles.
@@ -790,6 +800,8 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
         if (lane == 0) {
             int tile = u_begin / KB, kb = u_begin - tile * KB, wid, m0;
             tile_of(tile, wid, m0);
+            const uint64_t hint_w = p.l2_hints ? L2_EVICT_FIRST : 0x1000000000000000ull;      // weights: streamed once
+            const uint64_t hint_x = p.l2_hints ? L2_EVICT_LAST : 0x1000000000000000ull;       // activations: re-read by all
             auto advance = [&]() {
                 if (++kb == KB) { kb = 0; ++tile; tile_of(tile, wid, m0); }
             };
@@ -800,17 +812,17 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                 if (p.epi.kind == EPI_SILU_MUL) {
                     // this CTA's 128 rows = the gate rows and the up rows of ITS 64 features of the pair's 128-feature tile
                     const int r0 = tile * 128 + static_cast<int>(rank) * 64;
-                    tma_load_2d_2sm(&tmW0, &full_bar[s], a_dst, kb * BLOCK_K, r0);
-                    tma_load_2d_2sm(&tmW1, &full_bar[s], a_dst + 64 * BLOCK_K * 2, kb * BLOCK_K, r0);
+                    tma_load_2d_2sm(&tmW0, &full_bar[s], a_dst, kb * BLOCK_K, r0, hint_w);
+                    tma_load_2d_2sm(&tmW1, &full_bar[s], a_dst + 64 * BLOCK_K * 2, kb * BLOCK_K, r0, hint_w);
                 } else {
-                    tma_load_2d_2sm(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0);
+                    tma_load_2d_2sm(tmW, &full_bar[s], a_dst, kb * BLOCK_K, m0, hint_w);
                 }
             };
             auto load_b = [&](int s, int kbb) {
                 uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
                 for (int i = 0; i < p.n_mma; ++i)            // tokens [i*N_mma + rank*N_mma/2, +N_mma/2): rows past T are zeros
                     tma_load_2d_2sm(&tmX, &full_bar[s], b_dst + i * b_mma_bytes, kbb * BLOCK_K,
-                                    i * p.N_mma + static_cast<int>(rank) * b_half_rows);
+                                    i * p.N_mma + static_cast<int>(rank) * b_half_rows, hint_x);
             };
             const int npre = n_units < p.stages ? n_units : p.stages;
             const int kb_first = kb;
@@ -1303,6 +1315,7 @@ static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl,
     p.b_box_bytes = (pl.T_pad > 256 ? pl.T_pad : xm.box0) * BLOCK_K * 2;
     p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
     p.guard = spin_guard();
+    { static const bool on = []() { const char* e = getenv("ATSPEED_GEMM_L2HINT"); return !(e && atoi(e) == 0); }(); p.l2_hints = on ? 1 : 0; }
     p.trace = pl.two_cta ? gemm_trace() : GemmTrace{nullptr, 0};
     const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
                                        : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;

@@ -17,6 +17,7 @@ except Exception as e:
     print(sys.argv[1], 'ERR', e)
 PY
 }
+timeout 300 python -m pytest tests/test_gpu_prompts.py -q > $O/prompt_tests_$TAG.log 2>&1; echo "prompt tests rc=$?"; tail -2 $O/prompt_tests_$TAG.log
 # ---- configs[4]: K x gamma sweep (N = 40; gamma = 4 == gamma = 3 for 4 new tokens, code/beamSD.py:504, kept to show it) ----
 : > $O/sweep_$TAG.jsonl
 for K in 1 5 10 20; do for G in 2 3 4; do
