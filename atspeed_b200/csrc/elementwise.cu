@@ -19,6 +19,21 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;
 }
 
+// sum of a column chunk's partial-sum slices 1..splits-1 added to `acc` IN SLICE ORDER (deterministic), with the loads of up
+// to four slices in flight at once: a `for (s...) acc += load(s)` loop issues one load per L2/HBM round trip, and these
+// kernels are latency-bound (one wave of CTAs, profiles/r02_ncu_rowwise_attention_cohort.txt)
+__device__ __forceinline__ void add_slices4(float4& acc, const float* __restrict__ base, long long split_stride, int splits) {
+    for (int s0 = 1; s0 < splits; s0 += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (s0 + k < splits) v[k] = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(s0 + k) * split_stride));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (s0 + k < splits) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+}
+
 __global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ tok, int hidden,
                                   int vocab, __nv_bfloat16* __restrict__ h) {
     pdl_launch_dependents();
@@ -126,11 +141,7 @@ residual_rmsnorm_vec_kernel(__nv_bfloat16* __restrict__ h, const float* __restri
         const int i = threadIdx.x + c * THREADS;
         if (i < nchunk) {
             float4 acc = __ldg(reinterpret_cast<const float4*>(prow) + i);
-            const int splits = sm.slices(4 * i);
-            for (int s = 1; s < splits; ++s) {
-                const float4 o = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride) + i);
-                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-            }
+            add_slices4(acc, prow + 4 * i, split_stride, sm.slices(4 * i));
             const uint2 hb = *reinterpret_cast<const uint2*>(hrow + 4 * i);
             const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hb.x);
             const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hb.y);
@@ -262,13 +273,7 @@ qkv_rope_append_vec_kernel(const float* __restrict__ part, SplitMap sm, long lon
 #pragma unroll
     for (int k = 0; k < 6; ++k) a[k] = __ldg(reinterpret_cast<const float4*>(prow + cols[k]));
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const int splits = sm.slices(cols[k]);
-        for (int s = 1; s < splits; ++s) {
-            const float4 o = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + cols[k]));
-            a[k].x += o.x; a[k].y += o.y; a[k].z += o.z; a[k].w += o.w;
-        }
-    }
+    for (int k = 0; k < 6; ++k) add_slices4(a[k], prow + cols[k], split_stride, sm.slices(cols[k]));
     const float4 cs = __ldg(reinterpret_cast<const float4*>(rope_cos + static_cast<long long>(p) * half + i));
     const float4 sn = __ldg(reinterpret_cast<const float4*>(rope_sin + static_cast<long long>(p) * half + i));
     auto rope = [](float x0, float x1, float c, float s_, float& o0, float& o1) {
@@ -341,15 +346,8 @@ silu_mul_vec_kernel(const float* __restrict__ part, SplitMap sm, long long split
     const float* prow = part + static_cast<long long>(t) * ldp;
     float4 g = __ldg(reinterpret_cast<const float4*>(prow + i));
     float4 u = __ldg(reinterpret_cast<const float4*>(prow + mlp + i));
-    const int sg = sm.slices(i), su = sm.slices(mlp + i);
-    for (int s = 1; s < sg; ++s) {
-        const float4 g2 = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + i));
-        g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
-    }
-    for (int s = 1; s < su; ++s) {
-        const float4 u2 = __ldg(reinterpret_cast<const float4*>(prow + s * split_stride + mlp + i));
-        u.x += u2.x; u.y += u2.y; u.z += u2.z; u.w += u2.w;
-    }
+    add_slices4(g, prow + i, split_stride, sm.slices(i));
+    add_slices4(u, prow + mlp + i, split_stride, sm.slices(mlp + i));
     auto f = [](float gg, float uu) {
         gg = bf16_round(gg); uu = bf16_round(uu);
         return bf16_round(gg / (1.0f + expf(-gg))) * uu;
