@@ -652,7 +652,15 @@ def hf_baseline(a, ds, fn, dev, users, weights=None, ours=None, sess=None):
                       num_hidden_layers=s["n_layers"], num_attention_heads=s["n_heads"], num_key_value_heads=s["n_heads"],
                       tie_word_embeddings=False, pad_token_id=0, bos_token_id=1, eos_token_id=2)
     with torch.device(dev):
-        m = LlamaForCausalLM(cfg).to(torch.bfloat16).eval()
+        m = LlamaForCausalLM(cfg)
+    # `.to(bfloat16)` would also round the rotary embedding's inv_freq buffer, which from_pretrained(dtype=bf16) keeps in fp32
+    # (positions x a bf16-rounded frequency are off by up to ~0.2 rad at position 100: measured as a 0.05 systematic logit
+    # offset against a true fp32 forward, tools/forward_accuracy.py): convert, then restore the buffer
+    inv_freq = m.model.rotary_emb.inv_freq.detach().clone().float()
+    m = m.to(torch.bfloat16).eval()
+    m.model.rotary_emb.inv_freq = inv_freq
+    if hasattr(m.model.rotary_emb, "original_inv_freq"):
+        m.model.rotary_emb.original_inv_freq = inv_freq
     same_weights = False
     if weights is not None:
         sd = {"model.embed_tokens.weight": weights["embed"], "model.norm.weight": weights["norm"], "lm_head.weight": weights["lm_head"]}
@@ -696,6 +704,7 @@ def hf_baseline(a, ds, fn, dev, users, weights=None, ours=None, sess=None):
     if cmp_rows:
         try:
             m = m.float()                                   # the same module and weights in fp32: the yardstick
+            m.model.rotary_emb.inv_freq = inv_freq
             lo, hi = ds.level_ranges()[0]
             acc = {"ours_vs_hf_bf16": [], "ours_vs_hf_fp32": [], "hf_bf16_vs_hf_fp32": [], "std": [], "ov_ours": [], "ov_hf": []}
             for prompt, mine, theirs in cmp_rows:
