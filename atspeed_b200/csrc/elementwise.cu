@@ -3,6 +3,8 @@
 // fixed-order reduction of the GEMM's split-K fp32 slices and the bf16 roundings of the numerical
 // contract documented in oracle/llama_ref.py (the places where an HF bf16 module rounds).
 // All are HBM/L2-bound streaming kernels: one CTA per token row, 128-bit accesses where aligned.
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -196,11 +198,12 @@ int residual_rmsnorm(__nv_bfloat16* h, const float* part, const SplitMap& sm, lo
         return ATS_OK;
     }
     ATS_CHECK_ARG(hidden * 4 <= 96 * 1024, "residual_rmsnorm: hidden=%d too large", hidden);
-    static bool attr_set = false;
-    if (!attr_set) {
-        ATS_CUDA(cudaFuncSetAttribute(residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    static std::once_flag once;          // sessions on several host threads (bench.py lanes) may arrive here together
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, []() {
+        attr_err = cudaFuncSetAttribute(residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    });
+    ATS_CUDA(attr_err);
     ATS_CUDA(launch_pdl(residual_rmsnorm_kernel, dim3(T), dim3(256), hidden * sizeof(float), st, h, part, sm, split_stride,
                         ldp, g, hidden, eps, x));
     return ATS_OK;

@@ -33,7 +33,8 @@ static constexpr int GEMM_THREADS = 192;
 static constexpr size_t EXCLUSIVE_SMEM_BYTES = 120 * 1024;   // > 227 KiB / 2: at most one GEMM CTA per SM
 static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 static constexpr int MAX_STAGES = 12;
-static constexpr int OUT_STAGE_BYTES = 2 * 16 * 128 * 4;   // epilogue staging: two [16 tokens][128 features] fp32 tiles
+static constexpr int OUT_STAGE_BUFS = 3;                     // epilogue staging ring: [16 tokens][128 features] fp32 tiles
+static constexpr int OUT_STAGE_BYTES = OUT_STAGE_BUFS * 16 * 128 * 4;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -119,6 +120,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* 
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, uint64_t hint) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -162,6 +169,56 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((BLOCK_M >> 4) << 24);
 }
 
+// Drain one segment's accumulators (this CTA's 128 TMEM lanes x `halves` x n_chunks x 16 columns) into its fp32 partial-sum
+// slice: TMEM -> registers -> [16 tokens][128 features] staging tile -> ONE bulk tensor store per 8 KB (a scalar-store
+// epilogue is LSU-issue bound: 40 % of the kernel at T = 512).  Called by the four epilogue warps (128 threads, named
+// barrier 1).  The epilogue of a T > 256 segment is exposed (one accumulator fills TMEM), so it is built to be short:
+//   * the tcgen05.ld of chunk i+1 is in flight while chunk i is staged (two register sets, ping-pong);
+//   * a ring of OUT_STAGE_BUFS = 3 staging tiles needs ONE barrier per chunk: before the barrier of chunk i the elected
+//     thread has seen the store of chunk i-2 finish reading its tile (wait_group.read 1), which is the tile chunk i+1 writes;
+//   * `release` (TMEM may be overwritten by the next segment's MMAs) runs as soon as the last tcgen05.ld has completed,
+//     before the last tile is staged and stored.
+template <typename ReleaseFn>
+__device__ __forceinline__ void drain_segment_tma(const CUtensorMap* tmO, uint32_t tb0, int halves, int n_chunks, uint32_t acc_stride,
+                                                  int m0, int slice, float* stage_out, int& ring, int f, bool elected,
+                                                  uint64_t store_hint, ReleaseFn release) {
+    const int total = halves * n_chunks;
+    auto taddr = [&](int idx) -> uint32_t {
+        const int half = idx >= n_chunks ? 1 : 0;
+        return tb0 + half * acc_stride + static_cast<uint32_t>((idx - half * n_chunks) << 4);
+    };
+    auto emit = [&](const uint32_t (&r)[16], int idx) {
+        float* stg = stage_out + ring * (16 * 128);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (elected) {
+            const int half = idx >= n_chunks ? 1 : 0;
+            const int c = (idx - half * n_chunks) << 4;
+            if (store_hint) tma_store_3d_hint(tmO, stg, m0 + half * BLOCK_M, c, slice, store_hint);   // clipped to [rows_i, T, slices]
+            else tma_store_3d(tmO, stg, m0 + half * BLOCK_M, c, slice);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ring = ring + 1 == OUT_STAGE_BUFS ? 0 : ring + 1;
+    };
+    uint32_t ra[16], rb[16];
+    tmem_ld16(taddr(0), ra);
+    for (int idx = 0; idx < total; idx += 2) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (idx + 1 < total) tmem_ld16(taddr(idx + 1), rb);
+        else release();
+        emit(ra, idx);
+        if (idx + 1 < total) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (idx + 2 < total) tmem_ld16(taddr(idx + 2), ra);
+            else release();
+            emit(rb, idx + 1);
+        }
+    }
+}
+
 struct GemmParams {
     float* out;
     long long slice_stride;   // elements between partial-sum slices
@@ -184,6 +241,7 @@ struct GemmParams {
     GemmTrace trace;          // optional per-CTA progress words (ATSPEED_GEMM_TRACE=1)
     FusedEpi epi;             // kind != EPI_SLICES: tiles are finished inside the kernel (kernels.h)
     int l2_hints;             // TMA loads carry L2 eviction priorities (ATSPEED_GEMM_L2HINT=0: plain loads)
+    uint64_t store_hint;      // L2 eviction priority of the epilogue's bulk stores (0: none; ATSPEED_GEMM_STORE_HINT)
 };
 __device__ __forceinline__ void trace_put(const GemmTrace& t, int word, unsigned v) {
     if (t.buf != nullptr && blockIdx.x < TRACE_CTAS) {
@@ -628,7 +686,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         // ===== epilogue: TMEM -> registers -> global fp32 partial-sum slice =====
         asm volatile("griddepcontrol.wait;" ::: "memory");    // `out` may still be read by the previous consumer
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);   // 2 x 8 KB
+        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);   // staging ring
         int st_chunk = 0;
         int seg = 0;
         if (p.epi.kind != EPI_SLICES) {
@@ -644,32 +702,15 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             mbar_wait(&accum_full[buf], use & 1, wc, HANG_B_ACCUM_FULL, buf, u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (p.tma_store) {
-                // TMEM -> registers -> [16 tokens][128 features] fp32 staging tile -> ONE bulk tensor store per 8 KB: the
-                // scalar-store epilogue below is LSU-issue bound (40 % of the kernel at T = 512, tools/gemm_sweep.py bigT)
                 const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
-                const bool elected = threadIdx.x == 64;                       // first epilogue thread
-                const int f = q * 32 + lane;                                  // feature within the 128-row half
-                for (int half = 0; half < (p.BM >> 7); ++half) {
-                    const uint32_t tbase = tmem_base + buf * p.buf_stride + half * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-                    for (int c = 0; c < p.T_pad; c += 16) {
-                        uint32_t r[16];
-                        tmem_ld16(tbase + static_cast<uint32_t>(c), r);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        float* stg = stage_out + (st_chunk & 1) * (16 * 128);
-                        // the store issued two chunks ago has finished reading this staging buffer
-                        if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (elected) {
-                            tma_store_3d(tmO, stg, m0 + half * BLOCK_M, c, slice);   // clipped to [rows_i, T, slices]
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        }
-                        ++st_chunk;
-                    }
-                }
+                const uint32_t tb0 = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
+                drain_segment_tma(tmO, tb0, p.BM >> 7, p.T_pad >> 4, static_cast<uint32_t>(p.acc_stride), m0, slice, stage_out, st_chunk,
+                                  q * 32 + lane, threadIdx.x == 64, p.store_hint, [&]() {
+                                      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                                      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
+                                  });
+                u = seg_end;
+                continue;
             } else
             for (int half = 0; half < (p.BM >> 7); ++half) {
                 const int row = m0 + half * BLOCK_M + q * 32 + lane;           // output feature
@@ -911,6 +952,14 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
             const uint32_t tbase = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
+            if (p.tma_store) {
+                drain_segment_tma(tmO, tbase, 1, (min(T64, p.T) + 15) >> 4, 0u, m0, slice, stage_out, st_chunk, f, elected, p.store_hint, [&]() {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], 0);     // the leader's MMA thread waits for all 8 warps
+                });
+                u = seg_end;
+                continue;
+            }
             const int row = m0 + f;
             const bool row_ok = row < p.n_rows[wid];
             float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
@@ -918,20 +967,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                 uint32_t r[16];
                 tmem_ld16(tbase + static_cast<uint32_t>(c), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (p.tma_store) {
-                    float* stg = stage_out + (st_chunk & 1) * (16 * 128);
-                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (elected) {
-                        tma_store_3d(tmO, stg, m0, c, slice);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    ++st_chunk;
-                } else if (row_ok) {
+                if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
@@ -1316,6 +1352,10 @@ static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl,
     p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
     p.guard = spin_guard();
     { static const bool on = []() { const char* e = getenv("ATSPEED_GEMM_L2HINT"); return !(e && atoi(e) == 0); }(); p.l2_hints = on ? 1 : 0; }
+    {   // partial sums are re-read by the consumer kernel microseconds later: 1 = evict-last, 2 = evict-first, 0 = no hint
+        static const int mode = []() { const char* e = getenv("ATSPEED_GEMM_STORE_HINT"); return e ? atoi(e) : 0; }();
+        p.store_hint = mode == 1 ? L2_EVICT_LAST : (mode == 2 ? L2_EVICT_FIRST : 0ull);
+    }
     p.trace = pl.two_cta ? gemm_trace() : GemmTrace{nullptr, 0};
     const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
                                        : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
