@@ -35,6 +35,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("ATSPEED_NVCC_DEFS", "").split()      # diagnostic builds, e.g. -DATT_TIMING
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

@@ -22,9 +22,18 @@
 
 namespace atspeed {
 
+// -DATT_TIMING (diagnostic builds only, tools/att_timing.py): thread 0 of CTA (0,0) leaves clock64 stamps at the phase boundaries
+#ifdef ATT_TIMING
+__device__ long long g_att_stamps[16];
+#define ATT_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_att_stamps[i] = clock64(); } while (0)
+#else
+#define ATT_STAMP(i) do { } while (0)
+#endif
+
 static constexpr int ATT_BQ = 64;   // queries per CTA
 static constexpr int ATT_BK = 64;   // keys per tile
 static constexpr int ATT_THREADS = 128;
+static constexpr int SPARSE_CAP = 16;   // visible tree / accepted slots folded per round of the sparse phase (a beam sees <= ~11)
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
@@ -41,6 +50,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     const uint32_t n = valid ? 16u : 0u;     // src-size 0: the 16 destination bytes are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+// the 128-byte line at gptr -> L2: no destination, nothing to wait for.  (cp.async.bulk.prefetch.L2 was tried for the same
+// purpose: hundreds of 256-byte requests per CTA queue in the TMA unit, +9 us per launch.)
+__device__ __forceinline__ void l2_prefetch_line(const void* gptr) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -78,9 +92,13 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     __shared__ int sPl[BQ];
     __shared__ int sMaxPl;
     __shared__ float sM[BQ], sL[BQ];
+    __shared__ unsigned short sKeys[BQ * SPARSE_CAP];
+    __shared__ int sCnt[BQ];
 
+    ATT_STAMP(0);
     pdl_launch_dependents();
     pdl_wait();
+    ATT_STAMP(1);
     const int head = blockIdx.y;
     int q0 = blockIdx.x * BQ;
     if (ckv.n > 0) {
@@ -103,27 +121,6 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     const int HD = n_heads * D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
 
-    if (threadIdx.x == 0) sMaxPl = 0;
-    __syncthreads();
-    // stage the Q tile with cp.async (group 0), prefix lengths and visibility words directly
-    for (int i = threadIdx.x; i < BQ * (D / 8); i += ATT_THREADS) {
-        const int r = i / (D / 8), c = (i % (D / 8)) * 8;
-        const bool ok = q0 + r < T;
-        cp_async16(&sQ[r * LDS + c], q + static_cast<long long>(ok ? q0 + r : 0) * HD + head * D + c, ok);
-    }
-    cp_async_commit();
-    for (int i = threadIdx.x; i < BQ; i += ATT_THREADS) {
-        const int pl = (q0 + i < T) ? min(prefix_len[q0 + i], S) : 0;
-        sPl[i] = pl;
-        atomicMax(&sMaxPl, pl);
-    }
-    for (int i = threadIdx.x; i < BQ * VIS_WORDS; i += ATT_THREADS) {
-        const int r = i / VIS_WORDS, w = i % VIS_WORDS;
-        sVis[i] = (q0 + r < T) ? vis[static_cast<long long>(q0 + r) * VIS_WORDS + w] : 0u;
-    }
-    __syncthreads();
-    const int n_tiles = (sMaxPl + ATT_BK - 1) / ATT_BK;      // dense phase: the keys some query sees through its prefix
-
     auto load_tile = [&](int buf, int key0) {
         __nv_bfloat16* sK = sKV + static_cast<size_t>(buf) * 2 * ATT_BK * LDS;
         __nv_bfloat16* sV = sK + ATT_BK * LDS;
@@ -136,6 +133,67 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
         }
     };
 
+    if (threadIdx.x == 0) sMaxPl = 0;
+    __syncthreads();
+    // stage the Q tile with cp.async (group 0) and -- without waiting to learn how many prompt tiles the block needs -- the
+    // first K/V tile (group 1): the prefix lengths and visibility words below are a second global round trip that the first
+    // tile would otherwise queue behind (a CTA has 4 warps: every exposed round trip is ~1 us of its ~10 us life)
+    for (int i = threadIdx.x; i < BQ * (D / 8); i += ATT_THREADS) {
+        const int r = i / (D / 8), c = (i % (D / 8)) * 8;
+        const bool ok = q0 + r < T;
+        cp_async16(&sQ[r * LDS + c], q + static_cast<long long>(ok ? q0 + r : 0) * HD + head * D + c, ok);
+    }
+    cp_async_commit();
+    load_tile(0, 0);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < BQ; i += ATT_THREADS) {
+        const int pl = (q0 + i < T) ? min(prefix_len[q0 + i], S) : 0;
+        sPl[i] = pl;
+        atomicMax(&sMaxPl, pl);
+    }
+    for (int i = threadIdx.x; i < BQ * VIS_WORDS; i += ATT_THREADS) {
+        const int r = i / VIS_WORDS, w = i % VIS_WORDS;
+        sVis[i] = (q0 + r < T) ? vis[static_cast<long long>(q0 + r) * VIS_WORDS + w] : 0u;
+    }
+    __syncthreads();
+    const int n_tiles = (sMaxPl + ATT_BK - 1) / ATT_BK;      // dense phase: the keys some query sees through its prefix
+    ATT_STAMP(2);
+
+    // Sparse-phase key lists, built BEFORE the dense phase so that the rows can be requested from HBM now (prefetch.global.L2,
+    // fire and forget): lane l < 16 of warp w compacts the visibility words of row 16 w + l into up to SPARSE_CAP slot
+    // numbers, ascending (the order the keys are folded in).  The cursor stays in the lane's registers for further rounds.
+    const int lrow = warp * 16 + (lane & 15);
+    int vw = 0, my_cnt = 0;
+    uint32_t vbits = 0u;
+    auto fill_keys = [&]() {                                         // lanes < 16 only
+        const int spl = sPl[lrow];
+        int n = 0;
+        while (n < SPARSE_CAP) {
+            while (vbits == 0u && ++vw < VIS_WORDS) vbits = sVis[lrow * VIS_WORDS + vw];
+            if (vbits == 0u) break;
+            const int b = __ffs(vbits) - 1;
+            vbits &= vbits - 1;
+            const int key = vis_base + vw * 32 + b;
+            if (key >= S || key < spl) continue;                     // out of this forward's extent / already seen through the prefix
+            sKeys[lrow * SPARSE_CAP + n++] = static_cast<unsigned short>(key);
+        }
+        sCnt[lrow] = n;
+        my_cnt = n;
+    };
+    if (lane < 16) {
+        vbits = sVis[lrow * VIS_WORDS];                              // rows >= T hold zeros: empty list
+        fill_keys();
+        for (int i = 0; i < my_cnt; ++i) {
+            const long long off = static_cast<long long>(sKeys[lrow * SPARSE_CAP + i]) * HD + head * D;
+#pragma unroll
+            for (int b = 0; b < D * 2; b += 128) {
+                l2_prefetch_line(reinterpret_cast<const char*>(kcache + off) + b);
+                l2_prefetch_line(reinterpret_cast<const char*>(vcache + off) + b);
+            }
+        }
+    }
+    __syncwarp();
+
     const int r0 = warp * 16 + g, r1 = r0 + 8;         // the two query rows this thread owns in the dense phase
     const int pl0 = sPl[r0], pl1 = sPl[r1];
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
@@ -143,14 +201,14 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 
-    if (n_tiles > 0) load_tile(0, 0);
-    cp_async_commit();
     // ldmatrix lane addressing (see the fragment layouts of mma.m16n8k16):
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;        // A operand (Q), 16x16 tiles
     const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;        // B operand (K), 2 n-blocks x 16 k
     const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_col = (lane >> 4) * 8;        // B operand (V, transposed)
 
+    ATT_STAMP(3);
     for (int it = 0; it < n_tiles; ++it) {
+        if (it < 4) ATT_STAMP(4 + it);
         const int key0 = it * ATT_BK;
         const int buf = it & 1;
         if (it + 1 < n_tiles) load_tile(buf ^ 1, key0 + ATT_BK);      // overlaps this tile's math
@@ -243,6 +301,7 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
         }
         __syncthreads();   // this buffer is refilled by the next iteration's prefetch
     }
+    ATT_STAMP(8);
     cp_async_wait<0>();
     __syncthreads();       // Q has landed for everybody (n_tiles == 0) and the K/V ring is free: it now carries the row states
     float* sO = reinterpret_cast<float*>(sKV);
@@ -255,80 +314,132 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     if (t4 == 0) { sM[r0] = m0; sL[r0] = l0; sM[r1] = m1; sL[r1] = l1; }
     __syncthreads();
 
-    // ---- sparse phase: two threads per query row, each DH dimensions ----
-    const int row = threadIdx.x >> 1, part = threadIdx.x & 1;
-    const int tq = q0 + row;
-    if (tq >= T) return;
-    const unsigned pair_mask = 3u << (lane & ~1);
-    const int pl = sPl[row];
-    float m = sM[row], l = sL[row];
-    float acc[DH], qf[DH];
+    ATT_STAMP(9);
+    // ---- sparse phase ----
+    // A warp owns the 16 rows it owned in the dense phase and folds their key lists LPR lanes per row, RPP = 32 / LPR rows at a
+    // time: lane j of a row holds the 16-byte chunks j, j + LPR, ... of the head dimension, so one load instruction of the
+    // warp reads LPR * 16 contiguous bytes per row (the first version gave each thread half a row: every 16-byte load of a warp
+    // touched 32 different lines and the phase was bound by L1 wavefronts, 2.2 us per key).  K and V rows are loaded two keys
+    // ahead (three register sets) -- they sit in L2 by now (prefetched above), ~700 cycles away.
+    constexpr int LPR = D >= 32 ? 4 : 2;
+    constexpr int RPP = 32 / LPR;
+    constexpr int NCH = D / (8 * LPR);                               // chunks (8 dimensions) per lane
+    const int sub = lane % LPR, rsel = lane / LPR;
+    const unsigned row_mask = ((1u << LPR) - 1u) << (lane - sub);
+    struct KVRegs { uint4 k[NCH], v[NCH]; };
+    for (;;) {
+        // rounds of up to SPARSE_CAP keys per row (one round unless a row sees more): is this the last one?
+        const bool last = !__any_sync(0xffffffffu, lane < 16 && my_cnt == SPARSE_CAP);
+#pragma unroll 1
+        for (int pass = 0; pass < 16 / RPP; ++pass) {
+            const int row = warp * 16 + pass * RPP + rsel;
+            const int tq = q0 + row;
+            const int n = sCnt[row];
+            const unsigned short* keys = sKeys + row * SPARSE_CAP;
+            float m = sM[row], l = sL[row];
+            float acc[NCH][8];
+            uint4 qp[NCH];                                          // this lane's query dimensions, packed bf16
 #pragma unroll
-    for (int i = 0; i < DH; ++i) {
-        acc[i] = sO[row * LDO + part * DH + i];
-        qf[i] = __bfloat162float(sQ[row * LDS + part * DH + i]);
-    }
-    const long long col0 = static_cast<long long>(head) * D + part * DH;
-    for (int w = 0; w < VIS_WORDS; ++w) {
-        uint32_t bits = sVis[row * VIS_WORDS + w];
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int key = vis_base + w * 32 + b;
-            if (key >= S || key < pl) continue;               // out of this forward's extent / already seen through the prefix
-            const uint4* kp = reinterpret_cast<const uint4*>(kcache + static_cast<long long>(key) * HD + col0);
-            const uint4* vp = reinterpret_cast<const uint4*>(vcache + static_cast<long long>(key) * HD + col0);
-            uint4 kr[DH / 8], vr[DH / 8];
-#pragma unroll
-            for (int i = 0; i < DH / 8; ++i) kr[i] = __ldg(kp + i);
-#pragma unroll
-            for (int i = 0; i < DH / 8; ++i) vr[i] = __ldg(vp + i);
-            float dot = 0.f;
-#pragma unroll
-            for (int i = 0; i < DH / 8; ++i) {
-                const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[i]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 kf = __bfloat1622float2(k2[j]);
-                    dot += qf[i * 8 + 2 * j] * kf.x + qf[i * 8 + 2 * j + 1] * kf.y;
-                }
+            for (int c = 0; c < NCH; ++c) {
+                const int d0 = 8 * (sub + LPR * c);
+                const float4 a0 = *reinterpret_cast<const float4*>(sO + row * LDO + d0), a1 = *reinterpret_cast<const float4*>(sO + row * LDO + d0 + 4);
+                acc[c][0] = a0.x; acc[c][1] = a0.y; acc[c][2] = a0.z; acc[c][3] = a0.w;
+                acc[c][4] = a1.x; acc[c][5] = a1.y; acc[c][6] = a1.z; acc[c][7] = a1.w;
+                qp[c] = *reinterpret_cast<const uint4*>(sQ + row * LDS + d0);
             }
-            dot += __shfl_xor_sync(pair_mask, dot, 1);
-            const float sc = dot * scale;
-            const float mn = fmaxf(m, sc);
-            const float corr = m == -INFINITY ? 0.f : expf(m - mn);
-            const float pw = expf(sc - mn);
-            l = l * corr + pw;
-            m = mn;
+            auto load_kv = [&](int key, KVRegs& r) {
+                const long long off = static_cast<long long>(key) * HD + head * D + 8 * sub;
 #pragma unroll
-            for (int i = 0; i < DH / 8; ++i) {
-                const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[i]);
+                for (int c = 0; c < NCH; ++c) r.k[c] = __ldg(reinterpret_cast<const uint4*>(kcache + off + 8 * LPR * c));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 vf = __bfloat1622float2(v2[j]);
-                    acc[i * 8 + 2 * j] = acc[i * 8 + 2 * j] * corr + pw * vf.x;
-                    acc[i * 8 + 2 * j + 1] = acc[i * 8 + 2 * j + 1] * corr + pw * vf.y;
+                for (int c = 0; c < NCH; ++c) r.v[c] = __ldg(reinterpret_cast<const uint4*>(vcache + off + 8 * LPR * c));
+            };
+            auto fold = [&](const KVRegs& r) {
+                float dot = 0.f;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&r.k[c]);
+                    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qp[c]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 kf = __bfloat1622float2(k2[j]), qf = __bfloat1622float2(q2[j]);
+                        dot += qf.x * kf.x + qf.y * kf.y;
+                    }
                 }
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(row_mask, dot, o);
+                const float sc = dot * scale;
+                const float mn = fmaxf(m, sc);
+                const float corr = m == -INFINITY ? 0.f : expf(m - mn);
+                const float pw = expf(sc - mn);
+                l = l * corr + pw;
+                m = mn;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&r.v[c]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 vf = __bfloat1622float2(v2[j]);
+                        acc[c][2 * j] = acc[c][2 * j] * corr + pw * vf.x;
+                        acc[c][2 * j + 1] = acc[c][2 * j + 1] * corr + pw * vf.y;
+                    }
+                }
+            };
+            ATT_STAMP(10);
+            KVRegs r0, r1, r2;
+            if (n > 0) load_kv(keys[0], r0);
+            if (n > 1) load_kv(keys[1], r1);
+            for (int i = 0; i < n; i += 3) {
+                if (i + 2 < n) load_kv(keys[i + 2], r2);
+                fold(r0);
+                if (i + 3 < n) load_kv(keys[i + 3], r0);
+                if (i + 1 < n) fold(r1);
+                if (i + 4 < n) load_kv(keys[i + 4], r1);
+                if (i + 2 < n) fold(r2);
+            }
+            if (last) {
+                // ---- normalise and store (bf16) ----
+                if (tq < T) {
+                    const float inv = l > 0.f ? 1.0f / l : 0.f;
+                    __nv_bfloat16* dst = out + static_cast<long long>(tq) * HD + head * D;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        uint4 pk;
+                        pk.x = pack_bf16(acc[c][0] * inv, acc[c][1] * inv);
+                        pk.y = pack_bf16(acc[c][2] * inv, acc[c][3] * inv);
+                        pk.z = pack_bf16(acc[c][4] * inv, acc[c][5] * inv);
+                        pk.w = pack_bf16(acc[c][6] * inv, acc[c][7] * inv);
+                        *reinterpret_cast<uint4*>(dst + 8 * (sub + LPR * c)) = pk;
+                    }
+                }
+            } else {
+                // more keys to come: the row state goes back to shared memory for the next round
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int d0 = 8 * (sub + LPR * c);
+                    *reinterpret_cast<float4*>(sO + row * LDO + d0) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                    *reinterpret_cast<float4*>(sO + row * LDO + d0 + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+                }
+                if (sub == 0) { sM[row] = m; sL[row] = l; }
             }
         }
+        if (last) break;
+        __syncwarp();
+        if (lane < 16) fill_keys();
+        __syncwarp();
     }
-    // ---- normalise and store (bf16) ----
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
-    __nv_bfloat16* dst = out + static_cast<long long>(tq) * HD + col0;
-#pragma unroll
-    for (int i = 0; i < DH / 8; ++i) {
-        uint4 pk;
-        pk.x = pack_bf16(acc[i * 8 + 0] * inv, acc[i * 8 + 1] * inv);
-        pk.y = pack_bf16(acc[i * 8 + 2] * inv, acc[i * 8 + 3] * inv);
-        pk.z = pack_bf16(acc[i * 8 + 4] * inv, acc[i * 8 + 5] * inv);
-        pk.w = pack_bf16(acc[i * 8 + 6] * inv, acc[i * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + i * 8) = pk;
-    }
+    ATT_STAMP(11);
 }
+
+#ifdef ATT_TIMING
+extern "C" int atspeed_debug_att_stamps(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_att_stamps, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int tree_attention(const __nv_bfloat16* q, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                    const BatchDesc& b, int T, int S, int n_heads, int head_dim, __nv_bfloat16* out, cudaStream_t st) {
-    ATS_CHECK_ARG(T >= 1 && S >= 1, "attention: T=%d S=%d", T, S);
+    ATS_CHECK_ARG(T >= 1 && S >= 1 && S < 65536, "attention: T=%d S=%d", T, S);
     int q_blocks = (T + ATT_BQ - 1) / ATT_BQ;
     if (b.ckv.n > 0) {
         q_blocks = 0;
