@@ -46,6 +46,7 @@ SYMBOLS = {
     "atspeed_last_error": (C.c_char_p, []),
     "atspeed_abi_version": (C.c_int, []),
     "atspeed_debug_gemm_trace": (C.c_int, [C.POINTER(C.c_uint32), C.c_int32]),
+    "atspeed_debug_rowwise_us": (C.c_int, [C.c_int32] * 7 + [c_f32p, C.c_void_p]),
     "atspeed_session_workspace_bytes": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(ModelDesc), C.POINTER(Config),
                                                   C.POINTER(C.c_size_t)]),
     "atspeed_session_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(ModelDesc), C.POINTER(Config),

@@ -84,7 +84,6 @@ tree_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     constexpr int BQ = ATT_BQ;
     constexpr int LDS = D + 8;                     // padded row (bf16 elements): conflict-free ldmatrix, rows 16-byte aligned
     constexpr int LDO = D + 4;                     // padded fp32 row of the state hand-off
-    constexpr int DH = D / 2;                      // dimensions per thread in the sparse phase
     extern __shared__ __align__(16) uint8_t att_smem[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
     __nv_bfloat16* sKV = sQ + BQ * LDS;        // [2 buffers][K | V][ATT_BK][LDS]; afterwards: fp32 [BQ][LDO] output state

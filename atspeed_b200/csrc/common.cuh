@@ -85,7 +85,7 @@ struct HangDiag {
     unsigned int T;
     unsigned long long waited_ns;
 };
-enum : unsigned { HANG_K_GEMM = 1, HANG_K_GEMM_PAIR = 2, HANG_K_KVGATHER = 3 };
+enum : unsigned { HANG_K_GEMM = 1, HANG_K_GEMM_PAIR = 2, HANG_K_KVGATHER = 3, HANG_K_ROWWISE = 4 };
 enum : unsigned { HANG_R_PRODUCER = 1, HANG_R_MMA = 2, HANG_R_EPILOGUE = 3, HANG_R_COPY = 4 };
 enum : unsigned { HANG_B_EMPTY = 1, HANG_B_FULL = 2, HANG_B_ACCUM_FULL = 3, HANG_B_ACCUM_EMPTY = 4, HANG_B_ROW = 5, HANG_B_FLAG = 6 };
 struct SpinGuard {            // passed by value to the kernels that wait on mbarriers
@@ -180,6 +180,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// bf16(silu(g)) * u with g, u rounded to bf16 first: the rounding points of an HF bf16 LlamaMLP.  silu runs in fp32 on the SFU
+// (ex2.approx, rcp.approx: relative error < 1e-6, three orders of magnitude below the bf16 rounding that follows).  The IEEE
+// division + expf this replaces cost ~135 SASS instructions per element and made silu_mul issue-bound (20 us of issue slots at
+// T = 480 against 16 us of HBM time, tools/rowwise_bench.py).
+__device__ __forceinline__ float silu_mul_bf16(float g, float u) {
+    g = bf16_round(g); u = bf16_round(u);
+    return bf16_round(__fdividef(g, 1.0f + __expf(-g))) * u;
+}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -3,7 +3,10 @@
 // fixed-order reduction of the GEMM's split-K fp32 slices and the bf16 roundings of the numerical
 // contract documented in oracle/llama_ref.py (the places where an HF bf16 module rounds).
 // All are HBM/L2-bound streaming kernels: one CTA per token row, 128-bit accesses where aligned.
+#include <stdlib.h>
+
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -33,6 +36,35 @@ __device__ __forceinline__ void add_slices4(float4& acc, const float* __restrict
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (s0 + k < splits) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+}
+
+// a[k] = sum over the ns[k] partial-sum slices of the 4 columns at base[k], IN SLICE ORDER (deterministic, the order every
+// consumer has always used), for N column groups at once: the loads of slice s of ALL groups are issued before any of them is
+// used, slices 0 and 1 together.  Per-group loops (add_slices4 once per group) made a thread wait for one HBM round trip per
+// group and slice -- 6 in a row in qkv_rope_append, which ran at 2.4 TB/s with every byte it needed addressable up front.
+template <int N>
+__device__ __forceinline__ void sum_slices(float4 (&a)[N], const float* const (&base)[N], const int (&ns)[N], long long split_stride) {
+    float4 b[N];
+    int smax = 1;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (ns[k] > 0) a[k] = __ldg(reinterpret_cast<const float4*>(base[k]));
+        smax = ns[k] > smax ? ns[k] : smax;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        if (ns[k] > 1) b[k] = __ldg(reinterpret_cast<const float4*>(base[k] + split_stride));
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        if (ns[k] > 1) { a[k].x += b[k].x; a[k].y += b[k].y; a[k].z += b[k].z; a[k].w += b[k].w; }
+    for (int s2 = 2; s2 < smax; ++s2) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (s2 < ns[k]) b[k] = __ldg(reinterpret_cast<const float4*>(base[k] + static_cast<long long>(s2) * split_stride));
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (s2 < ns[k]) { a[k].x += b[k].x; a[k].y += b[k].y; a[k].z += b[k].z; a[k].w += b[k].w; }
     }
 }
 
@@ -138,12 +170,21 @@ residual_rmsnorm_vec_kernel(__nv_bfloat16* __restrict__ h, const float* __restri
     const int nchunk = hidden >> 2;
     float4 v[CH];
     float ss = 0.f;
+    float4 accs[CH];
+    const float* bases[CH];
+    int ns[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int i = threadIdx.x + c * THREADS;
+        bases[c] = prow + 4 * (i < nchunk ? i : 0);
+        ns[c] = i < nchunk ? sm.slices(4 * i) : 0;
+    }
+    sum_slices<CH>(accs, bases, ns, split_stride);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
         const int i = threadIdx.x + c * THREADS;
         if (i < nchunk) {
-            float4 acc = __ldg(reinterpret_cast<const float4*>(prow) + i);
-            add_slices4(acc, prow + 4 * i, split_stride, sm.slices(4 * i));
+            const float4 acc = accs[c];
             const uint2 hb = *reinterpret_cast<const uint2*>(hrow + 4 * i);
             const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hb.x);
             const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hb.y);
@@ -273,10 +314,11 @@ qkv_rope_append_vec_kernel(const float* __restrict__ part, SplitMap sm, long lon
     const int c0 = hd * head_dim + i, c1 = c0 + half;
     float4 a[6];
     const int cols[6] = {c0, c1, HD + c0, HD + c1, 2 * HD + c0, 2 * HD + c1};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) a[k] = __ldg(reinterpret_cast<const float4*>(prow + cols[k]));
-#pragma unroll
-    for (int k = 0; k < 6; ++k) add_slices4(a[k], prow + cols[k], split_stride, sm.slices(cols[k]));
+    const float* const bases[6] = {prow + cols[0], prow + cols[1], prow + cols[2], prow + cols[3], prow + cols[4], prow + cols[5]};
+    // c0 and c1 = c0 + head_dim / 2 lie in the same head, hence (heads never straddle a GEMM tile) in the same tile
+    const int nq = sm.slices(cols[0]), nk = sm.slices(cols[2]), nv = sm.slices(cols[4]);
+    const int ns[6] = {nq, nq, nk, nk, nv, nv};
+    sum_slices<6>(a, bases, ns, split_stride);
     const float4 cs = __ldg(reinterpret_cast<const float4*>(rope_cos + static_cast<long long>(p) * half + i));
     const float4 sn = __ldg(reinterpret_cast<const float4*>(rope_sin + static_cast<long long>(p) * half + i));
     auto rope = [](float x0, float x1, float c, float s_, float& o0, float& o1) {
@@ -332,40 +374,59 @@ __global__ void silu_mul_kernel(const float* __restrict__ part, SplitMap sm, lon
         const int sg = sm.slices(i), su = sm.slices(mlp + i);
         for (int s = 1; s < sg; ++s) g += prow[s * split_stride + i];
         for (int s = 1; s < su; ++s) u += prow[s * split_stride + mlp + i];
-        g = bf16_round(g); u = bf16_round(u);
-        const float a = bf16_round(g / (1.0f + expf(-g)));
-        dst[i] = __float2bfloat16_rn(a * u);
+        dst[i] = __float2bfloat16_rn(silu_mul_bf16(g, u));
     }
 }
 
-__global__ void __launch_bounds__(256)
-silu_mul_vec_kernel(const float* __restrict__ part, SplitMap sm, long long split_stride, int ldp, int mlp,
+// One thread = 4 consecutive columns of NR consecutive token rows (same columns: the slice count and the column arithmetic are
+// computed once).  All 2 * NR * min(slices, 2) 16-byte loads of a thread are issued before the first is used: with one row per
+// thread the kernel kept ~50 KB in flight per SM and streamed 2.2 TB/s (tools/rowwise_bench.py); HBM at full rate needs ~100 KB.
+template <int NR>
+__global__ void __launch_bounds__(256, NR == 4 ? 2 : (NR == 2 ? 3 : 4))
+silu_mul_vec_kernel(const float* __restrict__ part, SplitMap sm, long long split_stride, int ldp, int T, int mlp,
                     __nv_bfloat16* __restrict__ m) {
     pdl_launch_dependents();
     pdl_wait();
-    const int t = blockIdx.x;
+    const int t0 = blockIdx.x * NR;
     const int i = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
     if (i >= mlp) return;
-    const float* prow = part + static_cast<long long>(t) * ldp;
-    float4 g = __ldg(reinterpret_cast<const float4*>(prow + i));
-    float4 u = __ldg(reinterpret_cast<const float4*>(prow + mlp + i));
-    add_slices4(g, prow + i, split_stride, sm.slices(i));
-    add_slices4(u, prow + mlp + i, split_stride, sm.slices(mlp + i));
-    auto f = [](float gg, float uu) {
-        gg = bf16_round(gg); uu = bf16_round(uu);
-        return bf16_round(gg / (1.0f + expf(-gg))) * uu;
-    };
-    __nv_bfloat162 lo = __floats2bfloat162_rn(f(g.x, u.x), f(g.y, u.y)), hi = __floats2bfloat162_rn(f(g.z, u.z), f(g.w, u.w));
-    uint2 r;
-    r.x = *reinterpret_cast<uint32_t*>(&lo); r.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(m + static_cast<long long>(t) * mlp + i) = r;
+    const int sg = sm.slices(i), su = sm.slices(mlp + i);
+    const float* p0 = part + static_cast<long long>(t0) * ldp + i;
+    float4 gu[2 * NR];                        // gu[2r] = gate, gu[2r + 1] = up of row t0 + r
+    const float* bases[2 * NR];
+    int ns[2 * NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const bool ok = t0 + r < T;
+        bases[2 * r] = p0 + static_cast<long long>(ok ? r : 0) * ldp;
+        bases[2 * r + 1] = bases[2 * r] + mlp;
+        ns[2 * r] = ok ? sg : 0;
+        ns[2 * r + 1] = ok ? su : 0;
+    }
+    sum_slices<2 * NR>(gu, bases, ns, split_stride);
+    auto f = [](float gg, float uu) { return silu_mul_bf16(gg, uu); };
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        if (t0 + r >= T) break;
+        const float4 g = gu[2 * r], u = gu[2 * r + 1];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(f(g.x, u.x), f(g.y, u.y)), hi = __floats2bfloat162_rn(f(g.z, u.z), f(g.w, u.w));
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(m + static_cast<long long>(t0 + r) * mlp + i) = o;
+    }
 }
 
 int silu_mul(const float* part, const SplitMap& sm, long long split_stride, int ldp, int T, int mlp, __nv_bfloat16* m,
              cudaStream_t st) {
     if ((mlp & 3) == 0 && (ldp & 3) == 0 && (split_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0) {
-        dim3 grid(T, (mlp / 4 + 255) / 256);
-        ATS_CUDA(launch_pdl(silu_mul_vec_kernel, grid, dim3(256), 0, st, part, sm, split_stride, ldp, mlp, m));
+        static const int nr = []() { const char* e = getenv("ATSPEED_SILU_NR"); return e ? atoi(e) : 2; }();
+        const int gy = (mlp / 4 + 255) / 256;
+        if (nr >= 4)
+            ATS_CUDA(launch_pdl(silu_mul_vec_kernel<4>, dim3((T + 3) / 4, gy), dim3(256), 0, st, part, sm, split_stride, ldp, T, mlp, m));
+        else if (nr >= 2)
+            ATS_CUDA(launch_pdl(silu_mul_vec_kernel<2>, dim3((T + 1) / 2, gy), dim3(256), 0, st, part, sm, split_stride, ldp, T, mlp, m));
+        else
+            ATS_CUDA(launch_pdl(silu_mul_vec_kernel<1>, dim3(T, gy), dim3(256), 0, st, part, sm, split_stride, ldp, T, mlp, m));
         return ATS_OK;
     }
     ATS_CUDA(launch_pdl(silu_mul_kernel, dim3(T), dim3(256), 0, st, part, sm, split_stride, ldp, mlp, m));
@@ -391,3 +452,69 @@ int reduce_slices(const float* part, const SplitMap& sm, long long split_stride,
 }
 
 }  // namespace atspeed
+
+// Diagnostics (tools/rowwise_bench.py): microseconds per launch of one row-wise consumer kernel at a cohort-forward size, every
+// column held in `slices` partial-sum slices, inputs cycled through buffers larger than L2 so each launch reads HBM.
+// kind 0: qkv_rope_append, 1: silu_mul, 2: residual_rmsnorm.
+extern "C" int atspeed_debug_rowwise_us(int32_t kind, int32_t T, int32_t hidden, int32_t mlp, int32_t n_heads, int32_t slices,
+                                        int32_t iters, float* us_out, void* stream) {
+    using namespace atspeed;
+    ATS_CHECK_ARG(kind >= 0 && kind <= 2 && T >= 1 && slices >= 1 && iters >= 1 && us_out && n_heads >= 1 && hidden % n_heads == 0,
+                  "rowwise bench: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int head_dim = hidden / n_heads;
+    const int cols = kind == 0 ? 3 * hidden : (kind == 1 ? 2 * mlp : hidden);
+    const long long stride = static_cast<long long>(T) * cols;
+    const size_t part_bytes = sizeof(float) * stride * slices;
+    const int nbuf = static_cast<int>((300ull << 20) / part_bytes) + 2;
+    SplitMap sm;
+    memset(&sm, 0, sizeof(sm));
+    sm.n = 1; sm.colbase[0] = 0; sm.colbase[1] = sm.colbase[2] = 0x7fffffff; sm.BM = 256; sm.U = 8; sm.KB = 8 * slices; sm.tps = 1;
+    sm.bm_shift = 8; sm.tab_n = (cols + 255) / 256 <= SPLIT_TAB ? (cols + 255) / 256 : 0;
+    for (int t = 0; t < sm.tab_n; ++t) sm.tab[t] = static_cast<unsigned char>(slices);
+    float* part = nullptr; __nv_bfloat16 *h = nullptr, *x = nullptr, *g = nullptr, *q = nullptr, *kv = nullptr, *mm = nullptr;
+    float* rope = nullptr; int* meta = nullptr;
+    const int max_pos = 1024, S = T + 8;
+    ATS_CUDA(cudaMalloc(&part, part_bytes * nbuf));
+    ATS_CUDA(cudaMemsetAsync(part, 0, part_bytes * nbuf, st));
+    ATS_CUDA(cudaMalloc(&h, sizeof(__nv_bfloat16) * T * hidden * 2));
+    x = h + static_cast<long long>(T) * hidden;
+    ATS_CUDA(cudaMalloc(&g, sizeof(__nv_bfloat16) * hidden));
+    ATS_CUDA(cudaMalloc(&q, sizeof(__nv_bfloat16) * T * hidden));
+    ATS_CUDA(cudaMalloc(&kv, sizeof(__nv_bfloat16) * 2 * S * hidden));
+    ATS_CUDA(cudaMalloc(&mm, sizeof(__nv_bfloat16) * T * (mlp > 0 ? mlp : 1)));
+    ATS_CUDA(cudaMalloc(&rope, sizeof(float) * 2 * max_pos * (head_dim / 2)));
+    ATS_CUDA(cudaMalloc(&meta, sizeof(int) * 2 * T));
+    ATS_CUDA(cudaMemsetAsync(h, 0, sizeof(__nv_bfloat16) * T * hidden * 2, st));
+    ATS_CUDA(cudaMemsetAsync(g, 0, sizeof(__nv_bfloat16) * hidden, st));
+    ATS_CUDA(cudaMemsetAsync(rope, 0, sizeof(float) * 2 * max_pos * (head_dim / 2), st));
+    std::vector<int> hm(2 * T);
+    for (int t = 0; t < T; ++t) { hm[t] = t % max_pos; hm[T + t] = t; }
+    ATS_CUDA(cudaMemcpyAsync(meta, hm.data(), sizeof(int) * 2 * T, cudaMemcpyHostToDevice, st));
+    BatchDesc b;
+    memset(&b, 0, sizeof(b));
+    b.pos = meta; b.slot = meta + T;
+    auto run = [&](int i) -> int {
+        const float* pp = part + static_cast<long long>(i % nbuf) * stride * slices;
+        if (kind == 0)
+            return qkv_rope_append(pp, sm, stride, cols, b, T, n_heads, head_dim, rope, rope + max_pos * (head_dim / 2), max_pos, q, kv,
+                                   kv + static_cast<long long>(S) * hidden, st);
+        if (kind == 1) return silu_mul(pp, sm, stride, cols, T, mlp, mm, st);
+        return residual_rmsnorm(h, pp, sm, stride, cols, g, T, hidden, 1e-5f, x, st);
+    };
+    for (int i = 0; i < 3; ++i) ATS_TRY(run(i));
+    cudaEvent_t e0, e1;
+    ATS_CUDA(cudaEventCreate(&e0));
+    ATS_CUDA(cudaEventCreate(&e1));
+    ATS_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) ATS_TRY(run(i + 3));
+    ATS_CUDA(cudaEventRecord(e1, st));
+    ATS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    ATS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *us_out = ms * 1e3f / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(part); cudaFree(h); cudaFree(g); cudaFree(q); cudaFree(kv); cudaFree(mm); cudaFree(rope); cudaFree(meta);
+    return ATS_OK;
+}
+

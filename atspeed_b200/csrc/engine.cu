@@ -73,10 +73,10 @@ void hang_diag_describe(char* buf, size_t n) {
     if (n) buf[0] = 0;
     const volatile HangDiag* d = g_diag_host;
     if (!d || d->flag == 0) return;
-    static const char* const kern[] = {"?", "gemm_wx_tcgen05", "gemm_wx_tcgen05_2cta", "kv_gather"};
+    static const char* const kern[] = {"?", "gemm_wx_tcgen05", "gemm_wx_tcgen05_2cta", "kv_gather", "row-wise consumer"};
     static const char* const role[] = {"?", "TMA producer", "MMA issuer", "epilogue", "copy thread"};
     static const char* const bar[] = {"?", "empty", "full", "accum_full", "accum_empty", "row", "partial-sum flag of worker"};
-    const unsigned k = d->kernel < 4 ? d->kernel : 0, r = d->role < 5 ? d->role : 0, b = d->barrier < 7 ? d->barrier : 0;
+    const unsigned k = d->kernel < 5 ? d->kernel : 0, r = d->role < 5 ? d->role : 0, b = d->barrier < 7 ? d->barrier : 0;
     snprintf(buf, n,
              " [device stall: %s block %u thread %u (%s) waited %.0f ms for %s[%u] parity %u, unit %u of [%u,%u), T=%u%s]",
              kern[k], d->block, d->thread, role[r], d->waited_ns * 1e-6, bar[b], d->index, d->parity, d->unit, d->u_begin,
@@ -363,6 +363,7 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
     // fused epilogues (opt-in, ATSPEED_FUSED_EPI=1): the q|k|v GEMM applies RoPE and appends to the KV cache, the gate|up GEMM
     // applies SiLU * up; default: fp32 partial-sum slices + row-wise consumer kernels for both
     const bool fused = s->fused;
+    static const bool dup_rowwise = []() { const char* e = getenv("ATSPEED_DEBUG_DUP_ROWWISE"); return e && atoi(e) == 1; }();
     GemmPlan p_qkv, p_o, p_gu, p_down, p_lm;
     if (fused) {
         ATS_TRY(gemm_make_plan_fused(L0.qkv, T, s->num_sms, EPI_QKV_ROPE, &p_qkv));
@@ -379,11 +380,12 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
     memset(&sm_qkv, 0, sizeof(sm_qkv));
     memset(&sm_gu, 0, sizeof(sm_gu));
     if (!fused) { sm_qkv = gemm_split_map(L0.qkv, p_qkv); sm_gu = gemm_split_map(L0.gu, p_gu); }
-    XMap xm_x, xm_a, xm_m, xm_sel;
-    ATS_TRY(gemm_make_xmap(&xm_x, m.x, T, d.hidden));
-    ATS_TRY(gemm_make_xmap(&xm_a, m.a, T, m.HD));
-    ATS_TRY(gemm_make_xmap(&xm_m, m.m, T, d.mlp));
-    ATS_TRY(gemm_make_xmap(&xm_sel, m.xsel, R, d.hidden));
+    XMap xm_x, xm_xg, xm_a, xm_m, xm_sel;       // one per consumer: the box of a map depends on the consumer's cluster size
+    ATS_TRY(gemm_make_xmap(&xm_x, m.x, T, d.hidden, p_qkv.cluster));
+    ATS_TRY(gemm_make_xmap(&xm_xg, m.x, T, d.hidden, p_gu.cluster));
+    ATS_TRY(gemm_make_xmap(&xm_a, m.a, T, m.HD, p_o.cluster));
+    ATS_TRY(gemm_make_xmap(&xm_m, m.m, T, d.mlp, p_down.cluster));
+    ATS_TRY(gemm_make_xmap(&xm_sel, m.xsel, R, d.hidden, p_lm.cluster));
     const int c_qkv = 3 * m.HD, c_gu = 2 * d.mlp;
     OMap om_qkv, om_o, om_gu, om_down, om_lm;
     if (!fused) {
@@ -420,6 +422,10 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
             PROF(s, CAT_ELEM, 0,
                  qkv_rope_append(m.part, sm_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
                                  d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
+            if (dup_rowwise)      // timing experiment: both consumers are idempotent, so running them twice only costs time
+                PROF(s, CAT_ELEM, 0,
+                     qkv_rope_append(m.part, sm_qkv, static_cast<long long>(T) * c_qkv, c_qkv, b, T, d.n_heads, d.head_dim,
+                                     d.rope_cos, d.rope_sin, d.max_pos, m.q, kc, vc, st));
         }
         PROF(s, CAT_ATTN, 0, tree_attention(m.q, kc, vc, b, T, S, d.n_heads, d.head_dim, m.a, st));
         PROF_GEMM(s, L.o, T, gemm_wx(L.o, xm_a, p_o, om_o, st));
@@ -428,10 +434,11 @@ int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, co
                               d.rms_eps, m.x, st));
         if (fused) {
             e_gu.epoch = next_epoch();
-            PROF_GEMM(s, L.gu, T, gemm_wx_fused(L.gu, xm_x, p_gu, e_gu, st));
+            PROF_GEMM(s, L.gu, T, gemm_wx_fused(L.gu, xm_xg, p_gu, e_gu, st));
         } else {
-            PROF_GEMM(s, L.gu, T, gemm_wx(L.gu, xm_x, p_gu, om_gu, st));
+            PROF_GEMM(s, L.gu, T, gemm_wx(L.gu, xm_xg, p_gu, om_gu, st));
             PROF(s, CAT_ELEM, 0, silu_mul(m.part, sm_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
+            if (dup_rowwise) PROF(s, CAT_ELEM, 0, silu_mul(m.part, sm_gu, static_cast<long long>(T) * c_gu, c_gu, T, d.mlp, m.m, st));
         }
         PROF_GEMM(s, L.down, T, gemm_wx(L.down, xm_m, p_down, om_down, st));
         const __nv_bfloat16* next_ln = l + 1 < d.n_layers ? m.layers[l + 1].ln1 : nullptr;
@@ -1003,7 +1010,7 @@ static int standalone_gemm(const void* x, int32_t T, int32_t K, const void* cons
     ATS_CUDA(cudaGetDevice(&dev));
     ATS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     ATS_TRY(gemm_make_plan(*g, T, sms, true, pl));
-    return x ? gemm_make_xmap(xm, x, T, K) : ATS_OK;
+    return x ? gemm_make_xmap(xm, x, T, K, pl->cluster) : ATS_OK;
 }
 
 int atspeed_gemm_plan(int32_t T, int32_t K, int32_t rows0, int32_t rows1, int32_t rows2, int32_t num_sms, int32_t allow_cut,

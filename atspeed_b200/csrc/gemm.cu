@@ -85,6 +85,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint64_t*
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
+// the same, delivered to every CTA of `cta_mask` (same shared-memory offset in each); each destination's bytes are credited to
+// the full barrier of ITS pair leader (peer bit cleared).  CUTLASS: SM100_TMA_2SM_LOAD_MULTICAST.
+__device__ __forceinline__ void tma_load_2d_2sm_mc(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, uint16_t cta_mask,
+                                                   uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(cta_mask), "l"(hint)
+        : "memory");
+}
 __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                               uint32_t accumulate) {
     asm volatile(
@@ -96,11 +105,11 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// arrive (once the issuing thread's MMAs retire) on the barrier at the same shared-memory offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+// arrive (once the issuing thread's MMAs retire) on the barrier at the same shared-memory offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
-                 "h"(static_cast<uint16_t>(3))
+                 "h"(cta_mask)
                  : "memory");
 }
 // arrive on the barrier at this offset in CTA `cta` of the cluster
@@ -288,12 +297,6 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
     r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
     return r;
 }
-// bf16(bf16(silu(g)) * u) with g, u rounded to bf16 first: the rounding points of an HF bf16 LlamaMLP (elementwise.cu silu_mul)
-__device__ __forceinline__ float silu_mul_bf16(float g, float u) {
-    g = bf16_round(g); u = bf16_round(u);
-    return bf16_round(g / (1.0f + expf(-g))) * u;
-}
-
 // Drain every segment of this CTA's unit range [u_begin, u_end).  `worker` = owner of the unit range (the CTA, or the CTA pair),
 // `sub` = this CTA's rank inside the worker.  One 128-row half of a tile sits in TMEM lanes 0..127 (lane = feature row),
 // token t in accumulator column t.  Called by the four epilogue warps (threads 64..191).
@@ -756,7 +759,17 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
 // every TMA of the pair completes on it); empty[s] and accum_full[b] are signalled in both CTAs by the leader's
 // multicast commit; accum_empty[b] lives in the leader and collects the 8 epilogue warps of the pair.
 // ---------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+//
+// CL = 4: two pairs in one cluster work on ADJACENT tiles (a 512-row "super-tile") over the same k-blocks, in lock step, and
+// share the activation stream: each CTA fetches only HALF of its half of the activation tile and multicasts it to the CTA of
+// the same pair rank in the other pair.  L2 -> SM requests per CTA and k-block: 16 KB + T/4 x 128 B instead of 16 KB + T/2 x
+// 128 B (ncu, T = 512, CL = 2: the launch moves 585 MB out of L2 for 190 MB of weights and runs at ~4800 B/clk of the
+// ~6300 B/clk the L2 delivers to TMA; the tensor pipe is busy 63 % of a CTA's life).  A stage may be refilled only when BOTH
+// pairs have consumed it (a CTA's multicast writes into the other pair's shared memory): empty[s] collects one commit from
+// each leader.  The work unit is (super-tile, k-block) and the worker is the cluster; an odd tile count leaves the last
+// super-tile with a phantom tile (zero-filled loads, epilogue skipped).
+template <int CL>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
                      const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
@@ -780,8 +793,13 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
         trace_put(p.trace, 7, (gridDim.x << 16) | static_cast<unsigned>(p.T));
         trace_put(p.trace, 2, 1);
     }
-    const bool leader = rank == 0;
-    const int pair = blockIdx.x >> 1;
+    const uint32_t prank = rank & 1u;                         // rank inside the pair
+    const int cpair = static_cast<int>(rank >> 1);            // pair inside the cluster (0 when CL == 2)
+    const bool leader = prank == 0;
+    const uint32_t lead_rank = rank & ~1u;
+    const int pair = blockIdx.x / CL;                         // the worker: owner of a unit range (a pair, or a cluster of two pairs)
+    constexpr int TPS = CL / 2;                               // tiles per (super-)tile of a unit
+    const int n_tiles_total = p.tiles[0] + p.tiles[1] + p.tiles[2];
     const int T64 = p.n_mma * p.N_mma;                       // tokens padded to a multiple of 64
     const int b_half_rows = p.N_mma >> 1;                    // tokens of one MMA held by this CTA
     const int b_mma_bytes = b_half_rows * BLOCK_K * 2;
@@ -796,11 +814,13 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
         wid = 0;
         if (tile >= p.tiles[0]) { tile -= p.tiles[0]; wid = 1; }
         if (wid == 1 && tile >= p.tiles[1]) { tile -= p.tiles[1]; wid = 2; }
-        m0 = tile * 256 + static_cast<int>(rank) * BLOCK_M;   // this CTA's 128 rows of the pair's 256-row tile
+        m0 = tile * 256 + static_cast<int>(prank) * BLOCK_M;  // this CTA's 128 rows of the pair's 256-row tile
     };
+    // this pair's tile of super-tile `st` (>= n_tiles_total: the phantom tile behind an odd tile count)
+    auto my_tile = [&](int st) { return st * TPS + cpair; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TPS); }   // one commit per leader
         for (int b = 0; b < 2; ++b) {
             mbar_init(&accum_full[b], 1);
             mbar_init(&accum_empty[b], 8);        // 4 epilogue warps of each CTA of the pair
@@ -839,12 +859,18 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
     if (warp == 0) {
         // ===== TMA producer (one thread in each CTA) =====
         if (lane == 0) {
-            int tile = u_begin / KB, kb = u_begin - tile * KB, wid, m0;
-            tile_of(tile, wid, m0);
+            int stile = u_begin / KB, kb = u_begin - stile * KB, wid, m0;
+            // a phantom tile loads fully out-of-bounds boxes: zero fill, the byte count still arrives
+            auto tile_or_phantom = [&](int st) {
+                const int t = my_tile(st);
+                if (t < n_tiles_total) tile_of(t, wid, m0);
+                else { wid = 0; m0 = p.n_rows[0] + 256; }
+            };
+            tile_or_phantom(stile);
             const uint64_t hint_w = p.l2_hints ? L2_EVICT_FIRST : 0x1000000000000000ull;      // weights: streamed once
             const uint64_t hint_x = p.l2_hints ? L2_EVICT_LAST : 0x1000000000000000ull;       // activations: re-read by all
             auto advance = [&]() {
-                if (++kb == KB) { kb = 0; ++tile; tile_of(tile, wid, m0); }
+                if (++kb == KB) { kb = 0; ++stile; tile_or_phantom(stile); }
             };
             auto load_a = [&](int s) {
                 const CUtensorMap* tmW = wid == 0 ? &tmW0 : (wid == 1 ? &tmW1 : &tmW2);
@@ -852,7 +878,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                 uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
                 if (p.epi.kind == EPI_SILU_MUL) {
                     // this CTA's 128 rows = the gate rows and the up rows of ITS 64 features of the pair's 128-feature tile
-                    const int r0 = tile * 128 + static_cast<int>(rank) * 64;
+                    const int r0 = stile * 128 + static_cast<int>(prank) * 64;    // fused plans: CL == 2, stile is the tile
                     tma_load_2d_2sm(&tmW0, &full_bar[s], a_dst, kb * BLOCK_K, r0, hint_w);
                     tma_load_2d_2sm(&tmW1, &full_bar[s], a_dst + 64 * BLOCK_K * 2, kb * BLOCK_K, r0, hint_w);
                 } else {
@@ -861,9 +887,18 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
             };
             auto load_b = [&](int s, int kbb) {
                 uint8_t* b_dst = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
-                for (int i = 0; i < p.n_mma; ++i)            // tokens [i*N_mma + rank*N_mma/2, +N_mma/2): rows past T are zeros
-                    tma_load_2d_2sm(&tmX, &full_bar[s], b_dst + i * b_mma_bytes, kbb * BLOCK_K,
-                                    i * p.N_mma + static_cast<int>(rank) * b_half_rows, hint_x);
+                for (int i = 0; i < p.n_mma; ++i) {          // tokens [i*N_mma + prank*N_mma/2, +N_mma/2): rows past T are zeros
+                    if (CL == 2) {
+                        tma_load_2d_2sm(&tmX, &full_bar[s], b_dst + i * b_mma_bytes, kbb * BLOCK_K,
+                                        i * p.N_mma + static_cast<int>(prank) * b_half_rows, hint_x);
+                    } else {
+                        // this CTA fetches quarter `cpair` of those tokens for itself and for its twin in the other pair
+                        const int qrows = b_half_rows >> 1;
+                        tma_load_2d_2sm_mc(&tmX, &full_bar[s], b_dst + i * b_mma_bytes + cpair * (b_mma_bytes >> 1), kbb * BLOCK_K,
+                                           i * p.N_mma + static_cast<int>(prank) * b_half_rows + cpair * qrows,
+                                           static_cast<uint16_t>(0x5u << prank), hint_x);
+                    }
+                }
             };
             const int npre = n_units < p.stages ? n_units : p.stages;
             const int kb_first = kb;
@@ -914,11 +949,11 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                     if (p.n_mma == 2)
                         umma_bf16_2sm(tacc + p.N_mma, da, make_smem_desc(b_addr + b_mma_bytes + k * UMMA_K * 2), idesc, acc);
                 }
-                umma_commit_2sm(&empty_bar[s]);                           // frees the slot in both CTAs
+                umma_commit_2sm(&empty_bar[s], static_cast<uint16_t>((1u << CL) - 1u));   // this pair is done with the slot: every CTA of the cluster hears it
                 if (++s == p.stages) { s = 0; ph ^= 1; }
                 if (++kb == KB) kb = 0;
                 if (u + 1 == u_end || kb == 0) {
-                    umma_commit_2sm(&accum_full[buf]);                    // accumulators complete in both CTAs
+                    umma_commit_2sm(&accum_full[buf], static_cast<uint16_t>(3u << lead_rank));   // accumulators complete in both CTAs of the pair
                     if (buf) ++use1; else ++use0;
                     if (p.n_bufs == 2) buf ^= 1;
                 }
@@ -938,24 +973,32 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
         const bool elected = threadIdx.x == 64;
         const int f = q * 32 + lane;
         if (p.epi.kind != EPI_SLICES) {
-            fused_epilogue<true>(p, pair, static_cast<int>(rank), u_begin, u_end, tmem_base, stage_out, accum_full, accum_empty, wc, s_pos, s_slotuser, s_kvoff);
+            fused_epilogue<true>(p, pair, static_cast<int>(prank), u_begin, u_end, tmem_base, stage_out, accum_full, accum_empty, wc, s_pos, s_slotuser, s_kvoff);
         } else
         for (int u = u_begin; u < u_end; ++seg) {
-            const int tile = u / KB;
-            const int seg_end = min((tile + 1) * KB, u_end);
-            int wid, m0;
-            tile_of(tile, wid, m0);
-            const int slice = pair - (tile * KB) / p.U;
+            const int stile = u / KB;
+            const int seg_end = min((stile + 1) * KB, u_end);
+            const int tile = my_tile(stile);
+            int wid = 0, m0 = 0;
+            const bool phantom = tile >= n_tiles_total;
+            if (!phantom) tile_of(tile, wid, m0);
+            const int slice = pair - (stile * KB) / p.U;
             const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
             if (elected) trace_put(p.trace, 6, 0x30000u | static_cast<unsigned>(seg));
             mbar_wait(&accum_full[buf], use & 1, wc, HANG_B_ACCUM_FULL, buf, u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (phantom) {                                            // nothing to store: hand the accumulator back
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], lead_rank);
+                u = seg_end;
+                continue;
+            }
             const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
             const uint32_t tbase = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
             if (p.tma_store) {
                 drain_segment_tma(tmO, tbase, 1, (min(T64, p.T) + 15) >> 4, 0u, m0, slice, stage_out, st_chunk, f, elected, p.store_hint, [&]() {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], 0);     // the leader's MMA thread waits for all 8 warps
+                    if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], lead_rank);     // the leader's MMA thread waits for all 8 warps
                 });
                 u = seg_end;
                 continue;
@@ -974,7 +1017,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], 0);     // the leader's MMA thread waits for all 8 warps
+            if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], lead_rank);     // the leader's MMA thread waits for all 8 warps
             u = seg_end;
         }
         if (p.tma_store && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1042,6 +1085,24 @@ bool gemm_use_2cta(int T) {
     return T_pad > (m ? atoi(m) : 256);
 }
 
+// Cluster size of the CTA-pair kernel: 4 (two pairs sharing the activation stream by multicast) when ATSPEED_GEMM_CLUSTER=4 and
+// the device can keep num_sms / 4 such clusters resident (a cluster lives inside one GPC: 148 SMs do not always tile into 37
+// clusters of 4); 2 otherwise.  Read per call like ATSPEED_GEMM_2CTA.
+static int g_max_clusters4[64];      // per device: co-resident 4-CTA clusters of gemm_wx_tcgen05_2cta<4> (0 = not queried / none)
+static int gemm_init_device(int* max_dyn_out);
+// workers (clusters of 4) a cluster-of-4 plan may use on this device, 0 = use CTA pairs
+static int gemm_cluster4_workers(int num_sms) {
+    const char* e = getenv("ATSPEED_GEMM_CLUSTER");
+    if (!e || atoi(e) != 4 || num_sms < 4) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return num_sms / 4; }   // no device (CPU tests of the plan arithmetic)
+    int md = 0;
+    if (dev < 0 || dev >= 64 || gemm_init_device(&md) != ATS_OK) return 0;
+    const int n = g_max_clusters4[dev] < num_sms / 4 ? g_max_clusters4[dev] : num_sms / 4;
+    return n >= 1 ? n : 0;
+}
+int gemm_cluster_size(int num_sms) { return gemm_cluster4_workers(num_sms) > 0 ? 4 : 2; }
+
 // Choose the tile height, the persistent grid and the unit range of every CTA for one GEMM shape.
 //   allow_cut : tiles may be cut along K across CTAs (partial-sum slices; consumers reduce via SplitMap).  When false
 //               (lm_head: its consumer, kernel (a), reads plain fp32 logits) whole tiles are dealt out instead.
@@ -1055,7 +1116,8 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
     pl->KB = (w.K + BLOCK_K - 1) / BLOCK_K;
     if (gemm_use_2cta(T) && num_sms >= 2) {
         // CTA-pair kernel (gemm_wx_tcgen05_2cta): 256-row tiles owned by SM pairs, tokens padded to 64 and covered by one
-        // or two M=256 MMAs of N_mma columns (each CTA holds N_mma/2 tokens of each)
+        // or two M=256 MMAs of N_mma columns (each CTA holds N_mma/2 tokens of each).  cluster = 4: the worker is a cluster of
+        // two pairs on adjacent tiles (a super-tile) sharing the activation stream by multicast.
         pl->two_cta = 1;
         const int T64 = (T + 63) & ~63;
         pl->n_mma = T64 > 256 ? 2 : 1;
@@ -1067,21 +1129,25 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
             pl->tilebase[i] = pl->total_tiles;
             pl->total_tiles += pl->tiles[i];
         }
-        const int pairs = num_sms / 2;
-        const int units = pl->total_tiles * pl->KB;
+        const int w4 = gemm_cluster4_workers(num_sms);
+        pl->cluster = w4 > 0 && pl->total_tiles >= 2 ? 4 : 2;
+        const int tps = pl->cluster / 2;
+        const int n_super = (pl->total_tiles + tps - 1) / tps;         // units are (super-tile, k-block)
+        const int pairs = pl->cluster == 4 ? w4 : num_sms / 2;         // workers
+        const int units = n_super * pl->KB;
         if (allow_cut) {
             const int grid = units < pairs ? units : pairs;
             pl->U = (units + grid - 1) / grid;
             const int min_u = pl->KB < 8 ? pl->KB : 8;
             if (pl->U < min_u) pl->U = min_u;
-            const int s = pairs / pl->total_tiles;      // narrow outputs: whole k-splits per tile (one segment per pair)
-            if (s >= 2 && s <= pl->KB && pl->total_tiles * s * 10 >= pairs * 8) pl->U = (pl->KB + s - 1) / s;
+            const int s = pairs / n_super;              // narrow outputs: whole k-splits per tile (one segment per worker)
+            if (s >= 2 && s <= pl->KB && n_super * s * 10 >= pairs * 8) pl->U = (pl->KB + s - 1) / s;
         } else {
-            pl->U = ((pl->total_tiles + pairs - 1) / pairs) * pl->KB;
+            pl->U = ((n_super + pairs - 1) / pairs) * pl->KB;
         }
-        pl->grid = 2 * ((units + pl->U - 1) / pl->U);
+        pl->grid = pl->cluster * ((units + pl->U - 1) / pl->U);
         pl->max_slices = 1;
-        for (int t = 0; t < pl->total_tiles; ++t) {
+        for (int t = 0; t < n_super; ++t) {
             const int n = (t * pl->KB + pl->KB - 1) / pl->U - (t * pl->KB) / pl->U + 1;
             if (n > pl->max_slices) pl->max_slices = n;
         }
@@ -1170,6 +1236,7 @@ int gemm_make_plan_fused(const GemmWeights& w, int T, int num_sms, int kind, Gem
     int workers = num_sms, stage_bytes;
     if (pair) {
         pl->two_cta = 1;
+        pl->cluster = 2;
         const int T64 = (T + 63) & ~63;
         pl->n_mma = T64 > 256 ? 2 : 1;
         pl->N_mma = T64 / pl->n_mma;
@@ -1237,22 +1304,34 @@ int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms) {
 
 SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& pl) {
     SplitMap m;
+    memset(&m, 0, sizeof(m));
     m.n = w.n;
     for (int i = 0; i < 3; ++i) { m.colbase[i] = i < w.n ? w.colbase[i] : 0x7fffffff; m.tilebase[i] = pl.tilebase[i]; }
     m.BM = pl.BM; m.KB = pl.KB; m.U = pl.U;
+    m.tps = pl.two_cta && pl.cluster == 4 ? 2 : 1;
+    m.tab_n = 0; m.bm_shift = 0;
+    memset(m.tab, 0, sizeof(m.tab));
+    if (pl.total_tiles <= SPLIT_TAB && (pl.BM & (pl.BM - 1)) == 0) {
+        while ((1 << m.bm_shift) < pl.BM) ++m.bm_shift;
+        for (int t = 0; t < pl.total_tiles; ++t) m.tab[t] = static_cast<unsigned char>(m.slices_of_tile(t));
+        m.tab_n = pl.total_tiles;
+    }
     return m;
 }
 
-int gemm_make_xmap(XMap* xm, const void* x, int T, int K) {
+int gemm_make_xmap(XMap* xm, const void* x, int T, int K, int cluster) {
     if (gemm_use_2cta(T)) {
-        // CTA-pair kernel: one box = the N_mma/2 tokens of one MMA that one CTA of the pair holds
+        // CTA-pair kernel: one box = the N_mma/2 tokens of one MMA that one CTA of the pair holds (cluster of 4: half of them,
+        // the other half arrives by multicast from the twin CTA)
         const int T64 = (T + 63) & ~63;
         const int n_mma = T64 > 256 ? 2 : 1;
-        ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, T64 / n_mma / 2));
+        const int box = T64 / n_mma / 2 / (cluster == 4 ? 2 : 1);
+        ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, box));
         xm->tm1 = xm->tm0;
-        xm->T = T; xm->K = K; xm->box0 = T64 / n_mma / 2;
+        xm->T = T; xm->K = K; xm->box0 = box; xm->cluster = cluster;
         return ATS_OK;
     }
+    xm->cluster = 0;
     const int T_pad = (T + 15) & ~15;
     // activations: tokens 0..255 through tm0 (box = min(T_pad,256) rows), tokens 256..T_pad-1 through tm1
     // (box = T_pad-256 rows); rows past T are zero-filled by TMA, and each box always delivers its full byte count.
@@ -1303,7 +1382,8 @@ static int gemm_init_device(int* max_dyn_out) {
         cudaFuncAttributes fa;
         int md = 227 * 1024;
         err[dev] = cudaSuccess;
-        for (const void* fn : {reinterpret_cast<const void*>(gemm_wx_tcgen05), reinterpret_cast<const void*>(gemm_wx_tcgen05_2cta)}) {
+        for (const void* fn : {reinterpret_cast<const void*>(gemm_wx_tcgen05), reinterpret_cast<const void*>(gemm_wx_tcgen05_2cta<2>),
+                               reinterpret_cast<const void*>(gemm_wx_tcgen05_2cta<4>)}) {
             cudaError_t e = cudaFuncGetAttributes(&fa, fn);
             const int want = 227 * 1024 - static_cast<int>(fa.sharedSizeBytes);   // static barriers share the 227 KiB budget
             if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
@@ -1311,6 +1391,21 @@ static int gemm_init_device(int* max_dyn_out) {
             if (want < md) md = want;
         }
         max_dyn[dev] = md;
+        // how many clusters of 4 (one GEMM CTA per SM) can be resident at once: decides whether the cluster-of-4 plans are used
+        {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            int sms = 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cfg.gridDim = dim3((sms / 4) * 4); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = md;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_wx_tcgen05_2cta<4>, &cfg) == cudaSuccess) g_max_clusters4[dev] = n;
+            else cudaGetLastError();
+        }
     });
     if (err[dev] != cudaSuccess) { set_error("gemm: shared-memory set-up failed: %s", cudaGetErrorString(err[dev])); return ATS_ERR_CUDA; }
     *max_dyn_out = max_dyn[dev];
@@ -1345,7 +1440,8 @@ static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl,
         p.tiles[i] = pl.tiles[i];
         p.colbase[i] = i < w.n ? w.colbase[i] : 0;
     }
-    p.BM = pl.BM; p.U = pl.U; p.total_units = pl.total_tiles * pl.KB;
+    const int tps = pl.two_cta && pl.cluster == 4 ? 2 : 1;
+    p.BM = pl.BM; p.U = pl.U; p.total_units = ((pl.total_tiles + tps - 1) / tps) * pl.KB;
     p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.acc_stride = pl.acc_stride;
     p.n_bufs = pl.n_bufs; p.buf_stride = pl.buf_stride;
     p.b_box_bytes = (pl.T_pad > 256 ? pl.T_pad : xm.box0) * BLOCK_K * 2;
@@ -1374,11 +1470,20 @@ static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl,
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue + weight prefetch overlap the
-    attr[0].val.programmaticStreamSerializationAllowed = 1;            // previous kernel; see griddepcontrol.wait
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (pl.two_cta) {
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = pl.cluster; attr[n_attr].val.clusterDim.y = 1; attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
+    }
+    if (pdl_enabled()) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue + weight prefetch overlap the
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;            // previous kernel; see griddepcontrol.wait
+        ++n_attr;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = n_attr;
     // weight operand maps: 128-row boxes, 256-row boxes for the stacked single-CTA tiles, and for the interleaved SiLU tiles
     // the gate / up halves (BM/2 rows per box of a single CTA, 64 rows per CTA of a pair)
     const CUtensorMap* tw = (!pl.two_cta && pl.BM == 256) ? w.tmap256 : w.tmap;
@@ -1387,8 +1492,12 @@ static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl,
     const CUtensorMap& o1 = om ? om->tm[1] : tw[0];
     const CUtensorMap& o2 = om ? om->tm[2] : tw[0];
     if (pl.two_cta) {
-        ATS_CHECK_ARG((pl.grid & 1) == 0, "gemm (2-CTA): grid %d", pl.grid);
-        ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, o0, o1, o2, p));
+        ATS_CHECK_ARG((pl.cluster == 2 || pl.cluster == 4) && pl.grid % pl.cluster == 0, "gemm (CTA pairs): grid %d, cluster %d", pl.grid, pl.cluster);
+        ATS_CHECK_ARG(xm.cluster == pl.cluster, "gemm: activation map built for clusters of %d, plan uses %d", xm.cluster, pl.cluster);
+        if (pl.cluster == 4)
+            ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta<4>, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, o0, o1, o2, p));
+        else
+            ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta<2>, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, o0, o1, o2, p));
         return ATS_OK;
     }
     ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1, o0, o1, o2, p));

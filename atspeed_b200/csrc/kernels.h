@@ -52,20 +52,32 @@ struct GemmPlan {
     int max_slices;         // most slices any tile of this launch has
     int stages, tmem_cols, acc_stride, n_bufs, buf_stride;
     int two_cta, n_mma, N_mma;   // CTA-pair kernel (T > 256): see gemm_wx_tcgen05_2cta
+    int cluster;                 // CTA-pair kernel: CTAs per cluster, 2 (one pair) or 4 (two pairs sharing the activations by multicast)
     int epi_kind;                // EPI_*: EPI_SLICES plans feed a consumer kernel, the others finish tiles in the kernel
 };
-// What a consumer of the partial sums needs to know: how many slices hold column `col`.
+// What a consumer of the partial sums needs to know: how many slices hold column `col`.  The host tabulates the count per tile
+// (gemm_split_map), so the device side is a shift and a byte load; launches with more than SPLIT_TAB tiles fall back to the
+// arithmetic (two integer divisions per query: they made the row-wise consumers issue-bound).
+constexpr int SPLIT_TAB = 256;
 struct SplitMap {
     int n;
     int colbase[3], tilebase[3];
     int BM, KB, U;
-    __host__ __device__ __forceinline__ int slices(int col) const {
-        const int i = col >= colbase[2] ? 2 : (col >= colbase[1] ? 1 : 0);
-        const int u0 = (tilebase[i] + (col - colbase[i]) / BM) * KB;
+    int tps;                // tiles per unit row: 2 when the work unit is a super-tile (clusters of 4), else 1
+    int tab_n, bm_shift;    // tab_n > 0: tab[tile] is valid for tile < tab_n and BM == 1 << bm_shift
+    unsigned char tab[SPLIT_TAB];
+    __host__ __device__ __forceinline__ int slices_of_tile(int tile) const {
+        const int u0 = (tile / tps) * KB;
         return (u0 + KB - 1) / U - u0 / U + 1;
     }
+    __host__ __device__ __forceinline__ int slices(int col) const {
+        const int i = col >= colbase[2] ? 2 : (col >= colbase[1] ? 1 : 0);
+        if (tab_n > 0) return tab[tilebase[i] + ((col - colbase[i]) >> bm_shift)];
+        return slices_of_tile(tilebase[i] + (col - colbase[i]) / BM);
+    }
 };
-struct XMap { CUtensorMap tm0, tm1; int T, K, box0; };   // activation operand [T, K] bf16 (two boxes: tokens < 256, >= 256)
+struct XMap { CUtensorMap tm0, tm1; int T, K, box0, cluster; };   // activation operand [T, K] bf16 (two boxes: tokens < 256, >= 256)
+int gemm_cluster_size(int num_sms);     // CTAs per cluster of the pair kernel on this device (2 or 4)
 bool gemm_use_2cta(int T);
 int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, GemmPlan* plan);
 // plan of a fused-epilogue launch (kind = EPI_QKV_ROPE: w = {q, k, v}; EPI_SILU_MUL: w = {gate, up})
@@ -74,7 +86,7 @@ size_t gemm_fused_part_elems(int T_max, int num_sms);     // floats of FusedEpi:
 int gemm_wx_fused(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, const FusedEpi& epi, cudaStream_t stream);
 int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms);
 SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& plan);
-int gemm_make_xmap(XMap* xm, const void* x, int T, int K);
+int gemm_make_xmap(XMap* xm, const void* x, int T, int K, int cluster);   // cluster: GemmPlan::cluster of the launch that reads it
 struct OMap { CUtensorMap tm[3]; float* out; int ldo; long long slice_stride; int T; int ok; };   // fp32 partial-sum output
 int gemm_make_omap(OMap* om, const GemmWeights& w, float* out, int ldo, long long slice_stride, int T, int max_slices);
 int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, const OMap& om, cudaStream_t stream);

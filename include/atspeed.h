@@ -44,6 +44,11 @@ int atspeed_abi_version(void);
  * (0 = tracing off).  Readable while a launch is stuck.  Every mbarrier wait of the library is bounded separately
  * (ATSPEED_SPIN_LIMIT_MS, default 4000): an expired wait traps and atspeed_last_error() names kernel/CTA/role/barrier. */
 int atspeed_debug_gemm_trace(uint32_t* out, int32_t max_words);
+/* Diagnostics: microseconds per launch of one row-wise consumer kernel of the forward (kind 0 RoPE + KV append, 1 SiLU * up,
+ * 2 residual + RMSNorm) at T tokens with every output column held in `slices` fp32 partial-sum slices; inputs are cycled
+ * through buffers larger than L2.  tools/rowwise_bench.py prints GB/s against MEASURED_PEAKS.json. */
+int atspeed_debug_rowwise_us(int32_t kind, int32_t T, int32_t hidden, int32_t mlp, int32_t n_heads, int32_t slices, int32_t iters,
+                             float* us_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Model + session
