@@ -800,7 +800,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
     const int pair = blockIdx.x / CL;                         // the worker: owner of a unit range (a pair, or a cluster of two pairs)
     constexpr int TPS = CL / 2;                               // tiles per (super-)tile of a unit
     const int n_tiles_total = p.tiles[0] + p.tiles[1] + p.tiles[2];
-    const int T64 = p.n_mma * p.N_mma;                       // tokens padded to a multiple of 64
+    const int T64 = p.n_mma * p.N_mma;                       // tokens padded for the MMA / TMA boxes (pair_pad_tokens)
     const int b_half_rows = p.N_mma >> 1;                    // tokens of one MMA held by this CTA
     const int b_mma_bytes = b_half_rows * BLOCK_K * 2;
     const int a_bytes = A_TILE_BYTES;
@@ -1088,6 +1088,15 @@ bool gemm_use_2cta(int T) {
 // Cluster size of the CTA-pair kernel: 4 (two pairs sharing the activation stream by multicast) when ATSPEED_GEMM_CLUSTER=4 and
 // the device can keep num_sms / 4 such clusters resident (a cluster lives inside one GPC: 148 SMs do not always tile into 37
 // clusters of 4); 2 otherwise.  Read per call like ATSPEED_GEMM_2CTA.
+// Token padding of a CTA-pair launch: every TMA box of the activations must be a whole number of 8-row swizzle atoms and the
+// MMA's N a multiple of 16.  Two MMAs (more than 256 tokens): N_mma = Tp / 2 and a CTA's box holds N_mma / 2 rows (N_mma / 4 in
+// a cluster of 4) -> Tp is a multiple of 32 (64).  One MMA: N_mma = Tp, boxes of Tp / 2 (Tp / 4) rows -> 16 (32).
+static int pair_pad_tokens(int T, int cluster, int* n_mma) {
+    const int T16 = (T + 15) & ~15;
+    *n_mma = T16 > 256 ? 2 : 1;
+    const int q = (*n_mma == 2 ? 32 : 16) * (cluster == 4 ? 2 : 1);
+    return (T + q - 1) / q * q;
+}
 static int g_max_clusters4[64];      // per device: co-resident 4-CTA clusters of gemm_wx_tcgen05_2cta<4> (0 = not queried / none)
 static int gemm_init_device(int* max_dyn_out);
 // workers (clusters of 4) a cluster-of-4 plan may use on this device, 0 = use CTA pairs
@@ -1119,9 +1128,6 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
         // or two M=256 MMAs of N_mma columns (each CTA holds N_mma/2 tokens of each).  cluster = 4: the worker is a cluster of
         // two pairs on adjacent tiles (a super-tile) sharing the activation stream by multicast.
         pl->two_cta = 1;
-        const int T64 = (T + 63) & ~63;
-        pl->n_mma = T64 > 256 ? 2 : 1;
-        pl->N_mma = T64 / pl->n_mma;
         pl->BM = 256;
         pl->total_tiles = 0;
         for (int i = 0; i < 3; ++i) {
@@ -1131,6 +1137,8 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
         }
         const int w4 = gemm_cluster4_workers(num_sms);
         pl->cluster = w4 > 0 && pl->total_tiles >= 2 ? 4 : 2;
+        const int T64 = pair_pad_tokens(T, pl->cluster, &pl->n_mma);   // (named for its round-1 granularity)
+        pl->N_mma = T64 / pl->n_mma;
         const int tps = pl->cluster / 2;
         const int n_super = (pl->total_tiles + tps - 1) / tps;         // units are (super-tile, k-block)
         const int pairs = pl->cluster == 4 ? w4 : num_sms / 2;         // workers
@@ -1237,8 +1245,7 @@ int gemm_make_plan_fused(const GemmWeights& w, int T, int num_sms, int kind, Gem
     if (pair) {
         pl->two_cta = 1;
         pl->cluster = 2;
-        const int T64 = (T + 63) & ~63;
-        pl->n_mma = T64 > 256 ? 2 : 1;
+        const int T64 = pair_pad_tokens(T, 2, &pl->n_mma);
         pl->N_mma = T64 / pl->n_mma;
         pl->BM = 256;
         workers = num_sms / 2;
@@ -1323,8 +1330,8 @@ int gemm_make_xmap(XMap* xm, const void* x, int T, int K, int cluster) {
     if (gemm_use_2cta(T)) {
         // CTA-pair kernel: one box = the N_mma/2 tokens of one MMA that one CTA of the pair holds (cluster of 4: half of them,
         // the other half arrives by multicast from the twin CTA)
-        const int T64 = (T + 63) & ~63;
-        const int n_mma = T64 > 256 ? 2 : 1;
+        int n_mma = 1;
+        const int T64 = pair_pad_tokens(T, cluster, &n_mma);
         const int box = T64 / n_mma / 2 / (cluster == 4 ? 2 : 1);
         ATS_TRY(make_tmap_bf16_kmajor(&xm->tm0, x, T, K, box));
         xm->tm1 = xm->tm0;

@@ -43,7 +43,7 @@ def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut, pair, monke
         assert 2 <= stages <= 12 and tmem <= 512 and tmem & (tmem - 1) == 0
         if two_cta:
             assert BM == 256 and grid % 2 == 0 and (grid <= sms or not cut)
-            assert n_mma in (1, 2) and N_mma % 32 == 0 and N_mma <= 256 and n_mma * N_mma >= T > n_mma * N_mma - 64
+            assert n_mma in (1, 2) and N_mma % 16 == 0 and N_mma <= 256 and n_mma * N_mma >= T > n_mma * N_mma - 32
             assert stages * (16384 + (n_mma * N_mma // 2) * 128) + 24576 <= 220 * 1024
             assert bufs * n_mma * N_mma <= 512
         else:
