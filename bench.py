@@ -593,7 +593,8 @@ def atspeed_arm(a, rank, world, local_rank):
         # which resource bounds the launches in aggregate: time the algorithmic bytes need at the measured copy peak vs
         # time the FLOPs need at the measured sustained cuBLAS peak (cohort forwards are large enough to be tensor-bound)
         t_hbm, t_tensor = g["bytes"] / (peak * 1e9), g["flops"] / (peak_tf * 1e12)
-        kname = "gemm_wx_tcgen05" + ("_2cta" if base["config"]["gemm_pair_kernel"] else "")
+        kname = "gemm_wx_tcgen05" + (("_2cta<%s>" % ("4" if os.environ.get("ATSPEED_GEMM_CLUSTER") == "4" else "2"))
+                                     if base["config"]["gemm_pair_kernel"] else "")
         traffic, tinfo = ncu_traffic(kname, "cohort" if a.cohort > 1 else "single")
         if t_tensor > t_hbm:
             roofline = {"kernel": kname, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
