@@ -9,6 +9,8 @@
 // exactly that of the single-user session (same kernels' bodies, same candidate lists), so ranked lists, accepted
 // lengths and scores do not depend on who shares a forward -- tests/test_gpu_cohort.py checks that against single-user
 // runs.  One stream synchronisation per scheduler step returns the accepted lengths of the users verified in it.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -31,6 +33,7 @@ struct UserRun {
     int round;
     unsigned long long user_seq;
     int n_run, total, acc[8], tf, df;
+    int waited;         // scheduler steps this user's target forward has been held back for a fuller pack
 };
 
 struct Pack {
@@ -151,6 +154,8 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
     int* h_cnt = h_tok + MAX_USERS * MAX_K * MAX_NEW;
     float* h_score = reinterpret_cast<float*>(h_cnt + MAX_USERS);
 
+    static const bool log_packs = []() { const char* e = getenv("ATSPEED_COHORT_LOG"); return e && atoi(e) == 1; }();   // diagnostics
+    static const bool pack_defer = []() { const char* e = getenv("ATSPEED_COHORT_DEFER"); return !(e && atoi(e) == 0); }();   // A/B: 0 = run every pack at once
     std::vector<UserRun> act;
     std::vector<int> free_slots;
     for (int u = U - 1; u >= 0; --u) free_slots.push_back(u);
@@ -219,15 +224,18 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
             for (int a : pk.who) { act[a].j += 1; act[a].df += 1; }
         }
         // ---- target: verify forwards (dl >= 1) and final steps (dl == 0) of the users that are ready ----
+        // Packing: a target forward costs ~100 us + 0.19 us per token and layer at the 7B shape, so what matters is how FEW
+        // forwards carry the tokens.  Ready users are packed best-fit-decreasing (largest forward first, then the largest that
+        // still fit); a pack that fills less than 7/8 of the forward is held back one scheduler step -- the users launched now
+        // come back with small later-round trees (K + dl N tokens) that fill it -- unless nothing else would run, no new work
+        // can arrive, or one of its users has already waited twice.  Who shares a forward never changes a user's results.
         bool any_target = false;
-        for (;;) {
-            Pack pk;
-            memset(&pk.c, 0, sizeof(pk.c));
-            pk.T = pk.R = 0;
-            CohortKV ckv;
-            memset(&ckv, 0, sizeof(ckv));
-            bool has_verify = false, has_select = false;
-            int max_dl = 0;
+        std::vector<Pack> packs;
+        std::vector<CohortKV> pack_kv;
+        std::vector<int> pack_flags;       // bit 0: has_verify, bit 1: has_select; max_dl in bits 8..
+        {
+            struct Item { int a, T, R; };
+            std::vector<Item> items;
             for (size_t a = 0; a < act.size(); ++a) {
                 UserRun& u = act[a];
                 if (u.finished || u.j < u.dl) continue;
@@ -235,18 +243,68 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
                 memset(&x, 0, sizeof(x));
                 int S = 0;
                 plan_target(s, u, x, S);
-                if (pk.c.n == MAX_USERS || pk.T + x.T > s->T_max || pk.R + x.R > s->R_max) continue;
-                x.tree = u.slot; x.P = u.P; x.tok0 = pk.T; x.row0 = pk.R;
-                x.stream_base = noise_stream(u.user_seq, static_cast<uint32_t>(u.round), 0, 0);
-                ckv_entry(ckv, pk.c.n, u, x, S, s->kv_user_elems_tgt);
-                pk.c.u[pk.c.n++] = x;
-                pk.T += x.T; pk.R += x.R;
-                pk.who.push_back(static_cast<int>(a));
-                if (x.mode == 2) { has_verify = true; max_dl = u.dl > max_dl ? u.dl : max_dl; } else has_select = true;
+                items.push_back(Item{static_cast<int>(a), x.T, x.R});
             }
-            if (pk.c.n == 0) break;
+            std::stable_sort(items.begin(), items.end(), [](const Item& p, const Item& q) { return p.T > q.T; });
+            std::vector<char> used(items.size(), 0);
+            for (size_t first = 0; first < items.size(); ++first) {
+                if (used[first]) continue;
+                Pack pk;
+                memset(&pk.c, 0, sizeof(pk.c));
+                pk.T = pk.R = 0;
+                CohortKV ckv;
+                memset(&ckv, 0, sizeof(ckv));
+                int flags = 0, max_dl = 0;
+                for (size_t i = first; i < items.size(); ++i) {
+                    if (used[i]) continue;
+                    if (pk.c.n == MAX_USERS || pk.T + items[i].T > s->T_max || pk.R + items[i].R > s->R_max) continue;
+                    UserRun& u = act[items[i].a];
+                    UserCtx x;
+                    memset(&x, 0, sizeof(x));
+                    int S = 0;
+                    plan_target(s, u, x, S);
+                    x.tree = u.slot; x.P = u.P; x.tok0 = pk.T; x.row0 = pk.R;
+                    x.stream_base = noise_stream(u.user_seq, static_cast<uint32_t>(u.round), 0, 0);
+                    ckv_entry(ckv, pk.c.n, u, x, S, s->kv_user_elems_tgt);
+                    pk.c.u[pk.c.n++] = x;
+                    pk.T += x.T; pk.R += x.R;
+                    pk.who.push_back(items[i].a);
+                    if (x.mode == 2) { flags |= 1; max_dl = u.dl > max_dl ? u.dl : max_dl; } else flags |= 2;
+                    used[i] = 1;
+                }
+                ckv.n = pk.c.n;
+                packs.push_back(pk);
+                pack_kv.push_back(ckv);
+                pack_flags.push_back(flags | (max_dl << 8));
+            }
+        }
+        // which packs run now
+        std::vector<char> run_now(packs.size(), 0);
+        {
+            const bool no_more_work = next >= n_users;                   // nothing left to admit: waiting cannot fill a pack
+            const int full = s->T_max - s->T_max / 8;
+            int launched = 0, fullest = -1;
+            for (size_t b = 0; b < packs.size(); ++b) {
+                bool aged = false;
+                for (int a : packs[b].who) aged = aged || act[a].waited >= 2;
+                if (!pack_defer || packs[b].T >= full || no_more_work || aged) { run_now[b] = 1; ++launched; }
+                if (fullest < 0 || packs[b].T > packs[fullest].T) fullest = static_cast<int>(b);
+            }
+            // progress: if every pack would wait and no draft step can change the picture, run the fullest one
+            if (launched == 0 && fullest >= 0) run_now[fullest] = 1;
+            for (size_t b = 0; b < packs.size(); ++b)
+                for (int a : packs[b].who) act[a].waited = run_now[b] ? 0 : act[a].waited + 1;
+        }
+        for (size_t pb = 0; pb < packs.size(); ++pb) {
+            if (!run_now[pb]) continue;
+            Pack& pk = packs[pb];
+            CohortKV& ckv = pack_kv[pb];
+            const bool has_verify = (pack_flags[pb] & 1) != 0, has_select = (pack_flags[pb] & 2) != 0;
+            const int max_dl = pack_flags[pb] >> 8;
+            if (pk.c.n == 0) continue;
             any_target = true;
             ckv.n = pk.c.n;
+            if (log_packs) fprintf(stderr, "atspeed-pack target T=%d R=%d users=%d active=%zu\n", pk.T, pk.R, pk.c.n, act.size());
             ATS_TRY(run_pack(s, s->tgt, pk, ckv, sampling ? s->sample_B : K, has_verify, has_select, st));
             // kernel (c): move the survivors' ancestor rows into the accepted region, both caches, verified users only
             if (has_verify) {

@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="atspeed", choices=["atspeed", "reference"])
     ap.add_argument("--users-per-step", type=int, default=48)
-    ap.add_argument("--cohort", type=int, default=8,
+    ap.add_argument("--cohort", type=int, default=16,
                     help="users whose trees share each forward (atspeed_bssd_batch; <= 512 tokens per forward); 1 = one "
                          "search per forward as the reference")
     ap.add_argument("--dataset", default="beauty")
@@ -85,7 +85,7 @@ def parse():
                          "32 cores; N = 1 only; 0 = skip)")
     ap.add_argument("--constraint", default="strict", choices=["strict", "positional"])
     ap.add_argument("--profile-users", type=int, default=4)
-    ap.add_argument("--lanes", type=int, default=3,
+    ap.add_argument("--lanes", type=int, default=2,
                     help="independent searches in flight per GPU (each its own session + CUDA stream + host thread): one "
                          "user's latency-bound draft / verify phases overlap another's weight-streaming target forward")
     ap.add_argument("--cohort-tokens", type=int, default=512, help="most tokens one cohort forward packs (256..512)")
