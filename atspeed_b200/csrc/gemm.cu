@@ -33,8 +33,7 @@ static constexpr int GEMM_THREADS = 192;
 static constexpr size_t EXCLUSIVE_SMEM_BYTES = 120 * 1024;   // > 227 KiB / 2: at most one GEMM CTA per SM
 static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 static constexpr int MAX_STAGES = 12;
-static constexpr int OUT_STAGE_BUFS = 3;                     // epilogue staging ring: [16 tokens][128 features] fp32 tiles
-static constexpr int OUT_STAGE_BYTES = OUT_STAGE_BUFS * 16 * 128 * 4;
+static constexpr int OUT_STAGE_BYTES = 2 * 16 * 128 * 4;    // fused epilogues only: two [16 tokens][128 features] fp32 staging tiles
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -122,19 +121,6 @@ __device__ __forceinline__ uint32_t make_idesc_m(uint32_t m, uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-// smem [1][16][128] fp32 box -> global (coordinates: feature, token, slice); bulk-group completion
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                     reinterpret_cast<uint64_t>(tm)),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, uint64_t hint) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
-                     reinterpret_cast<uint64_t>(tm)),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -178,50 +164,39 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((BLOCK_M >> 4) << 24);
 }
 
-// Drain one segment's accumulators (this CTA's 128 TMEM lanes x `halves` x n_chunks x 16 columns) into its fp32 partial-sum
-// slice: TMEM -> registers -> [16 tokens][128 features] staging tile -> ONE bulk tensor store per 8 KB (a scalar-store
-// epilogue is LSU-issue bound: 40 % of the kernel at T = 512).  Called by the four epilogue warps (128 threads, named
-// barrier 1).  The epilogue of a T > 256 segment is exposed (one accumulator fills TMEM), so it is built to be short:
-//   * the tcgen05.ld of chunk i+1 is in flight while chunk i is staged (two register sets, ping-pong);
-//   * a ring of OUT_STAGE_BUFS = 3 staging tiles needs ONE barrier per chunk: before the barrier of chunk i the elected
-//     thread has seen the store of chunk i-2 finish reading its tile (wait_group.read 1), which is the tile chunk i+1 writes;
-//   * `release` (TMEM may be overwritten by the next segment's MMAs) runs as soon as the last tcgen05.ld has completed,
-//     before the last tile is staged and stored.
+// Drain one segment's accumulators (one 128-row half: this CTA's 128 TMEM lanes x n_chunks x 16 columns) into its fp32
+// partial-sum slice.  Every thread stores its feature's 16 tokens of a chunk straight from registers: a warp's store instruction
+// writes 32 consecutive features of one token, one full 128-byte line.  The tcgen05.ld of the next chunk is in flight while this
+// one is stored (two register sets), and `release` (the next segment's MMAs may overwrite TMEM) runs as soon as the last load has
+// completed.  The epilogue of a T > 256 segment is exposed -- one accumulator fills TMEM -- so its length is kernel time.
+// (Round 2 also had a shared-memory path: 16 x 128 staging tiles + cp.async.bulk.tensor stores, ring of three, one barrier per
+// chunk.  Same-box A/B, profiles/r02_gemm_epilogue_ab.txt: the register path is 4-10 % faster per launch at every T >= 50 --
+// four independent warps beat a barrier, a proxy fence and an elected thread per 8 KB -- so the staged path was removed.)
 template <typename ReleaseFn>
-__device__ __forceinline__ void drain_segment_tma(const CUtensorMap* tmO, uint32_t tb0, int halves, int n_chunks, uint32_t acc_stride,
-                                                  int m0, int slice, float* stage_out, int& ring, int f, bool elected,
-                                                  uint64_t store_hint, ReleaseFn release) {
-    const int total = halves * n_chunks;
-    auto taddr = [&](int idx) -> uint32_t {
-        const int half = idx >= n_chunks ? 1 : 0;
-        return tb0 + half * acc_stride + static_cast<uint32_t>((idx - half * n_chunks) << 4);
-    };
+__device__ __forceinline__ void drain_segment_stg(float* out_f, long long ldo, int T, bool row_ok, uint32_t tb0, int n_chunks,
+                                                  ReleaseFn release) {
     auto emit = [&](const uint32_t (&r)[16], int idx) {
-        float* stg = stage_out + ring * (16 * 128);
+        if (!row_ok) return;
+        float* o = out_f + static_cast<long long>(idx << 4) * ldo;
+        if ((idx << 4) + 16 <= T) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) stg[j * 128 + f] = __uint_as_float(r[j]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (elected) {
-            const int half = idx >= n_chunks ? 1 : 0;
-            const int c = (idx - half * n_chunks) << 4;
-            if (store_hint) tma_store_3d_hint(tmO, stg, m0 + half * BLOCK_M, c, slice, store_hint);   // clipped to [rows_i, T, slices]
-            else tma_store_3d(tmO, stg, m0 + half * BLOCK_M, c, slice);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            for (int j = 0; j < 16; ++j) o[static_cast<long long>(j) * ldo] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if ((idx << 4) + j < T) o[static_cast<long long>(j) * ldo] = __uint_as_float(r[j]);
         }
-        ring = ring + 1 == OUT_STAGE_BUFS ? 0 : ring + 1;
     };
     uint32_t ra[16], rb[16];
-    tmem_ld16(taddr(0), ra);
-    for (int idx = 0; idx < total; idx += 2) {
+    tmem_ld16(tb0, ra);
+    for (int idx = 0; idx < n_chunks; idx += 2) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (idx + 1 < total) tmem_ld16(taddr(idx + 1), rb);
+        if (idx + 1 < n_chunks) tmem_ld16(tb0 + static_cast<uint32_t>((idx + 1) << 4), rb);
         else release();
         emit(ra, idx);
-        if (idx + 1 < total) {
+        if (idx + 1 < n_chunks) {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (idx + 2 < total) tmem_ld16(taddr(idx + 2), ra);
+            if (idx + 2 < n_chunks) tmem_ld16(tb0 + static_cast<uint32_t>((idx + 2) << 4), ra);
             else release();
             emit(rb, idx + 1);
         }
@@ -244,13 +219,11 @@ struct GemmParams {
     int tmem_cols, acc_stride;
     int n_bufs, buf_stride;   // accumulator double buffering in TMEM: segment s uses buffer s % n_bufs
     int b_box_bytes;          // bytes the activation TMA box(es) deliver per stage (== T_pad * 128 except in timing experiments)
-    int tma_store;            // epilogue writes through shared memory + cp.async.bulk.tensor stores (tmO*) instead of STG
     int n_mma, N_mma;         // 2-CTA kernel: the token axis (padded to 64) is covered by n_mma MMAs of N_mma columns each
     SpinGuard guard;          // bound + diagnostic record of every mbarrier wait
     GemmTrace trace;          // optional per-CTA progress words (ATSPEED_GEMM_TRACE=1)
     FusedEpi epi;             // kind != EPI_SLICES: tiles are finished inside the kernel (kernels.h)
     int l2_hints;             // TMA loads carry L2 eviction priorities (ATSPEED_GEMM_L2HINT=0: plain loads)
-    uint64_t store_hint;      // L2 eviction priority of the epilogue's bulk stores (0: none; ATSPEED_GEMM_STORE_HINT)
 };
 __device__ __forceinline__ void trace_put(const GemmTrace& t, int word, unsigned v) {
     if (t.buf != nullptr && blockIdx.x < TRACE_CTAS) {
@@ -536,8 +509,7 @@ __device__ __forceinline__ void fused_epilogue(const GemmParams& p, int worker, 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
-                const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmO0,
-                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmX1, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -689,8 +661,7 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         // ===== epilogue: TMEM -> registers -> global fp32 partial-sum slice =====
         asm volatile("griddepcontrol.wait;" ::: "memory");    // `out` may still be read by the previous consumer
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);   // staging ring
-        int st_chunk = 0;
+        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);   // fused epilogues only
         int seg = 0;
         if (p.epi.kind != EPI_SLICES) {
             fused_epilogue<false>(p, blockIdx.x, 0, u_begin, u_end, tmem_base, stage_out, accum_full, accum_empty, wc, s_pos, s_slotuser, s_kvoff);
@@ -704,38 +675,22 @@ gemm_wx_tcgen05(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             const int buf = p.n_bufs == 2 ? (seg & 1) : 0, use = p.n_bufs == 2 ? (seg >> 1) : seg;
             mbar_wait(&accum_full[buf], use & 1, wc, HANG_B_ACCUM_FULL, buf, u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (p.tma_store) {
-                const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
-                const uint32_t tb0 = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
-                drain_segment_tma(tmO, tb0, p.BM >> 7, p.T_pad >> 4, static_cast<uint32_t>(p.acc_stride), m0, slice, stage_out, st_chunk,
-                                  q * 32 + lane, threadIdx.x == 64, p.store_hint, [&]() {
-                                      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                                      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
-                                  });
-                u = seg_end;
-                continue;
-            } else
-            for (int half = 0; half < (p.BM >> 7); ++half) {
-                const int row = m0 + half * BLOCK_M + q * 32 + lane;           // output feature
-                const bool row_ok = row < p.n_rows[wid];
-                float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
-                const uint32_t tbase = tmem_base + buf * p.buf_stride + half * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-                for (int c = 0; c < p.T_pad; c += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(tbase + static_cast<uint32_t>(c), r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
-                    }
+            {
+                const int halves = p.BM >> 7;
+                for (int half = 0; half < halves; ++half) {
+                    const int row = m0 + half * BLOCK_M + q * 32 + lane;           // output feature
+                    float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
+                    const uint32_t tbase = tmem_base + buf * p.buf_stride + half * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+                    const bool last_half = half + 1 == halves;
+                    drain_segment_stg(out, p.ldo, p.T, row < p.n_rows[wid], tbase, p.T_pad >> 4, [&]() {
+                        if (!last_half) return;
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
+                    });
                 }
+                u = seg_end;
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
-            u = seg_end;
         }
-        if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -772,8 +727,7 @@ template <int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
-                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-                     const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
+                     const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -967,8 +921,7 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (threadIdx.x == 64) trace_put(p.trace, 6, 0x20000u);
         const int q = warp & 3;
-        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
-        int st_chunk = 0;
+        float* stage_out = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);   // fused epilogues only
         int seg = 0;
         const bool elected = threadIdx.x == 64;
         const int f = q * 32 + lane;
@@ -993,34 +946,17 @@ gemm_wx_tcgen05_2cta(const __grid_constant__ CUtensorMap tmW0, const __grid_cons
                 u = seg_end;
                 continue;
             }
-            const CUtensorMap* tmO = wid == 0 ? &tmO0 : (wid == 1 ? &tmO1 : &tmO2);
             const uint32_t tbase = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
-            if (p.tma_store) {
-                drain_segment_tma(tmO, tbase, 1, (min(T64, p.T) + 15) >> 4, 0u, m0, slice, stage_out, st_chunk, f, elected, p.store_hint, [&]() {
+            {
+                const int row = m0 + f;
+                float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
+                drain_segment_stg(out, p.ldo, p.T, row < p.n_rows[wid], tbase, (min(T64, p.T) + 15) >> 4, [&]() {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], lead_rank);     // the leader's MMA thread waits for all 8 warps
+                    if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], lead_rank);
                 });
                 u = seg_end;
-                continue;
             }
-            const int row = m0 + f;
-            const bool row_ok = row < p.n_rows[wid];
-            float* out = p.out + static_cast<long long>(slice) * p.slice_stride + p.colbase[wid] + row;
-            for (int c = 0; c < T64 && c < p.T; c += 16) {
-                uint32_t r[16];
-                tmem_ld16(tbase + static_cast<uint32_t>(c), r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c + j < p.T) out[static_cast<long long>(c + j) * p.ldo] = __uint_as_float(r[j]);
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) mbar_arrive_cluster(&accum_empty[buf], lead_rank);     // the leader's MMA thread waits for all 8 warps
-            u = seg_end;
         }
-        if (p.tma_store && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (elected) trace_put(p.trace, 6, 0xFFFFFu);
     }
     if (threadIdx.x == 0) trace_put(p.trace, 2, 5);
@@ -1160,7 +1096,7 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
             if (n > pl->max_slices) pl->max_slices = n;
         }
         const int stage_bytes = A_TILE_BYTES + (T64 / 2) * BLOCK_K * 2;
-        int stages = (220 * 1024 - OUT_STAGE_BYTES) / stage_bytes;
+        int stages = (220 * 1024) / stage_bytes;
         if (stages > MAX_STAGES) stages = MAX_STAGES;
         if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
         pl->stages = stages;
@@ -1210,7 +1146,7 @@ int gemm_make_plan(const GemmWeights& w, int T, int num_sms, bool allow_cut, Gem
         if (n > pl->max_slices) pl->max_slices = n;
     }
     const int stage_bytes = pl->BM * BLOCK_K * 2 + pl->T_pad * BLOCK_K * 2;
-    int stages = (220 * 1024 - OUT_STAGE_BYTES) / stage_bytes;
+    int stages = (220 * 1024) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages > pl->U) stages = pl->U < 2 ? 2 : pl->U;
     ATS_CHECK_ARG(stages >= 2, "gemm: T=%d leaves room for %d pipeline stages", T, stages);
@@ -1350,29 +1286,11 @@ int gemm_make_xmap(XMap* xm, const void* x, int T, int K, int cluster) {
     return ATS_OK;
 }
 
-// Output tensor maps of one launch: per weight a 3-D view (feature, token, slice) of the fp32 partial-sum buffer, so the
-// epilogue's bulk stores are clipped to the weight's own columns, to T tokens and to the slice.  ok = 0 when the buffer
-// does not meet TMA's 16-byte rules (odd ldo in unit tests): the kernel then falls back to its scalar-store epilogue.
+// Where one launch's fp32 partial sums go: out[slice][t][colbase_i + n], slices `slice_stride` elements apart.
 int gemm_make_omap(OMap* om, const GemmWeights& w, float* out, int ldo, long long slice_stride, int T, int max_slices) {
+    (void)w; (void)max_slices;
     memset(om, 0, sizeof(*om));
     om->out = out; om->ldo = ldo; om->slice_stride = slice_stride; om->T = T;
-    EncodeTiledFn enc = get_encode_fn();
-    if (!enc) return ATS_OK;
-    const long long sstride = max_slices > 1 ? slice_stride : static_cast<long long>(T) * ldo;
-    if ((ldo & 3) || (sstride & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return ATS_OK;
-    for (int i = 0; i < w.n; ++i) {
-        if (w.colbase[i] & 3) return ATS_OK;
-        cuuint64_t dims[3] = {static_cast<cuuint64_t>(w.rows[i]), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(max_slices)};
-        cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldo) * 4, static_cast<cuuint64_t>(sstride) * 4};
-        cuuint32_t box[3] = {128, 16, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&om->tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out + w.colbase[i], dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return ATS_OK;
-    }
-    for (int i = w.n; i < 3; ++i) om->tm[i] = om->tm[0];
-    om->ok = 1;
     return ATS_OK;
 }
 
@@ -1430,7 +1348,7 @@ static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl,
                   xm.K, pl.T, w.K);
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    if (om) { p.out = om->out; p.ldo = om->ldo; p.slice_stride = om->slice_stride; p.tma_store = om->ok; }
+    if (om) { p.out = om->out; p.ldo = om->ldo; p.slice_stride = om->slice_stride; }
     if (epi) {
         p.epi = *epi;
         ATS_CHECK_ARG(epi->part && epi->flags && epi->epoch != 0, "gemm: fused epilogue without workspace / epoch");
@@ -1455,14 +1373,10 @@ static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl,
     p.n_mma = pl.n_mma; p.N_mma = pl.N_mma;
     p.guard = spin_guard();
     { static const bool on = []() { const char* e = getenv("ATSPEED_GEMM_L2HINT"); return !(e && atoi(e) == 0); }(); p.l2_hints = on ? 1 : 0; }
-    {   // partial sums are re-read by the consumer kernel microseconds later: 1 = evict-last, 2 = evict-first, 0 = no hint
-        static const int mode = []() { const char* e = getenv("ATSPEED_GEMM_STORE_HINT"); return e ? atoi(e) : 0; }();
-        p.store_hint = mode == 1 ? L2_EVICT_LAST : (mode == 2 ? L2_EVICT_FIRST : 0ull);
-    }
     p.trace = pl.two_cta ? gemm_trace() : GemmTrace{nullptr, 0};
     const int stage_bytes = pl.two_cta ? A_TILE_BYTES + (pl.n_mma * pl.N_mma / 2) * BLOCK_K * 2
                                        : pl.BM * BLOCK_K * 2 + pl.T_pad * BLOCK_K * 2;
-    size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + OUT_STAGE_BYTES + 1024;
+    size_t smem_bytes = static_cast<size_t>(p.stages) * stage_bytes + (epi ? OUT_STAGE_BYTES : 0) + 1024;
     // One GEMM CTA per SM, always: a CTA holds its TMEM columns from prologue to exit and, with PDL and several streams,
     // CTAs of different launches overlap in time.  A CTA that was launched early (PDL) and already holds TMEM while it
     // waits for its predecessor must never share an SM with a predecessor CTA that has not allocated yet; asking for more
@@ -1495,19 +1409,16 @@ static int gemm_launch(const GemmWeights& w, const XMap& xm, const GemmPlan& pl,
     // the gate / up halves (BM/2 rows per box of a single CTA, 64 rows per CTA of a pair)
     const CUtensorMap* tw = (!pl.two_cta && pl.BM == 256) ? w.tmap256 : w.tmap;
     if (pl.epi_kind == EPI_SILU_MUL) tw = (pl.two_cta || pl.BM == 128) ? w.tmap64 : w.tmap;
-    const CUtensorMap& o0 = om ? om->tm[0] : tw[0];                     // fused launches never touch the output maps
-    const CUtensorMap& o1 = om ? om->tm[1] : tw[0];
-    const CUtensorMap& o2 = om ? om->tm[2] : tw[0];
     if (pl.two_cta) {
         ATS_CHECK_ARG((pl.cluster == 2 || pl.cluster == 4) && pl.grid % pl.cluster == 0, "gemm (CTA pairs): grid %d, cluster %d", pl.grid, pl.cluster);
         ATS_CHECK_ARG(xm.cluster == pl.cluster, "gemm: activation map built for clusters of %d, plan uses %d", xm.cluster, pl.cluster);
         if (pl.cluster == 4)
-            ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta<4>, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, o0, o1, o2, p));
+            ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta<4>, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, p));
         else
-            ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta<2>, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, o0, o1, o2, p));
+            ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05_2cta<2>, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, p));
         return ATS_OK;
     }
-    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1, o0, o1, o2, p));
+    ATS_CUDA(cudaLaunchKernelEx(&cfg, gemm_wx_tcgen05, tw[0], tw[w.n > 1 ? 1 : 0], tw[w.n > 2 ? 2 : 0], xm.tm0, xm.tm1, p));
     return ATS_OK;
 }
 

@@ -87,7 +87,7 @@ int gemm_wx_fused(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, co
 int gemm_max_slices(const GemmWeights& w, int T_max, int num_sms);
 SplitMap gemm_split_map(const GemmWeights& w, const GemmPlan& plan);
 int gemm_make_xmap(XMap* xm, const void* x, int T, int K, int cluster);   // cluster: GemmPlan::cluster of the launch that reads it
-struct OMap { CUtensorMap tm[3]; float* out; int ldo; long long slice_stride; int T; int ok; };   // fp32 partial-sum output
+struct OMap { float* out; int ldo; long long slice_stride; int T; };   // fp32 partial-sum output: out[slice][t][column]
 int gemm_make_omap(OMap* om, const GemmWeights& w, float* out, int ldo, long long slice_stride, int T, int max_slices);
 int gemm_wx(const GemmWeights& w, const XMap& xm, const GemmPlan& plan, const OMap& om, cudaStream_t stream);
 bool pdl_enabled();   // ATSPEED_PDL=0 disables programmatic dependent launch (debugging)

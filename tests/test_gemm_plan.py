@@ -44,11 +44,11 @@ def test_plan_tiles_the_work_and_slice_counts_agree(K, rows, T, cut, pair, monke
         if two_cta:
             assert BM == 256 and grid % 2 == 0 and (grid <= sms or not cut)
             assert n_mma in (1, 2) and N_mma % 16 == 0 and N_mma <= 256 and n_mma * N_mma >= T > n_mma * N_mma - 32
-            assert stages * (16384 + (n_mma * N_mma // 2) * 128) + 24576 <= 220 * 1024
+            assert stages * (16384 + (n_mma * N_mma // 2) * 128) <= 220 * 1024
             assert bufs * n_mma * N_mma <= 512
         else:
             assert grid <= sms or not cut        # persistent: at most one CTA per SM when tiles may be cut
-            assert stages * (BM * 128 + T_pad * 128) + 24576 <= 220 * 1024
+            assert stages * (BM * 128 + T_pad * 128) <= 220 * 1024
             assert (BM // 128) * bufs * T_pad <= 512
         if not cut:
             assert U % KB == 0 and max_slices == 1
@@ -94,5 +94,5 @@ def test_every_token_count_has_a_sane_plan(pair, monkeypatch):
             workers = grid // 2 if two else grid
             assert (workers - 1) * U < units <= workers * U and grid <= 148, (name, T)
             stage = 16384 + (n_mma * N_mma // 2) * 128 if two else BM * 128 + T_pad * 128
-            assert 2 <= stages and stages * stage + 24576 + 1024 <= 226 * 1024, (name, T)
+            assert 2 <= stages and stages * stage + 1024 <= 226 * 1024, (name, T)
             assert tmem <= 512 and (bufs * n_mma * N_mma <= 512 if two else (BM // 128) * bufs * T_pad <= 512), (name, T)
