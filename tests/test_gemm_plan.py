@@ -96,3 +96,46 @@ def test_every_token_count_has_a_sane_plan(pair, monkeypatch):
             stage = 16384 + (n_mma * N_mma // 2) * 128 if two else BM * 128 + T_pad * 128
             assert 2 <= stages and stages * stage + 1024 <= 226 * 1024, (name, T)
             assert tmem <= 512 and (bufs * n_mma * N_mma <= 512 if two else (BM // 128) * bufs * T_pad <= 512), (name, T)
+
+
+@pytest.mark.parametrize("K,rows", [(4096, (4096, 4096, 4096)), (4096, (4096,)), (4096, (11008, 11008)), (11008, (4096,)),
+                                    (4096, (32859,)), (768, (768, 768, 768)), (768, (3072, 3072)), (3072, (768,))])
+@pytest.mark.parametrize("T", [257, 289, 300, 400, 481, 512])
+@pytest.mark.parametrize("cut", [1, 0])
+def test_cluster_of_four_plans(K, rows, T, cut, monkeypatch):
+    """ATSPEED_GEMM_CLUSTER=4 (opt-in): the worker is a cluster of two CTA pairs on adjacent tiles, the work unit a
+    (super-tile, k-block).  Without a device the plan takes num_sms / 4 workers; the unit ranges must tile the super-tile x
+    k-block space and a column's slice count must be the number of workers whose range touches its SUPER-tile."""
+    from atspeed_b200 import _lib
+    lib = _lib.load()
+    monkeypatch.delenv("ATSPEED_GEMM_2CTA", raising=False)
+    monkeypatch.setenv("ATSPEED_GEMM_CLUSTER", "4")
+    r = list(rows) + [0] * (3 - len(rows))
+    info = (C.c_int32 * 16)()
+    cols = sum(rows)
+    sl = (C.c_int32 * cols)()
+    for sms in (148, 132):
+        assert lib.atspeed_gemm_plan(T, K, r[0], r[1], r[2], sms, cut, info, sl) == 0, lib.atspeed_last_error()
+        BM, KB, tiles, U, grid, max_slices, stages, tmem, bufs, T_pad = (int(info[i]) for i in range(10))
+        two_cta, n_mma, N_mma = (int(info[i]) for i in (13, 14, 15))
+        assert two_cta == 1 and BM == 256 and tiles == sum(-(-x // 256) for x in rows)
+        if tiles < 2:
+            continue                                   # a single tile keeps the pair kernel (nothing to share)
+        assert grid % 4 == 0 and (grid <= sms or not cut)
+        n_super = -(-tiles // 2)
+        units, workers = n_super * KB, grid // 4
+        assert (workers - 1) * U < units <= workers * U
+        # token padding: a CTA's multicast box holds N_mma / 4 tokens, a whole number of 8-row swizzle atoms
+        assert N_mma % 32 == 0 and n_mma * N_mma >= T > n_mma * N_mma - 64
+        assert stages * (16384 + (n_mma * N_mma // 2) * 128) <= 220 * 1024 and bufs * n_mma * N_mma <= 512
+        slices = np.frombuffer(sl, dtype=np.int32)
+        col, t = 0, 0
+        for w in rows:
+            for i in range(-(-w // 256)):
+                st = t // 2
+                lo, hi = st * KB, (st + 1) * KB - 1
+                expect = hi // U - lo // U + 1
+                assert (slices[col: col + min(256, w - i * 256)] == expect).all(), (K, rows, T, sms, t)
+                col += min(256, w - i * 256)
+                t += 1
+        assert max_slices == max(int(slices.max()), 1) or not cut

@@ -66,6 +66,37 @@ def test_gemm_tcgen05_matches_torch(lib, T, K, rows):
     assert torch.equal(outs[0][:, : sum(rows)], outs[1][:, : sum(rows)]), "run-to-run nondeterminism"
 
 
+@pytest.mark.parametrize("T,K,rows", [(289, 4096, (4096, 4096, 4096)), (300, 3072, (768,)), (400, 4096, (11008, 11008)),
+                                      (481, 4096, (32859,)), (512, 768, (3072, 3072)), (512, 11008, (4096,))])
+def test_gemm_cluster_of_four_matches_pairs_bit_for_bit(lib, T, K, rows, monkeypatch):
+    """ATSPEED_GEMM_CLUSTER=4 (opt-in): two CTA pairs per cluster on adjacent tiles, the activation tiles fetched once per cluster
+    and multicast to the twin CTA.  Every output element is the same sequence of MMAs over the same k-blocks as in the pair
+    kernel; only the cut points of the k-range differ (fewer workers), so the result is compared with torch fp32 and must be
+    deterministic run to run.  (On a B200 33 clusters of 4 can be resident; the plan uses that many workers.)"""
+    monkeypatch.setenv("ATSPEED_GEMM_CLUSTER", "4")
+    g = torch.Generator(device="cuda").manual_seed(T * 7 + K)
+    x = (torch.randn(T, K, generator=g, device="cuda") * 0.5).to(torch.bfloat16)
+    ws = [(torch.randn(r, K, generator=g, device="cuda") * 0.5).to(torch.bfloat16) for r in rows]
+    cols = sum(rows)
+    ptr = [w.data_ptr() for w in ws] + [None] * (3 - len(ws))
+    rr = list(rows) + [0] * (3 - len(rows))
+    nbytes = C.c_size_t(0)
+    _check(lib, lib.atspeed_gemm_scratch_bytes(T, K, rr[0], rr[1], rr[2], C.byref(nbytes)))
+    scratch = torch.full((nbytes.value // 4,), float("nan"), device="cuda", dtype=torch.float32)
+    outs = []
+    for _ in range(2):
+        out = torch.full((T, cols), float("nan"), device="cuda", dtype=torch.float32)
+        _check(lib, lib.atspeed_gemm_bf16(x.data_ptr(), T, K, ptr[0], rr[0], ptr[1], rr[1], ptr[2], rr[2],
+                                          scratch.data_ptr(), out.data_ptr(), cols, _stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = x.float() @ torch.cat(ws).float().T
+    assert torch.isfinite(outs[0]).all(), "unwritten outputs"
+    err = (outs[0] - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+    assert torch.equal(outs[0], outs[1]), "run-to-run nondeterminism"
+
+
 # ---------------------------------------------------------------------------------------------------
 # kernel (a)
 # ---------------------------------------------------------------------------------------------------
