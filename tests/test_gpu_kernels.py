@@ -68,7 +68,7 @@ def test_gemm_tcgen05_matches_torch(lib, T, K, rows):
 
 @pytest.mark.parametrize("T,K,rows", [(289, 4096, (4096, 4096, 4096)), (300, 3072, (768,)), (400, 4096, (11008, 11008)),
                                       (481, 4096, (32859,)), (512, 768, (3072, 3072)), (512, 11008, (4096,))])
-def test_gemm_cluster_of_four_matches_pairs_bit_for_bit(lib, T, K, rows, monkeypatch):
+def test_gemm_cluster_of_four_matches_torch(lib, T, K, rows, monkeypatch):
     """ATSPEED_GEMM_CLUSTER=4 (opt-in): two CTA pairs per cluster on adjacent tiles, the activation tiles fetched once per cluster
     and multicast to the twin CTA.  Every output element is the same sequence of MMAs over the same k-blocks as in the pair
     kernel; only the cut points of the k-range differ (fewer workers), so the result is compared with torch fp32 and must be

@@ -3,12 +3,12 @@
 # test (sharded users -> NCCL all-gather -> Recall/NDCG identical on every rank and equal to the reference's).
 # usage: gpurun --gpus N -- 'bash tools/gpu_job_r02h.sh N'
 N=${1:-2}
-TAG=r02h_n$N
+TAG=${2:-r02h}_n$N
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 600 python -m pytest tests/test_zz_gpu_sharded_metrics.py -q -s > $O/sharded_metrics_$TAG.log 2>&1; echo "sharded metrics rc=$?"; grep -E "passed|failed|skipped|Recall|identical" $O/sharded_metrics_$TAG.log | tail -5
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 \
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 12 --warmup 4 \
     > $O/bench_$TAG.log 2> $O/bench_$TAG.err; echo "bench N=$N rc=$?"
 python - <<PY
 import json
