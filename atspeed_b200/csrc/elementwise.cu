@@ -24,21 +24,6 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;
 }
 
-// sum of a column chunk's partial-sum slices 1..splits-1 added to `acc` IN SLICE ORDER (deterministic), with the loads of up
-// to four slices in flight at once: a `for (s...) acc += load(s)` loop issues one load per L2/HBM round trip, and these
-// kernels are latency-bound (one wave of CTAs, profiles/r02_ncu_rowwise_attention_cohort.txt)
-__device__ __forceinline__ void add_slices4(float4& acc, const float* __restrict__ base, long long split_stride, int splits) {
-    for (int s0 = 1; s0 < splits; s0 += 4) {
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (s0 + k < splits) v[k] = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(s0 + k) * split_stride));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (s0 + k < splits) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
-    }
-}
-
 // a[k] = sum over the ns[k] partial-sum slices of the 4 columns at base[k], IN SLICE ORDER (deterministic, the order every
 // consumer has always used), for N column groups at once: the loads of slice s of ALL groups are issued before any of them is
 // used, slices 0 and 1 together.  Per-group loops (add_slices4 once per group) made a thread wait for one HBM round trip per
@@ -382,7 +367,7 @@ __global__ void silu_mul_kernel(const float* __restrict__ part, SplitMap sm, lon
 // computed once).  All 2 * NR * min(slices, 2) 16-byte loads of a thread are issued before the first is used: with one row per
 // thread the kernel kept ~50 KB in flight per SM and streamed 2.2 TB/s (tools/rowwise_bench.py); HBM at full rate needs ~100 KB.
 template <int NR>
-__global__ void __launch_bounds__(256, NR == 4 ? 2 : (NR == 2 ? 3 : 4))
+__global__ void __launch_bounds__(256, 3)
 silu_mul_vec_kernel(const float* __restrict__ part, SplitMap sm, long long split_stride, int ldp, int T, int mlp,
                     __nv_bfloat16* __restrict__ m) {
     pdl_launch_dependents();
@@ -419,14 +404,9 @@ silu_mul_vec_kernel(const float* __restrict__ part, SplitMap sm, long long split
 int silu_mul(const float* part, const SplitMap& sm, long long split_stride, int ldp, int T, int mlp, __nv_bfloat16* m,
              cudaStream_t st) {
     if ((mlp & 3) == 0 && (ldp & 3) == 0 && (split_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0) {
-        static const int nr = []() { const char* e = getenv("ATSPEED_SILU_NR"); return e ? atoi(e) : 2; }();
-        const int gy = (mlp / 4 + 255) / 256;
-        if (nr >= 4)
-            ATS_CUDA(launch_pdl(silu_mul_vec_kernel<4>, dim3((T + 3) / 4, gy), dim3(256), 0, st, part, sm, split_stride, ldp, T, mlp, m));
-        else if (nr >= 2)
-            ATS_CUDA(launch_pdl(silu_mul_vec_kernel<2>, dim3((T + 1) / 2, gy), dim3(256), 0, st, part, sm, split_stride, ldp, T, mlp, m));
-        else
-            ATS_CUDA(launch_pdl(silu_mul_vec_kernel<1>, dim3(T, gy), dim3(256), 0, st, part, sm, split_stride, ldp, T, mlp, m));
+        constexpr int NR = 2;
+        ATS_CUDA(launch_pdl(silu_mul_vec_kernel<NR>, dim3((T + NR - 1) / NR, (mlp / 4 + 255) / 256), dim3(256), 0, st, part, sm, split_stride,
+                            ldp, T, mlp, m));
         return ATS_OK;
     }
     ATS_CUDA(launch_pdl(silu_mul_kernel, dim3(T), dim3(256), 0, st, part, sm, split_stride, ldp, mlp, m));
