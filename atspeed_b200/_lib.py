@@ -59,6 +59,7 @@ SYMBOLS = {
     "atspeed_session_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "atspeed_session_sort_result": (C.c_int, [C.c_void_p, C.c_void_p]),
     "atspeed_session_set_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "atspeed_session_set_shared_prefix": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, C.c_void_p]),
     "atspeed_noise_stream": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]),
     "atspeed_noise_host_u32": (C.c_uint32, [C.c_uint64, C.c_uint64, C.c_uint32]),
     "atspeed_noise_fill": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

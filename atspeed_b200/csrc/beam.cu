@@ -49,7 +49,8 @@ __device__ void tree_build_batch_body(const TreeDev& t, const BatchDev& b, const
     const int gen0 = t.scal[SC_GEN0];
     const int miss_n = t.scal[SC_MISS];
     const int trash0 = g.tree_slot(P, MAX_LEVELS, 0);    // K trash slots after the last level, for padded entries
-    const int n_prompt = plan.with_prompt ? P : 0;
+    const int skip = plan.with_prompt ? plan.prompt_skip : 0;
+    const int n_prompt = plan.with_prompt ? P - skip : 0;
     const int n_miss = plan.with_missing ? g.K : 0;
     for (int x = threadIdx.x; x < T_cap; x += blockDim.x) {
         int tok = 0, pos = 0, slot = 0, prefix = 0;
@@ -58,7 +59,7 @@ __device__ void tree_build_batch_body(const TreeDev& t, const BatchDev& b, const
         for (int w = 0; w < VIS_WORDS; ++w) vis[w] = 0u;
         int y = x - n_prompt;
         if (x < n_prompt) {                               // causal prompt token (the batch arrays are reused by every forward)
-            tok = prompt[x]; pos = x; slot = x; prefix = x + 1;
+            tok = prompt[x + skip]; pos = x + skip; slot = x + skip; prefix = x + skip + 1;
         } else if (y < n_miss) {
             if (y < miss_n) {
                 tok = t.miss_tok[y]; pos = t.miss_pos[y]; slot = t.miss_slot[y]; prefix = P;
@@ -97,7 +98,7 @@ __device__ void tree_build_batch_body(const TreeDev& t, const BatchDev& b, const
         int idx = 0, node = -1;
         int y = r;
         if (plan.root_row) {
-            if (y == 0) { idx = P - 1; node = t.node[0]; y = -1; }
+            if (y == 0) { idx = P - 1 - skip; node = t.node[0]; y = -1; }
             else y -= 1;
         }
         if (y >= 0) {
@@ -918,6 +919,24 @@ __global__ void cohort_build_batch_kernel(Cohort c, const TreeDev* __restrict__ 
     const UserCtx& u = c.u[blockIdx.x];
     tree_build_batch_body(trees[u.tree], b, g, u.plan, prompts + static_cast<long long>(u.tree) * prompt_stride, u.P, u.T, u.R,
                           u.tok0, u.row0, static_cast<int>(blockIdx.x));
+}
+
+// every user's prompt row must start with the n shared-prefix tokens (row `prefix_row` of prompts): *bad |= 1 otherwise
+__global__ void cohort_check_prefix_kernel(Cohort c, const int* __restrict__ prompts, int prompt_stride, int prefix_row, int n,
+                                           int* __restrict__ bad) {
+    const UserCtx& u = c.u[blockIdx.x];
+    const int* mine = prompts + static_cast<long long>(u.tree) * prompt_stride;
+    const int* pre = prompts + static_cast<long long>(prefix_row) * prompt_stride;
+    bool ok = u.P > n;
+    for (int i = threadIdx.x; i < n && i < u.P; i += blockDim.x) ok = ok && mine[i] == pre[i];
+    if (!ok) atomicOr(bad, 1);
+}
+
+int cohort_check_prefix(const Cohort& c, const int* prompts, int prompt_stride, int prefix_row, int n, int* bad, cudaStream_t st) {
+    ATS_CHECK_ARG(c.n >= 1 && c.n <= MAX_USERS, "cohort of %d users", c.n);
+    cohort_check_prefix_kernel<<<c.n, 64, 0, st>>>(c, prompts, prompt_stride, prefix_row, n, bad);
+    ATS_LAUNCH_CHECK();
+    return ATS_OK;
 }
 
 int cohort_build_batch(const Cohort& c, const TreeDev* trees, const BatchDev& b, const TreeGeom& g, const int* prompts,

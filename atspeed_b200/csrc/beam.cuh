@@ -84,6 +84,8 @@ struct BatchPlan {
     int width;         // cap of levels >= 1
     int rows_from;     // first level whose tokens produce logits rows; with_prompt adds the root row (P-1)
     int root_row;      // 1: emit the prompt's last position as row 0 (first round)
+    int prompt_skip;   // with_prompt: the first prompt_skip prompt tokens are NOT in the batch -- their K/V already sit in the
+                       // user's cache (shared prompt prefix, atspeed_session_set_shared_prefix); 0 otherwise
 };
 int tree_build_batch(const TreeDev& t, const BatchDev& b, const TreeGeom& g, const BatchPlan& plan, const int* prompt,
                      int P, int T_cap, int R_cap, cudaStream_t st);
@@ -117,6 +119,7 @@ struct Cohort {
 int cohort_begin(const Cohort& c, const TreeDev* trees, cudaStream_t st);
 int cohort_build_batch(const Cohort& c, const TreeDev* trees, const BatchDev& b, const TreeGeom& g, const int* prompts,
                        int prompt_stride, cudaStream_t st);
+int cohort_check_prefix(const Cohort& c, const int* prompts, int prompt_stride, int prefix_row, int n, int* bad, cudaStream_t st);
 // select / verify for every user of the cohort whose mode asks for it; candidates are read from cand_* rows
 // [row0, row0 + R) of each user with row stride B
 int cohort_select(const Cohort& c, const TreeDev* trees, const TreeGeom& g, const TrieCSR& trie, int B, const int* cand_tok,

@@ -49,7 +49,8 @@ void plan_draft_step(const atspeed_session* s, const UserRun& u, UserCtx& x, int
     x.level = u.j; x.width = g.N; x.mode = 1; x.is_draft = 1; x.draft_len = 0; x.root_rows = 0;
     if (u.j == 0 && u.first) {
         x.plan.with_prompt = 1; x.plan.l_from = 1; x.plan.l_to = 0; x.plan.rows_from = 1; x.plan.root_row = 1; x.plan.width = g.N;
-        x.T = u.P; x.R = 1; S = u.P;
+        x.plan.prompt_skip = s->prefix_len;
+        x.T = u.P - s->prefix_len; x.R = 1; S = u.P;
     } else {
         const bool with_missing = u.j == 0 && u.miss;
         x.plan.with_missing = with_missing ? 1 : 0;
@@ -69,7 +70,8 @@ void plan_target(const atspeed_session* s, const UserRun& u, UserCtx& x, int& S)
         x.level = 0; x.width = g.K; x.mode = 1; x.draft_len = 0; x.root_rows = 0;
         if (u.first) {
             x.plan.with_prompt = 1; x.plan.l_from = 1; x.plan.l_to = 0; x.plan.rows_from = 1; x.plan.root_row = 1; x.plan.width = g.K;
-            x.T = u.P; x.R = 1; S = u.P;
+            x.plan.prompt_skip = s->prefix_len;
+            x.T = u.P - s->prefix_len; x.R = 1; S = u.P;
         } else {
             x.plan.l_from = x.plan.l_to = x.plan.rows_from = 0; x.plan.width = g.K;
             x.T = g.K; x.R = g.K; S = g.tree_slot(u.P, 0, 0) + g.K;
@@ -80,7 +82,8 @@ void plan_target(const atspeed_session* s, const UserRun& u, UserCtx& x, int& S)
     x.plan.width = g.N;
     if (u.first) {
         x.plan.with_prompt = 1; x.plan.l_from = 1; x.plan.l_to = u.dl; x.plan.rows_from = 1; x.plan.root_row = 1;
-        x.T = u.P + u.dl * g.N; x.R = 1 + u.dl * g.N;
+        x.plan.prompt_skip = s->prefix_len;
+        x.T = u.P - s->prefix_len + u.dl * g.N; x.R = 1 + u.dl * g.N;
     } else {
         x.plan.l_from = 0; x.plan.l_to = u.dl; x.plan.rows_from = 0;
         x.T = g.K + u.dl * g.N; x.R = x.T;
@@ -145,14 +148,18 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
         ATS_CHECK_ARG(P >= 1 && P <= s->cfg.max_prompt, "prompt %d: length %d outside [1,%d]", i, P, s->cfg.max_prompt);
         ATS_CHECK_ARG(P + (L - 1) * g.N <= s->T_max && P + K <= s->T_max, "prompt %d: %d + %d tree tokens exceed the %d-token forward",
                       i, P, (L - 1) * g.N, s->T_max);
+        ATS_CHECK_ARG(P > s->prefix_len, "prompt %d: length %d does not exceed the shared prefix (%d tokens)", i, P, s->prefix_len);
         poff[i + 1] = poff[i] + P;
     }
+    if (s->prefix_len > 0) ATS_CUDA(cudaMemsetAsync(s->prefix_bad_dev, 0, sizeof(int), static_cast<cudaStream_t>(stream)));
     // pinned staging (owned by the session) for the per-step outcomes and the final beams of one cohort
     ATS_CHECK_ARG(s->cohort_pinned, "session has no cohort staging buffer");
     int* h_collect = s->cohort_pinned;
     int* h_tok = h_collect + MAX_USERS * 4;
     int* h_cnt = h_tok + MAX_USERS * MAX_K * MAX_NEW;
     float* h_score = reinterpret_cast<float*>(h_cnt + MAX_USERS);
+    int* h_prefix_bad = reinterpret_cast<int*>(h_score + MAX_USERS * MAX_K);
+    *h_prefix_bad = 0;
 
     static const bool log_packs = []() { const char* e = getenv("ATSPEED_COHORT_LOG"); return e && atoi(e) == 1; }();   // diagnostics
     static const bool pack_defer = []() { const char* e = getenv("ATSPEED_COHORT_DEFER"); return !(e && atoi(e) == 0); }();   // A/B: 0 = run every pack at once
@@ -190,10 +197,26 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
                 ++c.n;
                 act.push_back(u);
                 ++next;
+                if (s->prefix_len > 0) {
+                    // the shared prefix's K/V rows -> slots [0, prefix_len) of this user's caches (kernel (c), out of place)
+                    for (ModelRT* m : {&s->tgt, &s->dft}) {
+                        const long long per_user = (m == &s->tgt ? s->kv_user_elems_tgt : s->kv_user_elems_dft) * m->elem_bytes;
+                        uint8_t* base = m->f32 ? reinterpret_cast<uint8_t*>(m->fkv) : reinterpret_cast<uint8_t*>(m->kv);
+                        PROF(s, CAT_GATHER, 0,
+                             kv_gather_rows_oop(base + static_cast<long long>(U) * per_user, base + static_cast<long long>(u.slot) * per_user,
+                                                m->kv_plane * m->elem_bytes, m->kv_plane * m->elem_bytes, m->d.n_layers * 2,
+                                                m->HD * m->elem_bytes, s->prefix_iota_dev, s->prefix_iota_dev, nullptr, s->prefix_len, st));
+                        s->launches += 1;
+                    }
+                }
             }
             if (c.n > 0) {
                 PROF(s, CAT_BEAM, 0, cohort_begin(c, s->trees_dev, st));
                 s->launches += 1;
+                if (s->prefix_len > 0) {
+                    PROF(s, CAT_BEAM, 0, cohort_check_prefix(c, s->prompts_dev, s->cfg.max_prompt, U, s->prefix_len, s->prefix_bad_dev, st));
+                    s->launches += 1;
+                }
             }
         }
         // ---- draft: every user with draft steps left runs its next step; repeat until none has ----
@@ -328,11 +351,14 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
             PROF(s, CAT_BEAM, 0, cohort_collect(pk.c, s->trees_dev, s->collect_dev, st));
             s->launches += 1;
             ATS_CUDA(cudaMemcpyAsync(h_collect, s->collect_dev, sizeof(int) * 4 * pk.c.n, cudaMemcpyDeviceToHost, st));
+            if (s->prefix_len > 0) ATS_CUDA(cudaMemcpyAsync(h_prefix_bad, s->prefix_bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
             // users that finish in this pack: results straight away (their slots are refilled next step)
             Cohort fin;
             memset(&fin, 0, sizeof(fin));
             std::vector<int> fin_who;
             ATS_CUDA(cudaStreamSynchronize(st));
+            ATS_CHECK_ARG(s->prefix_len == 0 || *h_prefix_bad == 0,
+                          "a prompt does not start with the %d tokens given to atspeed_session_set_shared_prefix", s->prefix_len);
             for (int i = 0; i < pk.c.n; ++i) {
                 UserRun& u = act[pk.who[i]];
                 u.tf += 1;
@@ -398,6 +424,56 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
         const int per_user = static_cast<int>((s->launches - l0) / n_users);
         for (int i = 0; i < n_users; ++i) stats[i].kernel_launches = per_user;
     }
+    return ATS_OK;
+}
+
+// Shared prompt prefix: every prompt of the reference's datasets opens with the same instruction template (39 tokens of ~105 on
+// Beauty / Games).  Its K/V rows do not depend on the user, so they are computed ONCE per session and model here -- one forward
+// of the prefix in the extra user slot -- and copied into a user's caches on admission; the user's own forwards then start at
+// token `n`.  Exact in the fp32 parity mode; in bf16 the prefix rows come from a forward of a different size, which may flip
+// the same near-ties any other batch-composition change does.  n = 0 switches it off.
+extern "C" int atspeed_session_set_shared_prefix(atspeed_session* s, const int32_t* prefix_host, int32_t n, void* stream) {
+    ATS_CHECK_ARG(s && s->max_users > 1, "a shared prefix needs a cohort session (max_users > 1)");
+    ATS_CHECK_ARG(n >= 0 && n < s->cfg.max_prompt && n <= s->T_max && (n == 0 || prefix_host), "shared prefix of %d tokens", n);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    s->prefix_len = 0;
+    if (n == 0) return ATS_OK;
+    const int U = s->max_users;
+    {
+        std::vector<int> iota(s->cfg.max_prompt);
+        for (int i = 0; i < s->cfg.max_prompt; ++i) iota[i] = i;
+        ATS_CUDA(cudaMemcpyAsync(s->prefix_iota_dev, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice, st));
+        ATS_CUDA(cudaMemcpyAsync(s->prompts_dev + static_cast<long long>(U) * s->cfg.max_prompt, prefix_host, sizeof(int) * n,
+                                 cudaMemcpyHostToDevice, st));
+        ATS_CUDA(cudaStreamSynchronize(st));          // the host vectors go out of scope
+    }
+    Cohort c;
+    memset(&c, 0, sizeof(c));
+    c.n = 1; c.u[0].tree = U; c.u[0].P = n;
+    ATS_TRY(cohort_begin(c, s->trees_dev, st));
+    for (ModelRT* m : {&s->tgt, &s->dft}) {
+        if (m == &s->dft && !s->has_draft) continue;
+        Pack pk;
+        memset(&pk.c, 0, sizeof(pk.c));
+        UserCtx& x = pk.c.u[0];
+        x.plan.with_prompt = 1; x.plan.l_from = 1; x.plan.l_to = 0; x.plan.rows_from = 1; x.plan.root_row = 1; x.plan.width = s->geom.K;
+        x.level = 0; x.width = s->geom.K; x.mode = 0;
+        x.tree = U; x.P = n; x.tok0 = 0; x.row0 = 0; x.T = n; x.R = 1;
+        pk.c.n = 1; pk.T = n; pk.R = 1;
+        CohortKV ckv;
+        memset(&ckv, 0, sizeof(ckv));
+        ckv.n = 1;
+        ckv.kv_off[0] = static_cast<long long>(U) * (m == &s->tgt ? s->kv_user_elems_tgt : s->kv_user_elems_dft);
+        ckv.S[0] = n; ckv.vis_base[0] = n; ckv.tok0[0] = 0; ckv.T[0] = n;
+        ATS_TRY(cohort_build_batch(pk.c, s->trees_dev, s->batch, s->geom, s->prompts_dev, s->cfg.max_prompt, st));
+        BatchDesc b;
+        memset(&b, 0, sizeof(b));
+        b.tok = s->batch.tok; b.pos = s->batch.pos; b.slot = s->batch.slot; b.prefix_len = s->batch.prefix_len;
+        b.vis = s->batch.vis; b.vis_base = 0; b.n_valid = nullptr; b.tok_user = s->batch.tok_user; b.ckv = ckv;
+        ATS_TRY(forward(s, *m, b, n, n, s->batch.rows_idx, 1, st));
+    }
+    ATS_CUDA(cudaStreamSynchronize(st));
+    s->prefix_len = n;
     return ATS_OK;
 }
 

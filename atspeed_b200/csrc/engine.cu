@@ -203,14 +203,15 @@ static void carve_tree(Carver& c, TreeDev& t) {
 
 static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_desc* target, const atspeed_model_desc* draft) {
     const int U = s->max_users;
-    carve_model(c, s->tgt, *target, s->T_max, s->R_max, s->S_max, s->num_sms, U);
-    if (draft) carve_model(c, s->dft, *draft, s->T_max, s->R_max, s->S_max, s->num_sms, U);
+    const int UX = U > 1 ? U + 1 : U;               // cohort sessions: one more slot (trees, prompts, KV) for the shared prompt prefix
+    carve_model(c, s->tgt, *target, s->T_max, s->R_max, s->S_max, s->num_sms, UX);
+    if (draft) carve_model(c, s->dft, *draft, s->T_max, s->R_max, s->S_max, s->num_sms, UX);
     s->kv_user_elems_tgt = static_cast<long long>(target->n_layers) * 2 * s->tgt.kv_plane;
     s->kv_user_elems_dft = draft ? static_cast<long long>(draft->n_layers) * 2 * s->dft.kv_plane : 0;
-    s->trees_host.resize(U);
-    for (int u = 0; u < U; ++u) carve_tree(c, s->trees_host[u]);
+    s->trees_host.resize(UX);
+    for (int u = 0; u < UX; ++u) carve_tree(c, s->trees_host[u]);
     s->tree = s->trees_host[0];                     // the single-user stages drive user slot 0
-    s->trees_dev = c.take<TreeDev>(U);
+    s->trees_dev = c.take<TreeDev>(UX);
     BatchDev& b = s->batch;
     b.tok = c.take<int>(s->T_max);
     b.pos = c.take<int>(s->T_max);
@@ -225,8 +226,10 @@ static void carve_session(Carver& c, atspeed_session* s, const atspeed_model_des
     s->cand_logp = c.take<float>(static_cast<size_t>(s->R_max) * MAX_BEAMS);
     s->cand_cnt = c.take<int>(s->R_max);
     s->lse = c.take<float>(s->R_max);
-    s->prompts_dev = c.take<int>(static_cast<size_t>(U) * s->cfg.max_prompt);
+    s->prompts_dev = c.take<int>(static_cast<size_t>(UX) * s->cfg.max_prompt);
     s->prompt_dev = s->prompts_dev;
+    s->prefix_iota_dev = c.take<int>(s->cfg.max_prompt);
+    s->prefix_bad_dev = c.take<int>(1);
     s->fused_part = c.take<float>(gemm_fused_part_elems(s->T_max, s->num_sms));
     s->fused_flags = c.take<unsigned int>(1024);
     s->collect_dev = c.take<int>(U * 4);
@@ -585,7 +588,7 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
     int r = build_model(s->tgt, sms);
     if (r == ATS_OK && draft) r = build_model(s->dft, sms);
     if (r != ATS_OK) { delete s; return r; }
-    if (cudaMemcpy(s->trees_dev, s->trees_host.data(), sizeof(TreeDev) * s->max_users, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMemcpy(s->trees_dev, s->trees_host.data(), sizeof(TreeDev) * s->trees_host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("uploading the per-user tree table failed");
         delete s;
         return ATS_ERR_CUDA;
@@ -598,8 +601,8 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
     memset(s->pinned, 0, 64 * sizeof(int));
     s->cohort_pinned = nullptr;
     if (s->max_users > 1 &&
-        cudaMallocHost(&s->cohort_pinned, sizeof(int) * (MAX_USERS * 4 + MAX_USERS * MAX_K * MAX_NEW + MAX_USERS) +
-                                              sizeof(float) * MAX_USERS * MAX_K) != cudaSuccess) {
+        cudaMallocHost(&s->cohort_pinned, sizeof(int) * (MAX_USERS * 4 + MAX_USERS * MAX_K * MAX_NEW + MAX_USERS + 4) +
+                                              sizeof(float) * MAX_USERS * MAX_K) != cudaSuccess) {   // + the shared-prefix flag
         set_error("cudaMallocHost failed");
         cudaFreeHost(s->pinned);
         delete s;
@@ -613,6 +616,7 @@ int atspeed_session_create(const atspeed_model_desc* target, const atspeed_model
         if (s->sample_B > MAX_BEAMS) s->sample_B = MAX_BEAMS;
     }
     s->launches = 0;
+    s->prefix_len = 0;
     s->fused_epoch = 0;
     // opt-in (ATSPEED_FUSED_EPI=1): correct on every tile path (tests/test_gpu_fused_epilogue.py) but measured SLOWER than the
     // row-wise consumer kernels (124 vs 139 users/s, profiles/r02_fused_epilogue_ab.txt): with one TMEM accumulator at T > 256

@@ -59,6 +59,11 @@ struct atspeed_session {
     float* res_score_dev;                        // [max_users][K]
     long long kv_user_elems_tgt, kv_user_elems_dft;   // elements between two users' KV caches
     int* cohort_pinned;                          // pinned host staging of the cohort scheduler
+    // shared prompt prefix (atspeed_session_set_shared_prefix): user slot `max_users` of trees / prompts / KV caches holds the
+    // prefix; its K/V rows are copied into a user's caches when the user is admitted and the user's forwards skip those tokens
+    int prefix_len;
+    int* prefix_iota_dev;                        // 0, 1, ..., max_prompt - 1
+    int* prefix_bad_dev;                         // != 0: a device-resident prompt did not start with the prefix
     // fused GEMM epilogues (gemm.cu FusedEpi): in-kernel partial-sum workspace, per-CTA flags, launch epoch
     float* fused_part;
     unsigned int* fused_flags;

@@ -210,6 +210,17 @@ class Session:
                                              C.byref(st), self._stream()))
         return self._collect(st)
 
+    def set_shared_prefix(self, prefix_ids: Sequence[int]) -> int:
+        """Cohort sessions: the tokens every prompt of the coming bssd_batch* calls starts with (the instruction template of
+        the reference's prompts).  Their K/V rows are computed once here and copied into each user's caches on admission; a
+        prompt that does not start with them makes the call fail.  Empty = off.  Returns the prefix length in use."""
+        arr = np.ascontiguousarray(np.asarray(list(prefix_ids), dtype=np.int32))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.atspeed_session_set_shared_prefix(self.handle, arr.ctypes.data_as(_lib.c_i32p), int(arr.shape[0]),
+                                                                  self._stream()))
+        self.shared_prefix = int(arr.shape[0])
+        return self.shared_prefix
+
     def bssd_batch(self, prompts: Sequence[Sequence[int]], gamma: int) -> List[Dict]:
         """Cohort mode (Session(max_users > 1)): speculative beam search for all `prompts`, up to max_users of them in
         flight at a time with their trees packed into shared forwards.  Returns one dict per prompt, in order."""

@@ -91,6 +91,8 @@ def parse():
     ap.add_argument("--cohort-tokens", type=int, default=512, help="most tokens one cohort forward packs (256..512)")
     ap.add_argument("--do-sample", action="store_true", help="AtSpeed-R relaxed acceptance (configs[2]) instead of AtSpeed-S")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shared-prefix", action="store_true",
+                    help="cohort mode: do not share the K/V of the prompts' common opening tokens (the instruction template) between users")
     ap.add_argument("--emulate-shard", default=None, metavar="R/W",
                     help="diagnostic: on ONE GPU, process the user slice rank R of W would get (no collective), e.g. 0/8")
     ap.add_argument("--hf-baseline-users", type=int, default=12,
@@ -358,6 +360,19 @@ def atspeed_arm(a, rank, world, local_rank):
         skw["max_users"] = a.cohort
         skw["cohort_tokens"] = a.cohort_tokens
     lanes = [Session(tdm, ddm, dtrie, a.K, a.N, 4, **skw) for _ in range(n_lanes)]
+    # the opening tokens every prompt of the dataset shares (the instruction template): their K/V is computed once per session
+    shared_prefix = 0
+    if a.cohort > 1 and not a.no_shared_prefix:
+        probe = [ds.prompt_ids(u) for u in range(0, ds.n_users, max(1, ds.n_users // 64))]
+        n_common = min(len(p) for p in probe) - 1
+        for p in probe[1:]:
+            k = 0
+            while k < n_common and p[k] == probe[0][k]:
+                k += 1
+            n_common = k
+        if n_common >= 8:
+            for ss in lanes:
+                shared_prefix = ss.set_shared_prefix(probe[0][:n_common])
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
     sess = lanes[0]
     from concurrent.futures import ThreadPoolExecutor
@@ -495,7 +510,8 @@ def atspeed_arm(a, rank, world, local_rank):
             "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (13.5 GB of weights streamed per forward)",
                        "inputs": "history item ids resident in HBM; prompts built on the device inside the timed region (cohort mode)",
                        "parallelism": f"user-sharded x{world}, one all-gather of ranked lists per step",
-                       "gemm_pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "1") != "0"},
+                       "gemm_pair_kernel": os.environ.get("ATSPEED_GEMM_2CTA", "1") != "0",
+                       "shared_prompt_prefix_tokens": shared_prefix},
             "clocks": clocks.summary(), "gpu_launches": int(launches),
             "accepted_tokens_per_verify": accept * a.K / max(1, runs)}
     STATE["partial"] = dict(base)          # what the watchdog prints if a later phase stalls

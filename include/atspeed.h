@@ -200,6 +200,10 @@ int atspeed_target_generate(atspeed_session* s, const int32_t* prompt_host, int3
  * `index` = position in the reference's flat [n_prev * V] space (sites 0,3,4,5) or the draft pick position (1,2).
  * A multinomial without replacement over p is the top-n of p / Exp(1) noise, as in ATen.
  * ---------------------------------------------------------------------------------------------- */
+/* Cohort sessions only (no reference counterpart): the n tokens every prompt of the coming atspeed_bssd_batch* calls starts
+ * with (the instruction template).  Their K/V rows are computed once, here, and copied into each user's caches on admission;
+ * the users' forwards then skip them.  A prompt that does not start with them makes atspeed_bssd_batch* fail.  n = 0: off. */
+int atspeed_session_set_shared_prefix(atspeed_session* s, const int32_t* prefix_host, int32_t n, void* stream);
 /* Re-key the session: the next atspeed_session_begin* uses (seed, user_seq), the one after (seed, user_seq + 1), ... */
 int atspeed_session_set_seed(atspeed_session* s, uint64_t seed, uint64_t user_seq);
 uint64_t atspeed_noise_stream(uint64_t user_seq, uint32_t round, uint32_t level, uint32_t site);

@@ -88,6 +88,32 @@ def test_cohort_matches_single_user_sessions(models, draft, kind, K, N, gamma, m
     assert same_accept >= 0.7 * len(users)
 
 
+def test_cohort_bf16_shared_prompt_prefix_agrees_with_plain_cohort(models):
+    """bf16: with the shared prefix the prefix rows come from a forward of a different size, which moves the GEMM's k-cuts exactly
+    as any batch-composition change does -- ranked lists must agree with the plain cohort run modulo numerical near-ties."""
+    ds, csr, single, cohort = _sessions(models, "correlated", "strict", 10, 40, 16)
+    users = list(range(0, 32))
+    prompts = [ds.prompt_ids(u) for u in users]
+    plain = cohort.bssd_batch(prompts, 3)
+    n = min(len(p) for p in prompts) - 1
+    for p in prompts[1:]:
+        k = 0
+        while k < n and p[k] == prompts[0][k]:
+            k += 1
+        n = k
+    assert cohort.set_shared_prefix(prompts[0][:n]) == n >= 8
+    shared = cohort.bssd_batch(prompts, 3)
+    exact = 0
+    for u, a, b in zip(users, plain, shared):
+        for row in b["tokens"]:
+            assert csr.walk([int(t) for t in row]) >= 0, f"user {u}: beam {row} is not an item of the constraint"
+        exact += int(a["tokens"].tolist() == b["tokens"].tolist())
+        assert len(set(map(tuple, b["tokens"].tolist())) & set(map(tuple, a["tokens"].tolist()))) >= 7, f"user {u}: lists share < 7 of 10 items"
+    print(f"shared prefix of {n} tokens vs plain cohort (bf16): {exact}/{len(users)} ranked lists identical")
+    assert exact >= 0.7 * len(users)
+    cohort.set_shared_prefix([])
+
+
 def test_cohort_relaxed_mode_runs_and_is_reproducible(models):
     ds, csr, single, cohort = _sessions(models, "correlated", "strict", 10, 40, 8, do_sample=True, top_k=50, temperature=1.0)
     prompts = [ds.prompt_ids(u) for u in range(12)]

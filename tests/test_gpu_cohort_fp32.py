@@ -79,6 +79,48 @@ def test_cohort_fp32_matches_reference_on_golden_users(fp32_models, ds_name, kin
     assert tally["exact"] >= 30 and tally["steps"] >= 30, dict(tally)
 
 
+def _common_prefix(prompts):
+    n = min(len(p) for p in prompts) - 1
+    for p in prompts[1:]:
+        k = 0
+        while k < n and p[k] == prompts[0][k]:
+            k += 1
+        n = k
+    return list(prompts[0][:n])
+
+
+@pytest.mark.parametrize("ds_name,kind", [("beauty", "strict"), ("games", "positional")])
+def test_cohort_fp32_with_shared_prompt_prefix_matches_reference(fp32_models, ds_name, kind):
+    """atspeed_session_set_shared_prefix: the K/V rows of the prompts' common opening tokens are computed once per session and
+    copied into every user's caches; the users' forwards skip those tokens.  In the fp32 parity mode nothing may change: ranked
+    lists, accepted lengths and n_run are still the reference's."""
+    cases = [c for c in golden("bssd_strict_users.json")["cases"] if c["dataset"] == ds_name and c["constraint"] == kind]
+    ds, sess = cohort_session(fp32_models, ds_name, kind, "correlated", 10, 40, 16)
+    prompts = [ds.prompt_ids(c["user"]) for c in cases]
+    prefix = _common_prefix(prompts)
+    assert len(prefix) >= 8, "the datasets' prompts share their instruction template"
+    assert sess.set_shared_prefix(prefix) == len(prefix)
+    got = sess.bssd_batch(prompts, 3)
+    tally = collections.Counter(rel=0.0)
+    for g, c in zip(got, cases):
+        check_against_golden(g, c, tally)
+    print(f"cohort fp32 {ds_name}/{kind} with a shared prefix of {len(prefix)} tokens: {tally['exact']}/32 ranked lists identical to "
+          f"the reference, {tally['steps']}/32 accepted-length sequences identical, max relative score error {tally['rel']:.2e}")
+    assert tally["rel"] < 1e-3
+    assert tally["exact"] >= 30 and tally["steps"] >= 30, dict(tally)
+    # a prompt that does not start with the prefix is refused, not silently mis-evaluated
+    from atspeed_b200._lib import AtSpeedError
+    bad = list(prompts[0])
+    bad[3] = bad[3] + 1 if bad[3] + 1 < ds.vocab_size else bad[3] - 1
+    with pytest.raises(AtSpeedError, match="shared"):
+        sess.bssd_batch([bad, prompts[1]], 3)
+    # and switching it off restores the plain path
+    assert sess.set_shared_prefix([]) == 0
+    again = sess.bssd_batch(prompts[:4], 3)
+    for g, c in zip(again, cases[:4]):
+        check_against_golden(g, c, collections.Counter(rel=0.0))
+
+
 def test_cohort_fp32_matches_reference_on_the_config_grid(fp32_models):
     """Every (dataset, constraint, draft, K, N, gamma) configuration of the hf_fp32 golden grid: its users as one cohort."""
     groups = collections.defaultdict(list)
