@@ -10,7 +10,7 @@
 // are streamed 64 at a time through a double-buffered cp.async ring, fragments come from ldmatrix (transposing for V),
 // flash-style online softmax in fp32, QK^T and PV on the warp-level tensor-core path (mma.sync m16n8k16 bf16; P is split
 // into hi+lo bf16 parts so the PV product is accurate to ~2^-16, the fp32-softmax contract of oracle/llama_ref.py).  The
-// accepted / tree slots are NOT run through dense tiles: a beam sees <= ~8 of them, so each query folds its visible slots
+// accepted / tree slots are NOT run through dense tiles: a beam sees <= ~11 of them, so each query folds its visible slots
 // in one by one (sparse phase, see the kernel).  Round 1 ran 64-key tiles over the tree region as well: 31 us per layer at
 // T = 300..512, latency-bound on > 95 % masked MMAs (profiles/r02_att_bench.txt).
 #include <stdlib.h>
@@ -70,10 +70,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 // Two phases per CTA (64 queries of one head, one user):
 //   dense  : keys [0, max prefix_len) -- the prompt, which every query of the block sees (causally for prompt tokens) --
 //            in 64-key tiles on the warp-level tensor-core path, flash-style online softmax;
-//   sparse : the accepted / tree slots behind the prompt.  A beam sees only its own ancestor chain there (<= ~8 of the
-//            ~170 slots), so a dense pass over those tiles would be > 95 % masked work: instead every query walks the set
-//            bits of its 512-bit visibility mask and folds each visible key into its running (max, sum, output) state with
-//            plain fp32 dot products -- two threads per query, each half of the head dimension.
+//   sparse : the accepted / tree slots behind the prompt.  A beam sees only its own ancestor chain there (<= ~11 of the
+//            ~170 slots), so a dense pass over those tiles would be > 95 % masked work: instead every row's visible slots are
+//            compacted into a short key list (before the dense phase, so their K/V lines can be prefetched into L2) and the
+//            lists are folded into the rows' running (max, sum, output) states with plain fp32 dot products, 4 lanes per
+//            row and 8 rows per warp at a time, K/V rows loaded two keys ahead.
 // The dense phase hands its per-row softmax state to the sparse phase through shared memory (the K/V ring is free by then).
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS)
