@@ -71,6 +71,46 @@ def run_users(search: Callable[[List[int]], Dict], prompts: Callable[[int], List
     return rec
 
 
+def common_prefix(prompts: Sequence[Sequence[int]], min_len: int = 8) -> List[int]:
+    """The opening tokens every prompt shares (the instruction template of the reference's prompts, code/data.py:232-263),
+    at most len(shortest prompt) - 1 of them; [] when fewer than `min_len` are shared."""
+    if not prompts:
+        return []
+    n = min(len(p) for p in prompts) - 1
+    first = prompts[0]
+    for p in prompts[1:]:
+        k = 0
+        while k < n and p[k] == first[k]:
+            k += 1
+        n = k
+    return list(first[:n]) if n >= min_len else []
+
+
+def run_users_cohort(session, prompts: Callable[[int], List[int]], users: Sequence[int], gamma: int, K: int, L: int,
+                     chunk: int = 256, share_prefix: bool = True) -> UserRecords:
+    """The same loop through a cohort session (`Session(max_users > 1)`): this rank's users go through
+    `session.bssd_batch` `chunk` at a time, their trees sharing forwards, and -- unless share_prefix is False -- the K/V of
+    the tokens all their prompts open with computed once (`session.set_shared_prefix`).  A user's latency is its chunk's
+    wall time divided by the chunk size (users of a cohort finish together)."""
+    rec = UserRecords.empty(len(users), K, L)
+    plist = [list(prompts(u)) for u in users]
+    if hasattr(session, "set_shared_prefix"):
+        session.set_shared_prefix(common_prefix(plist) if share_prefix else [])
+    for c0 in range(0, len(users), chunk):
+        t0 = time.perf_counter()
+        outs = session.bssd_batch(plist[c0:c0 + chunk], gamma)
+        dt = time.perf_counter() - t0
+        for j, out in enumerate(outs):
+            i = c0 + j
+            k = out["tokens"].shape[0]
+            rec.users[i] = users[i]
+            rec.items[i, :k] = out["tokens"][:, :L]
+            rec.scores[i, :k] = out["scores"]
+            rec.scores[i, k:] = -np.inf
+            rec.meta[i] = (out.get("n_run", 0), out.get("total_accept_steps", 0), int(dt * 1e6 / max(1, len(outs))), k)
+    return rec
+
+
 def gather_records(local: UserRecords, K: int, L: int, per_rank: int, device=None) -> UserRecords:
     """One all_gather of the padded per-rank record block; returns all users sorted by user index.
     Without an initialised process group (single process) this is the identity."""

@@ -363,13 +363,9 @@ def atspeed_arm(a, rank, world, local_rank):
     # the opening tokens every prompt of the dataset shares (the instruction template): their K/V is computed once per session
     shared_prefix = 0
     if a.cohort > 1 and not a.no_shared_prefix:
+        from atspeed_b200.runner import common_prefix
         probe = [ds.prompt_ids(u) for u in range(0, ds.n_users, max(1, ds.n_users // 64))]
-        n_common = min(len(p) for p in probe) - 1
-        for p in probe[1:]:
-            k = 0
-            while k < n_common and p[k] == probe[0][k]:
-                k += 1
-            n_common = k
+        n_common = len(common_prefix(probe))
         if n_common >= 8:
             for ss in lanes:
                 shared_prefix = ss.set_shared_prefix(probe[0][:n_common])

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from _common import ROOT, dataset, golden
 from atspeed_b200.metrics import computeTopNAccuracy
-from atspeed_b200.runner import UserRecords, evaluate, gather_records, run_users, shard_users
+from atspeed_b200.runner import UserRecords, common_prefix, evaluate, gather_records, run_users, run_users_cohort, shard_users
 
 
 def test_metric_known_answer_of_the_reference():
@@ -56,6 +56,43 @@ def test_shard_and_evaluate_single_process():
     rec.items[u, 0] = gt
     m2 = evaluate(ds, gather_records(rec, K, L, per_rank=40), [10])
     assert m2["recall"][0] > 0
+
+
+class _FakeCohortSession:
+    """Stands in for engine.Session(max_users > 1): same results as _fake_search, records how it was driven."""
+
+    def __init__(self, ds, K, L):
+        self.search, self.prefix, self.calls = _fake_search(ds, K, L), None, []
+
+    def set_shared_prefix(self, ids):
+        self.prefix = list(ids)
+        return len(ids)
+
+    def bssd_batch(self, prompts, gamma):
+        self.calls.append(len(prompts))
+        assert all(list(p[: len(self.prefix)]) == self.prefix for p in prompts), "a prompt does not start with the shared prefix"
+        return [self.search(p) for p in prompts]
+
+
+def test_cohort_runner_equals_the_per_user_loop_and_shares_the_template_prefix():
+    ds = dataset("beauty")
+    users = list(range(0, 90, 3))
+    K, L = 10, 4
+    one = run_users(_fake_search(ds, K, L), ds.prompt_ids, users, K, L)
+    sess = _FakeCohortSession(ds, K, L)
+    many = run_users_cohort(sess, ds.prompt_ids, users, 3, K, L, chunk=16)
+    assert sess.calls == [16, 14]
+    assert np.array_equal(one.users, many.users) and np.array_equal(one.items, many.items) and np.array_equal(one.scores, many.scores)
+    assert np.array_equal(one.meta[:, [0, 1, 3]], many.meta[:, [0, 1, 3]])
+    # the datasets' prompts open with the same instruction template (39 tokens on Beauty and Games): that is what gets shared
+    prompts = [ds.prompt_ids(u) for u in users]
+    pre = common_prefix(prompts)
+    assert sess.prefix == pre and len(pre) >= 8 and all(p[: len(pre)] == pre for p in prompts)
+    assert len(pre) < min(len(p) for p in prompts), "at least one prompt token is left for every user's own forward"
+    assert common_prefix([[1, 2, 3], [1, 2, 4]]) == [] and common_prefix([[5] * 12, [5] * 20], min_len=8) == [5] * 11
+    off = _FakeCohortSession(ds, K, L)
+    run_users_cohort(off, ds.prompt_ids, users[:5], 3, K, L, share_prefix=False)
+    assert off.prefix == []
 
 
 def _worker(rank, world, port, out_dir):
