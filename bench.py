@@ -360,15 +360,6 @@ def atspeed_arm(a, rank, world, local_rank):
         skw["max_users"] = a.cohort
         skw["cohort_tokens"] = a.cohort_tokens
     lanes = [Session(tdm, ddm, dtrie, a.K, a.N, 4, **skw) for _ in range(n_lanes)]
-    # the opening tokens every prompt of the dataset shares (the instruction template): their K/V is computed once per session
-    shared_prefix = 0
-    if a.cohort > 1 and not a.no_shared_prefix:
-        from atspeed_b200.runner import common_prefix
-        probe = [ds.prompt_ids(u) for u in range(0, ds.n_users, max(1, ds.n_users // 64))]
-        n_common = len(common_prefix(probe))
-        if n_common >= 8:
-            for ss in lanes:
-                shared_prefix = ss.set_shared_prefix(probe[0][:n_common])
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
     sess = lanes[0]
     from concurrent.futures import ThreadPoolExecutor
@@ -382,6 +373,14 @@ def atspeed_arm(a, rank, world, local_rank):
     step_users = [[mine[(s * U + i) % len(mine)] for i in range(U)] for s in range(n_steps_total)]
     prompts_host = {u: ds.prompt_ids(u) for us in step_users for u in us}
     prompts_dev = {u: torch.tensor(p, dtype=torch.int32, device=dev) for u, p in prompts_host.items()}
+    # the opening tokens every prompt of this run shares (the instruction template): their K/V is computed once per session
+    shared_prefix = 0
+    if a.cohort > 1 and not a.no_shared_prefix:
+        from atspeed_b200.runner import common_prefix
+        pre = common_prefix(list(prompts_host.values()))
+        if pre:
+            for ss in lanes:
+                shared_prefix = ss.set_shared_prefix(pre)
     tok_dev = torch.zeros(U, a.K, _lib.MAX_NEW, dtype=torch.int32, device=dev)
     sc_dev = torch.zeros(U, a.K, dtype=torch.float32, device=dev)
     gathered = [torch.zeros_like(tok_dev) for _ in range(world)] if world > 1 else None
