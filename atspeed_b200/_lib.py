@@ -47,6 +47,8 @@ SYMBOLS = {
     "atspeed_abi_version": (C.c_int, []),
     "atspeed_debug_gemm_trace": (C.c_int, [C.POINTER(C.c_uint32), C.c_int32]),
     "atspeed_debug_rowwise_us": (C.c_int, [C.c_int32] * 7 + [c_f32p, C.c_void_p]),
+    "atspeed_debug_plan_packs": (C.c_int, [c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p,
+                                           C.POINTER(C.c_uint8), c_i32p]),
     "atspeed_session_workspace_bytes": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(ModelDesc), C.POINTER(Config),
                                                   C.POINTER(C.c_size_t)]),
     "atspeed_session_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(ModelDesc), C.POINTER(Config),

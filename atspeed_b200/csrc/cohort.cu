@@ -95,6 +95,46 @@ void plan_target(const atspeed_session* s, const UserRun& u, UserCtx& x, int& S)
 
 namespace atspeed {
 
+// Packing of the target forwards of one scheduler step (pure host arithmetic; atspeed_debug_plan_packs exposes it to the CPU
+// tests).  A target forward's cost is dominated by how many forwards carry the tokens, so ready users are packed best-fit
+// decreasing: items sorted by token count (stable), every pack opened by the largest item left and filled with the largest
+// that still fit (tokens <= T_max, logit rows <= R_max, users <= max_users).  A pack that fills less than 7/8 of the forward
+// is held back one step -- the users launched now come back with small later-round trees (K + dl N tokens) that fill it --
+// unless deferral is off, no new user can arrive (no_more_work), one of its users has already waited twice, or nothing at
+// all would run (then the fullest pack runs).  order[k] = index of the k-th item in packing order; pack_of[i] = pack of item
+// i (packs numbered in the order they are opened); run_now[b] = 1 when pack b runs in this step.  Returns the pack count.
+int plan_packs(const PackItem* items, int n, int T_max, int R_max, int max_users, bool defer, bool no_more_work, int* order,
+               int* pack_of, unsigned char* run_now) {
+    for (int i = 0; i < n; ++i) { order[i] = i; pack_of[i] = -1; }
+    std::stable_sort(order, order + n, [&](int p, int q) { return items[p].T > items[q].T; });
+    int n_packs = 0;
+    std::vector<int> pack_T;
+    for (int first = 0; first < n; ++first) {
+        if (pack_of[order[first]] >= 0) continue;
+        int T = 0, R = 0, users = 0;
+        for (int k = first; k < n; ++k) {
+            const int i = order[k];
+            if (pack_of[i] >= 0) continue;
+            if (users == max_users || T + items[i].T > T_max || R + items[i].R > R_max) continue;
+            pack_of[i] = n_packs; T += items[i].T; R += items[i].R; ++users;
+        }
+        if (users == 0) { pack_of[order[first]] = n_packs; T = items[order[first]].T; }   // an item larger than a forward: the caller rejects it
+        pack_T.push_back(T);
+        ++n_packs;
+    }
+    const int full = T_max - T_max / 8;
+    int launched = 0, fullest = -1;
+    for (int b = 0; b < n_packs; ++b) {
+        bool aged = false;
+        for (int i = 0; i < n; ++i) aged = aged || (pack_of[i] == b && items[i].waited >= 2);
+        run_now[b] = (!defer || pack_T[b] >= full || no_more_work || aged) ? 1 : 0;
+        launched += run_now[b];
+        if (fullest < 0 || pack_T[b] > pack_T[fullest]) fullest = b;
+    }
+    if (launched == 0 && fullest >= 0) run_now[fullest] = 1;          // progress
+    return n_packs;
+}
+
 // run one packed forward of model `m` + kernel (a) + the per-user select / verify kernels
 static int run_pack(atspeed_session* s, ModelRT& m, const Pack& pk, const CohortKV& ckv, int B, bool has_verify,
                     bool has_select, cudaStream_t st) {
@@ -247,18 +287,16 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
             for (int a : pk.who) { act[a].j += 1; act[a].df += 1; }
         }
         // ---- target: verify forwards (dl >= 1) and final steps (dl == 0) of the users that are ready ----
-        // Packing: a target forward costs ~100 us + 0.19 us per token and layer at the 7B shape, so what matters is how FEW
-        // forwards carry the tokens.  Ready users are packed best-fit-decreasing (largest forward first, then the largest that
-        // still fit); a pack that fills less than 7/8 of the forward is held back one scheduler step -- the users launched now
-        // come back with small later-round trees (K + dl N tokens) that fill it -- unless nothing else would run, no new work
-        // can arrive, or one of its users has already waited twice.  Who shares a forward never changes a user's results.
+        // Packing: plan_packs (above) decides who shares a forward and which packs wait a step for a better fill.  Who shares a
+        // forward never changes a user's results.
         bool any_target = false;
         std::vector<Pack> packs;
         std::vector<CohortKV> pack_kv;
         std::vector<int> pack_flags;       // bit 0: has_verify, bit 1: has_select; max_dl in bits 8..
+        std::vector<unsigned char> run_now;
         {
-            struct Item { int a, T, R; };
-            std::vector<Item> items;
+            std::vector<int> who;          // index into act of every ready user
+            std::vector<PackItem> items;
             for (size_t a = 0; a < act.size(); ++a) {
                 UserRun& u = act[a];
                 if (u.finished || u.j < u.dl) continue;
@@ -266,57 +304,42 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
                 memset(&x, 0, sizeof(x));
                 int S = 0;
                 plan_target(s, u, x, S);
-                items.push_back(Item{static_cast<int>(a), x.T, x.R});
+                who.push_back(static_cast<int>(a));
+                items.push_back(PackItem{x.T, x.R, u.waited});
             }
-            std::stable_sort(items.begin(), items.end(), [](const Item& p, const Item& q) { return p.T > q.T; });
-            std::vector<char> used(items.size(), 0);
-            for (size_t first = 0; first < items.size(); ++first) {
-                if (used[first]) continue;
-                Pack pk;
-                memset(&pk.c, 0, sizeof(pk.c));
-                pk.T = pk.R = 0;
-                CohortKV ckv;
-                memset(&ckv, 0, sizeof(ckv));
-                int flags = 0, max_dl = 0;
-                for (size_t i = first; i < items.size(); ++i) {
-                    if (used[i]) continue;
-                    if (pk.c.n == MAX_USERS || pk.T + items[i].T > s->T_max || pk.R + items[i].R > s->R_max) continue;
-                    UserRun& u = act[items[i].a];
-                    UserCtx x;
-                    memset(&x, 0, sizeof(x));
-                    int S = 0;
-                    plan_target(s, u, x, S);
-                    x.tree = u.slot; x.P = u.P; x.tok0 = pk.T; x.row0 = pk.R;
-                    x.stream_base = noise_stream(u.user_seq, static_cast<uint32_t>(u.round), 0, 0);
-                    ckv_entry(ckv, pk.c.n, u, x, S, s->kv_user_elems_tgt);
-                    pk.c.u[pk.c.n++] = x;
-                    pk.T += x.T; pk.R += x.R;
-                    pk.who.push_back(items[i].a);
-                    if (x.mode == 2) { flags |= 1; max_dl = u.dl > max_dl ? u.dl : max_dl; } else flags |= 2;
-                    used[i] = 1;
-                }
-                ckv.n = pk.c.n;
-                packs.push_back(pk);
-                pack_kv.push_back(ckv);
-                pack_flags.push_back(flags | (max_dl << 8));
+            const int n = static_cast<int>(items.size());
+            std::vector<int> order(n), pack_of(n);
+            run_now.assign(n > 0 ? n : 1, 0);
+            const int n_packs = plan_packs(items.data(), n, s->T_max, s->R_max, MAX_USERS, pack_defer, next >= n_users, order.data(),
+                                           pack_of.data(), run_now.data());
+            packs.resize(n_packs);
+            pack_kv.resize(n_packs);
+            pack_flags.assign(n_packs, 0);
+            for (int b = 0; b < n_packs; ++b) {
+                memset(&packs[b].c, 0, sizeof(packs[b].c));
+                packs[b].T = packs[b].R = 0;
+                memset(&pack_kv[b], 0, sizeof(CohortKV));
             }
-        }
-        // which packs run now
-        std::vector<char> run_now(packs.size(), 0);
-        {
-            const bool no_more_work = next >= n_users;                   // nothing left to admit: waiting cannot fill a pack
-            const int full = s->T_max - s->T_max / 8;
-            int launched = 0, fullest = -1;
-            for (size_t b = 0; b < packs.size(); ++b) {
-                bool aged = false;
-                for (int a : packs[b].who) aged = aged || act[a].waited >= 2;
-                if (!pack_defer || packs[b].T >= full || no_more_work || aged) { run_now[b] = 1; ++launched; }
-                if (fullest < 0 || packs[b].T > packs[fullest].T) fullest = static_cast<int>(b);
+            for (int k = 0; k < n; ++k) {
+                const int i = order[k], b = pack_of[i];
+                Pack& pk = packs[b];
+                UserRun& u = act[who[i]];
+                UserCtx x;
+                memset(&x, 0, sizeof(x));
+                int S = 0;
+                plan_target(s, u, x, S);
+                x.tree = u.slot; x.P = u.P; x.tok0 = pk.T; x.row0 = pk.R;
+                x.stream_base = noise_stream(u.user_seq, static_cast<uint32_t>(u.round), 0, 0);
+                ckv_entry(pack_kv[b], pk.c.n, u, x, S, s->kv_user_elems_tgt);
+                pk.c.u[pk.c.n++] = x;
+                pk.T += x.T; pk.R += x.R;
+                pk.who.push_back(who[i]);
+                int max_dl = pack_flags[b] >> 8, flags = pack_flags[b] & 0xff;
+                if (x.mode == 2) { flags |= 1; max_dl = u.dl > max_dl ? u.dl : max_dl; } else flags |= 2;
+                pack_flags[b] = flags | (max_dl << 8);
+                pack_kv[b].n = pk.c.n;
+                u.waited = run_now[b] ? 0 : u.waited + 1;
             }
-            // progress: if every pack would wait and no draft step can change the picture, run the fullest one
-            if (launched == 0 && fullest >= 0) run_now[fullest] = 1;
-            for (size_t b = 0; b < packs.size(); ++b)
-                for (int a : packs[b].who) act[a].waited = run_now[b] ? 0 : act[a].waited + 1;
         }
         for (size_t pb = 0; pb < packs.size(); ++pb) {
             if (!run_now[pb]) continue;
@@ -424,6 +447,19 @@ static int bssd_batch_impl(atspeed_session* s, int32_t n_users, const int32_t* p
         const int per_user = static_cast<int>((s->launches - l0) / n_users);
         for (int i = 0; i < n_users; ++i) stats[i].kernel_launches = per_user;
     }
+    return ATS_OK;
+}
+
+// CPU-testable view of the scheduler's packing policy (tests/test_cohort_packing.py)
+extern "C" int atspeed_debug_plan_packs(const int32_t* T, const int32_t* R, const int32_t* waited, int32_t n, int32_t T_max,
+                                        int32_t R_max, int32_t defer, int32_t no_more_work, int32_t* pack_of, uint8_t* run_now,
+                                        int32_t* n_packs) {
+    ATS_CHECK_ARG(n >= 0 && n <= 4096 && (n == 0 || (T && R && waited && pack_of)) && run_now && n_packs && T_max >= 1 && R_max >= 1,
+                  "plan_packs: bad arguments");
+    std::vector<PackItem> items(n);
+    for (int i = 0; i < n; ++i) items[i] = PackItem{T[i], R[i], waited[i]};
+    std::vector<int> order(n);
+    *n_packs = plan_packs(items.data(), n, T_max, R_max, MAX_USERS, defer != 0, no_more_work != 0, order.data(), pack_of, run_now);
     return ATS_OK;
 }
 

@@ -135,6 +135,10 @@ SampleCfg sample_cfg(const atspeed_session* s);
 // one forward of `m` over the batch in `b`: T tokens, logits for the R rows listed in rows_idx; S = KV slots scanned by
 // attention (ignored in cohort forwards, where b.ckv carries it per user)
 int forward(atspeed_session* s, ModelRT& m, const BatchDesc& b, int T, int S, const int* rows_idx, int R, cudaStream_t st);
+// cohort.cu: packing of the target forwards of one scheduler step (see the definition)
+struct PackItem { int T, R, waited; };
+int plan_packs(const PackItem* items, int n, int T_max, int R_max, int max_users, bool defer, bool no_more_work, int* order,
+               int* pack_of, unsigned char* run_now);
 int run_topk(atspeed_session* s, ModelRT& m, int R, int B, const CandOut& o, cudaStream_t st);
 
 }  // namespace atspeed

@@ -44,6 +44,12 @@ int atspeed_abi_version(void);
  * (0 = tracing off).  Readable while a launch is stuck.  Every mbarrier wait of the library is bounded separately
  * (ATSPEED_SPIN_LIMIT_MS, default 4000): an expired wait traps and atspeed_last_error() names kernel/CTA/role/barrier. */
 int atspeed_debug_gemm_trace(uint32_t* out, int32_t max_words);
+/* Diagnostics / CPU tests: the cohort scheduler's packing of one step's target forwards.  Item i needs T[i] tokens and R[i]
+ * logit rows and has been held back waited[i] steps; pack_of[i] receives its pack (packs numbered in the order they are
+ * opened, best-fit decreasing), run_now[b] whether pack b runs in this step (>= 7/8 full, or deferral off, or no more work can
+ * arrive, or an item has waited twice, or nothing else would run), *n_packs the pack count.  Pure host arithmetic. */
+int atspeed_debug_plan_packs(const int32_t* T, const int32_t* R, const int32_t* waited, int32_t n, int32_t T_max, int32_t R_max,
+                             int32_t defer, int32_t no_more_work, int32_t* pack_of, uint8_t* run_now, int32_t* n_packs);
 /* Diagnostics: microseconds per launch of one row-wise consumer kernel of the forward (kind 0 RoPE + KV append, 1 SiLU * up,
  * 2 residual + RMSNorm) at T tokens with every output column held in `slices` fp32 partial-sum slices; inputs are cycled
  * through buffers larger than L2.  tools/rowwise_bench.py prints GB/s against MEASURED_PEAKS.json. */
