@@ -68,7 +68,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="atspeed", choices=["atspeed", "reference"])
-    ap.add_argument("--users-per-step", type=int, default=48)
+    ap.add_argument("--users-per-step", type=int, default=96)
     ap.add_argument("--cohort", type=int, default=16,
                     help="users whose trees share each forward (atspeed_bssd_batch; <= 512 tokens per forward); 1 = one "
                          "search per forward as the reference")
