@@ -452,19 +452,28 @@ extern "C" int atspeed_debug_rowwise_us(int32_t kind, int32_t T, int32_t hidden,
     sm.n = 1; sm.colbase[0] = 0; sm.colbase[1] = sm.colbase[2] = 0x7fffffff; sm.BM = 256; sm.U = 8; sm.KB = 8 * slices; sm.tps = 1;
     sm.bm_shift = 8; sm.tab_n = (cols + 255) / 256 <= SPLIT_TAB ? (cols + 255) / 256 : 0;
     for (int t = 0; t < sm.tab_n; ++t) sm.tab[t] = static_cast<unsigned char>(slices);
+    struct DevBufs {                      // freed on every return path
+        std::vector<void*> p;
+        ~DevBufs() { for (void* q : p) cudaFree(q); }
+        cudaError_t take(void** out, size_t bytes) {
+            cudaError_t e = cudaMalloc(out, bytes);
+            if (e == cudaSuccess) p.push_back(*out);
+            return e;
+        }
+    } bufs;
     float* part = nullptr; __nv_bfloat16 *h = nullptr, *x = nullptr, *g = nullptr, *q = nullptr, *kv = nullptr, *mm = nullptr;
     float* rope = nullptr; int* meta = nullptr;
     const int max_pos = 1024, S = T + 8;
-    ATS_CUDA(cudaMalloc(&part, part_bytes * nbuf));
+    ATS_CUDA(bufs.take(reinterpret_cast<void**>(&part), part_bytes * nbuf));
     ATS_CUDA(cudaMemsetAsync(part, 0, part_bytes * nbuf, st));
-    ATS_CUDA(cudaMalloc(&h, sizeof(__nv_bfloat16) * T * hidden * 2));
+    ATS_CUDA(bufs.take(reinterpret_cast<void**>(&h), sizeof(__nv_bfloat16) * T * hidden * 2));
     x = h + static_cast<long long>(T) * hidden;
-    ATS_CUDA(cudaMalloc(&g, sizeof(__nv_bfloat16) * hidden));
-    ATS_CUDA(cudaMalloc(&q, sizeof(__nv_bfloat16) * T * hidden));
-    ATS_CUDA(cudaMalloc(&kv, sizeof(__nv_bfloat16) * 2 * S * hidden));
-    ATS_CUDA(cudaMalloc(&mm, sizeof(__nv_bfloat16) * T * (mlp > 0 ? mlp : 1)));
-    ATS_CUDA(cudaMalloc(&rope, sizeof(float) * 2 * max_pos * (head_dim / 2)));
-    ATS_CUDA(cudaMalloc(&meta, sizeof(int) * 2 * T));
+    ATS_CUDA(bufs.take(reinterpret_cast<void**>(&g), sizeof(__nv_bfloat16) * hidden));
+    ATS_CUDA(bufs.take(reinterpret_cast<void**>(&q), sizeof(__nv_bfloat16) * T * hidden));
+    ATS_CUDA(bufs.take(reinterpret_cast<void**>(&kv), sizeof(__nv_bfloat16) * 2 * S * hidden));
+    ATS_CUDA(bufs.take(reinterpret_cast<void**>(&mm), sizeof(__nv_bfloat16) * T * (mlp > 0 ? mlp : 1)));
+    ATS_CUDA(bufs.take(reinterpret_cast<void**>(&rope), sizeof(float) * 2 * max_pos * (head_dim / 2)));
+    ATS_CUDA(bufs.take(reinterpret_cast<void**>(&meta), sizeof(int) * 2 * T));
     ATS_CUDA(cudaMemsetAsync(h, 0, sizeof(__nv_bfloat16) * T * hidden * 2, st));
     ATS_CUDA(cudaMemsetAsync(g, 0, sizeof(__nv_bfloat16) * hidden, st));
     ATS_CUDA(cudaMemsetAsync(rope, 0, sizeof(float) * 2 * max_pos * (head_dim / 2), st));
@@ -494,7 +503,6 @@ extern "C" int atspeed_debug_rowwise_us(int32_t kind, int32_t T, int32_t hidden,
     ATS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *us_out = ms * 1e3f / iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(part); cudaFree(h); cudaFree(g); cudaFree(q); cudaFree(kv); cudaFree(mm); cudaFree(rope); cudaFree(meta);
     return ATS_OK;
 }
 
